@@ -1,0 +1,250 @@
+/*
+ * bem_b200.h — C-ABI of libbem_b200.so, the sm_100a implementation of the Bayesian-Enhancement-Model
+ * hot path (SS2D selective scan + CrossScan/CrossMerge + reparameterised Bayesian layers + MC selection).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in `_host`
+ *   - no entry point allocates, synchronises or throws; each returns 0 or a cudaError_t / BEM_ERR_* code
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
+ *   - strides are in ELEMENTS and 64-bit (the reference's SSMParamsBase uses uint32 strides and overflows
+ *     at B*KD*L >= 2^32, kernels/selective_scan/csrc/selective_scan/selective_scan.h:27)
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference root).
+ */
+#ifndef BEM_B200_H_
+#define BEM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BEM_ABI_VERSION 1
+
+/* element types of u/delta/B/C/x-activations */
+enum { BEM_F32 = 0, BEM_F16 = 1, BEM_BF16 = 2 };
+
+/* error codes outside the cudaError_t range */
+enum {
+    BEM_OK = 0,
+    BEM_ERR_BAD_ARG = 10001,      /* shape/dtype/NULL contract violated                     */
+    BEM_ERR_WORKSPACE = 10002,    /* workspace missing or too small                          */
+    BEM_ERR_UNSUPPORTED = 10003   /* legal in the reference, not built here  */
+};
+
+int bem_abi_version(void);
+/* human-readable name for a return code (static storage) */
+const char* bem_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------------
+ * Selective scan, boundary form.
+ * Replaces selective_scan_cuda_oflex.fwd / .bwd
+ *   (kernels/selective_scan/csrc/selective_scan/cusoflex/selective_scan_oflex.cpp:157-243, 245-358)
+ * and the kernels behind them (cusoflex/selective_scan_fwd_kernel_oflex.cuh:67-211,
+ * cusoflex/selective_scan_bwd_kernel_oflex.cuh:73-322).
+ *
+ *   u, delta : (batch, dim, seqlen)           dtype `dtype`, last-dim stride 1
+ *   A        : (dim, dstate)                  fp32
+ *   B, C     : (batch, n_groups, dstate, seqlen)  dtype `dtype`, last-dim stride 1, dim % n_groups == 0
+ *   D, delta_bias : (dim) fp32 or NULL
+ *   out      : (batch, dim, seqlen)           fp32 (out_dtype == BEM_F32, the "oflex" mode) or `dtype`
+ *   x        : (batch, dim, n_chunks, 2*dstate) fp32 contiguous, n_chunks = ceil(seqlen / bem_scan_chunk_len(dtype)).
+ *              x[b,d,c,2n]   = prod_{t < end(c)} exp(delta_t A_n)   (running decay from t = 0)
+ *              x[b,d,c,2n+1] = h_n at the last position of chunk c   (the recurrence state)
+ *              so `last_state = x[:, :, -1, 1::2]` holds exactly as in
+ *              kernels/selective_scan/test_selective_scan.py:79. The reference fixes the chunk at 2048;
+ *              here the chunk length depends on the element type (the tensor is opaque to callers).
+ *   workspace: bem_scan_workspace_bytes() bytes, 16-byte aligned; contents are scratch (zeroed by the call)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct BemScanFwdParams {
+    int32_t batch, dim, seqlen, dstate, n_groups;
+    int32_t dtype;           /* BEM_F32 | BEM_F16 | BEM_BF16 */
+    int32_t out_dtype;       /* BEM_F32 or == dtype          */
+    int32_t delta_softplus;  /* 0 | 1                        */
+    const void* u;
+    const void* delta;
+    const float* A;
+    const void* B;
+    const void* C;
+    const float* D;          /* may be NULL */
+    const float* delta_bias; /* may be NULL */
+    void* out;
+    float* x;                /* may be NULL: carries are then not returned */
+    int64_t u_bs, u_ds;          /* batch / dim strides of u      */
+    int64_t delta_bs, delta_ds;
+    int64_t A_ds, A_ns;
+    int64_t B_bs, B_gs, B_ns;    /* batch / group / dstate strides */
+    int64_t C_bs, C_gs, C_ns;
+    int64_t out_bs, out_ds;
+    void* workspace;
+    int64_t workspace_bytes;
+} BemScanFwdParams;
+
+typedef struct BemScanBwdParams {
+    int32_t batch, dim, seqlen, dstate, n_groups;
+    int32_t dtype;           /* u/delta/B/C and du/ddelta */
+    int32_t dout_dtype;      /* BEM_F32 or == dtype       */
+    int32_t delta_softplus;
+    const void* u;
+    const void* delta;
+    const float* A;
+    const void* B;
+    const void* C;
+    const float* D;          /* may be NULL */
+    const float* delta_bias; /* may be NULL */
+    const void* dout;        /* (batch, dim, seqlen), last-dim stride 1 */
+    const float* x;          /* carries written by bem_scan_fwd; may be NULL iff n_chunks == 1 */
+    void* du;                /* (batch, dim, seqlen) dtype, contiguous rows */
+    void* ddelta;
+    float* dA;               /* (dim, dstate) fp32, ACCUMULATED INTO: caller zero-fills */
+    float* dB;               /* (batch, n_groups, dstate, seqlen) fp32 contiguous, accumulated into: caller zero-fills */
+    float* dC;
+    float* dD;               /* (dim) fp32 accumulated into, or NULL */
+    float* ddelta_bias;      /* (dim) fp32 accumulated into, or NULL */
+    int64_t u_bs, u_ds;
+    int64_t delta_bs, delta_ds;
+    int64_t A_ds, A_ns;
+    int64_t B_bs, B_gs, B_ns;
+    int64_t C_bs, C_gs, C_ns;
+    int64_t dout_bs, dout_ds;
+    int64_t du_bs, du_ds;
+    int64_t ddelta_bs, ddelta_ds;
+    void* workspace;
+    int64_t workspace_bytes;
+} BemScanBwdParams;
+
+/* positions per carry chunk for an element type (multiple of 32) */
+int bem_scan_chunk_len(int dtype);
+/* scratch bytes needed by bem_scan_fwd / bem_scan_bwd for these sizes */
+int64_t bem_scan_workspace_bytes(int batch, int dim, int seqlen, int dstate, int dtype);
+int bem_scan_fwd(const BemScanFwdParams* p, void* stream);
+int bem_scan_bwd(const BemScanBwdParams* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CrossScan / CrossMerge (four-direction traversal).
+ * Replaces triton_cross_scan_flex and its torch twin
+ *   (basicsr/vmamba/models/csm_triton.py:22-85 torch, :278-390 Triton, API :491-505).
+ *
+ * Image side  : one_by_one == 0 : (B, C, H, W)   or channel-last (B, H, W, C)
+ *               one_by_one == 1 : (B, 4, C, H, W) or channel-last (B, H, W, 4, C)
+ * Sequence side: (B, 4, C, L) or channel-last (B, L, 4, C), L = H*W
+ * scans: 0 = cross2d (k0 row-major, k1 column-major, k2 = flip k0, k3 = flip k1), 1 = unidirectional
+ *        (4 copies of k0), 2 = bidirectional (k0,k0,flip,flip)                 (csm_triton.py:25-34)
+ * bem_cross_scan  : image -> sequences (a copy)
+ * bem_cross_merge : sequences -> image; one_by_one == 0 sums the four directions (csm_triton.py:60-67)
+ * All tensors contiguous, same dtype.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct BemCsmParams {
+    int32_t B, C, H, W;
+    int32_t dtype;
+    int32_t img_channel_first;   /* layout of the image-side tensor    */
+    int32_t seq_channel_first;   /* layout of the sequence-side tensor */
+    int32_t one_by_one;
+    int32_t scans;               /* 0 | 1 | 2 */
+    const void* src;
+    void* dst;
+} BemCsmParams;
+int bem_cross_scan(const BemCsmParams* p, void* stream);
+int bem_cross_merge(const BemCsmParams* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused SS2D core: cross-scan gather + selective scan + cross-merge scatter in one pass.
+ * Replaces the chain cross_scan_fn -> selective_scan_fn -> cross_merge_fn inside SS2Dv2.forward_corev2
+ *   (basicsr/vmamba/models/vmamba.py:656-684), scan_mode "cross2d".
+ * x, and the per-direction projections are given in IMAGE order (x_proj/dt_proj are
+ * pointwise in l and commute with the traversal):
+ *   x     : (B, D, H, W)        dtype
+ *   dts   : (B, 4, D, H, W)     dtype   (delta before bias/softplus, direction k's projection at pixel (h,w))
+ *   Bs,Cs : (B, 4, N, H, W)     dtype
+ *   A     : (4*D, N) fp32; Dskip, delta_bias : (4*D) fp32 (may be NULL)
+ *   y     : (B, D, H, W)        fp32  = sum over the 4 directions, already un-traversed
+ * Implemented in terms of the traversal-aware loader of the scan kernel; see DESIGN.md.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct BemSs2dFwdParams {
+    int32_t batch, d_inner, H, W, dstate;
+    int32_t dtype;
+    int32_t delta_softplus;
+    const void* x;
+    const void* dts;
+    const void* Bs;
+    const void* Cs;
+    const float* A;
+    const float* Dskip;
+    const float* delta_bias;
+    float* y;
+    void* workspace;
+    int64_t workspace_bytes;
+} BemSs2dFwdParams;
+int64_t bem_ss2d_workspace_bytes(int batch, int d_inner, int H, int W, int dstate, int dtype);
+int bem_ss2d_fwd(const BemSs2dFwdParams* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Bayesian reparameterised layers.
+ * Replaces Conv2dReparameterization / Linear2dReparameterization / LinearReparameterization
+ *   (basicsr/bayesian/conv.py:91-128, basicsr/bayesian/linear.py:67-104, 165-203):
+ *     sigma = log1p(exp(rho)); w = mu + sigma * eps; out = conv(x, w, b)
+ *
+ * bem_bayes_sample : w[s, i] = mu[i] + log1p(exp(rho[i])) * eps[s, i]      (conv.py:106-107)
+ *     eps == NULL  -> eps is generated in-kernel: Philox4x32-10 keyed (seed, stream_id), counter
+ *                     (sample0 + s, i / 4), Box-Muller; element i takes lane i % 4.  The generator is restated in
+ *                     oracle/philox.py so the same eps can be fed to the reference layer.
+ *     eps_out != NULL -> the eps used is also written there (what the reference leaves in eps_weight).
+ * bem_bayes_pointwise : 1x1 convolution / Linear2d with per-sample weights
+ *     x : (S*Bx, Cin, P)  w : (S or 1, Cout, Cin)  bias : (S or 1, Cout) or NULL  out : (S*Bx, Cout, P), fp32
+ *     mu/rho/eps given instead of w  -> the sample step is fused into the weight load.
+ * bem_bayes_depthwise : depthwise KxK (groups == channels, stride 1, dilation 1, zero padding K/2), K in {3}
+ *     x : (S*Bx, C, H, W)  w : (S or 1, C, K, K)  bias : (S or 1, C) or NULL
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct BemBayesSampleParams {
+    int64_t numel;       /* elements of one weight tensor */
+    int32_t n_samples;   /* S */
+    const float* mu;
+    const float* rho;    /* NULL -> deterministic: w = mu (conv.py:118-128) */
+    const float* eps;    /* (S, numel) or NULL */
+    float* w;            /* (S, numel) */
+    float* eps_out;      /* (S, numel) or NULL */
+    uint64_t seed;
+    uint64_t stream_id;  /* layer / tensor id */
+    int64_t sample0;     /* global index of sample 0 of this call */
+} BemBayesSampleParams;
+int bem_bayes_sample(const BemBayesSampleParams* p, void* stream);
+
+typedef struct BemBayesPointwiseParams {
+    int32_t n_samples;   /* S: weight sets; 1 = shared weights */
+    int32_t batch;       /* total images = S * Bx */
+    int32_t cin, cout;
+    int64_t P;           /* pixels per image */
+    const float* x;
+    const float* w;      /* (S, cout, cin) or NULL when mu/rho/eps are given */
+    const float* mu;     /* (cout, cin) */
+    const float* rho;    /* (cout, cin) */
+    const float* eps;    /* (S, cout, cin) */
+    const float* bias;   /* (S, cout) or NULL */
+    float* out;
+} BemBayesPointwiseParams;
+int bem_bayes_pointwise(const BemBayesPointwiseParams* p, void* stream);
+
+typedef struct BemBayesDepthwiseParams {
+    int32_t n_samples;
+    int32_t batch;
+    int32_t C, H, W, K;
+    const float* x;
+    const float* w;      /* (S, C, K, K) */
+    const float* bias;   /* (S, C) or NULL */
+    float* out;
+} BemBayesDepthwiseParams;
+int bem_bayes_depthwise(const BemBayesDepthwiseParams* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Monte-Carlo best-sample selection.
+ * Replaces `_idx = one_clip_list.index(max(one_clip_list))` (Enhancement/eval.py:270-271; NIQE uses min, :273-274):
+ * first index attaining the extremum; NaN scores are never selected unless all are NaN (then index 0).
+ *   scores : (n) fp32;  out_index : int32[1];  out_value : fp32[1] or NULL
+ * ---------------------------------------------------------------------------------------------- */
+int bem_select_best(const float* scores, int32_t n, int32_t take_min, int32_t* out_index, float* out_value, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEM_B200_H_ */
