@@ -1,0 +1,141 @@
+"""ctypes binding of libbem_b200.so (include/bem_b200.h). The library is the product: if it is missing this module
+raises at import time — there is no Python / PyTorch / CPU fallback for any operator in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbem_b200.so")
+
+BEM_F32, BEM_F16, BEM_BF16 = 0, 1, 2
+BEM_OK, BEM_ERR_BAD_ARG, BEM_ERR_WORKSPACE, BEM_ERR_UNSUPPORTED = 0, 10001, 10002, 10003
+ABI_VERSION = 1
+
+i32, i64, u64, vp = C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
+
+
+class BemScanFwdParams(C.Structure):
+    _fields_ = [(n, i32) for n in ("batch", "dim", "seqlen", "dstate", "n_groups", "dtype", "out_dtype", "delta_softplus")] + \
+               [(n, vp) for n in ("u", "delta", "A", "B", "C", "D", "delta_bias", "out", "x")] + \
+               [(n, i64) for n in ("u_bs", "u_ds", "delta_bs", "delta_ds", "A_ds", "A_ns", "B_bs", "B_gs", "B_ns",
+                                   "C_bs", "C_gs", "C_ns", "out_bs", "out_ds")] + \
+               [("workspace", vp), ("workspace_bytes", i64)]
+
+
+class BemScanBwdParams(C.Structure):
+    _fields_ = [(n, i32) for n in ("batch", "dim", "seqlen", "dstate", "n_groups", "dtype", "dout_dtype", "delta_softplus")] + \
+               [(n, vp) for n in ("u", "delta", "A", "B", "C", "D", "delta_bias", "dout", "x", "du", "ddelta", "dA", "dB",
+                                  "dC", "dD", "ddelta_bias")] + \
+               [(n, i64) for n in ("u_bs", "u_ds", "delta_bs", "delta_ds", "A_ds", "A_ns", "B_bs", "B_gs", "B_ns",
+                                   "C_bs", "C_gs", "C_ns", "dout_bs", "dout_ds", "du_bs", "du_ds", "ddelta_bs", "ddelta_ds")] + \
+               [("workspace", vp), ("workspace_bytes", i64)]
+
+
+class BemCsmParams(C.Structure):
+    _fields_ = [(n, i32) for n in ("B", "C", "H", "W", "dtype", "img_channel_first", "seq_channel_first", "one_by_one",
+                                   "scans")] + [("src", vp), ("dst", vp)]
+
+
+class BemSs2dFwdParams(C.Structure):
+    _fields_ = [(n, i32) for n in ("batch", "d_inner", "H", "W", "dstate", "dtype", "delta_softplus")] + \
+               [(n, vp) for n in ("x", "dts", "Bs", "Cs", "A", "Dskip", "delta_bias", "y", "workspace")] + \
+               [("workspace_bytes", i64)]
+
+
+class BemBayesSampleParams(C.Structure):
+    _fields_ = [("numel", i64), ("n_samples", i32)] + [(n, vp) for n in ("mu", "rho", "eps", "w", "eps_out")] + \
+               [("seed", u64), ("stream_id", u64), ("sample0", i64)]
+
+
+class BemBayesPointwiseParams(C.Structure):
+    _fields_ = [(n, i32) for n in ("n_samples", "batch", "cin", "cout")] + [("P", i64)] + \
+               [(n, vp) for n in ("x", "w", "mu", "rho", "eps", "bias", "out")]
+
+
+class BemBayesDepthwiseParams(C.Structure):
+    _fields_ = [(n, i32) for n in ("n_samples", "batch", "C", "H", "W", "K")] + [(n, vp) for n in ("x", "w", "bias", "out")]
+
+
+# every symbol include/bem_b200.h declares: (restype, argtypes)
+SYMBOLS = {
+    "bem_abi_version": (C.c_int, []),
+    "bem_error_string": (C.c_char_p, [C.c_int]),
+    "bem_scan_chunk_len": (C.c_int, [C.c_int]),
+    "bem_scan_workspace_bytes": (i64, [C.c_int] * 5),
+    "bem_scan_fwd": (C.c_int, [C.POINTER(BemScanFwdParams), vp]),
+    "bem_scan_bwd": (C.c_int, [C.POINTER(BemScanBwdParams), vp]),
+    "bem_cross_scan": (C.c_int, [C.POINTER(BemCsmParams), vp]),
+    "bem_cross_merge": (C.c_int, [C.POINTER(BemCsmParams), vp]),
+    "bem_ss2d_workspace_bytes": (i64, [C.c_int] * 6),
+    "bem_ss2d_fwd": (C.c_int, [C.POINTER(BemSs2dFwdParams), vp]),
+    "bem_bayes_sample": (C.c_int, [C.POINTER(BemBayesSampleParams), vp]),
+    "bem_bayes_pointwise": (C.c_int, [C.POINTER(BemBayesPointwiseParams), vp]),
+    "bem_bayes_depthwise": (C.c_int, [C.POINTER(BemBayesDepthwiseParams), vp]),
+    "bem_select_best": (C.c_int, [vp, i32, i32, vp, vp, vp]),
+}
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python bayesian-enhancement-model_b200/build.py` "
+        "(nvcc, sm_100a). bem_b200 has no fallback implementation.")
+lib = C.CDLL(LIB_PATH)
+for _name, (_res, _args) in SYMBOLS.items():
+    _fn = getattr(lib, _name)      # AttributeError here = library/header mismatch: fail loudly
+    _fn.restype = _res
+    _fn.argtypes = _args
+if lib.bem_abi_version() != ABI_VERSION:
+    raise ImportError(f"libbem_b200.so ABI {lib.bem_abi_version()} != binding ABI {ABI_VERSION}: rebuild the library")
+
+_DT = {torch.float32: BEM_F32, torch.float16: BEM_F16, torch.bfloat16: BEM_BF16}
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DT[dt]
+    except KeyError:
+        raise RuntimeError(f"bem_b200: unsupported dtype {dt} (float32 / float16 / bfloat16 only)")
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def check(code: int, what: str):
+    if code != 0:
+        raise RuntimeError(f"bem_b200.{what} failed: {lib.bem_error_string(code).decode()} (code {code})")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("bem_b200 operators run on CUDA tensors only (sm_100a kernels; there is no CPU fallback)")
+
+
+_workspaces: dict = {}
+
+
+def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Scratch for the scan look-back descriptors, cached per (device, stream): launches on one stream are ordered,
+    so they may share it; different streams get their own."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def scan_error_word(device: torch.device) -> int:
+    """Watchdog word of the last scan launch on the current stream (0 = clean). Synchronises; tests only."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None:
+        return 0
+    return int(ws[4:8].view(torch.int32).item())

@@ -1,0 +1,179 @@
+"""Kernel wrappers + autograd for the Bayesian layers (csrc/bayes.cu).
+
+sample_weights      w[s] = mu + log1p(exp(rho)) * eps[s]          (basicsr/bayesian/conv.py:106-107)
+pointwise_conv      S-batched 1x1 convolution with per-sample weights (conv.py:114 / linear.py:90 for 1x1 shapes)
+depthwise_conv3x3   S-batched depthwise 3x3 (conv.py:114 with groups == channels)
+
+Forward passes run the hand-written kernels. Backward passes (stage-1 training only) reuse the same kernels for the
+data gradients; the tiny weight-gradient reductions use torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from .. import _lib
+from .._lib import lib
+
+
+def _f32c(t, name):
+    if t is None:
+        return None
+    _lib.require_cuda(t)
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"bem_b200.bayesian: {name} must be float32 (got {t.dtype})")
+    return t.contiguous()
+
+
+def _sample_raw(mu, rho, eps, n_samples, seed, stream_id, sample0, want_eps):
+    mu = _f32c(mu, "mu")
+    rho = _f32c(rho, "rho")
+    eps = _f32c(eps, "eps")
+    numel = mu.numel()
+    if eps is not None and eps.numel() != n_samples * numel:
+        raise RuntimeError(f"eps has {eps.numel()} elements, expected n_samples * numel = {n_samples * numel}")
+    w = torch.empty((n_samples,) + tuple(mu.shape), dtype=torch.float32, device=mu.device)
+    eps_out = torch.empty_like(w) if (want_eps and eps is None and rho is not None) else None
+    p = _lib.BemBayesSampleParams(numel=numel, n_samples=n_samples, mu=_lib.ptr(mu), rho=_lib.ptr(rho), eps=_lib.ptr(eps),
+                                  w=_lib.ptr(w), eps_out=_lib.ptr(eps_out), seed=int(seed) & (2 ** 64 - 1),
+                                  stream_id=int(stream_id), sample0=int(sample0))
+    with torch.cuda.device(mu.device):
+        _lib.check(lib.bem_bayes_sample(C.byref(p), _lib.stream_ptr(mu.device)), "bayes_sample")
+    used = eps.view_as(w) if eps is not None else eps_out
+    return w, used
+
+
+class _SampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, rho, eps, n_samples, seed, stream_id, sample0):
+        w, used = _sample_raw(mu, rho, eps, n_samples, seed, stream_id, sample0, want_eps=True)
+        ctx.save_for_backward(rho, used)
+        ctx.mark_non_differentiable(used)
+        return w, used
+
+    @staticmethod
+    def backward(ctx, dw, _deps):
+        rho, eps = ctx.saved_tensors
+        dmu = dw.sum(0)
+        drho = (dw * eps).sum(0) * torch.sigmoid(rho)   # d log1p(exp(rho)) / d rho
+        return dmu, drho, None, None, None, None, None
+
+
+def sample_weights(mu, rho, eps=None, n_samples=1, seed=0, stream_id=0, sample0=0):
+    """-> (w, eps_used); w: (S, *mu.shape). eps=None draws the counter-based Philox stream inside the kernel
+    (keyed (seed, stream_id, sample0 + s): independent of how samples are split over ranks)."""
+    if torch.is_grad_enabled() and (mu.requires_grad or rho.requires_grad):
+        return _SampleFn.apply(mu, rho, eps, n_samples, seed, stream_id, sample0)
+    return _sample_raw(mu, rho, eps, n_samples, seed, stream_id, sample0, want_eps=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def _pointwise_raw(x, w=None, bias=None, mu=None, rho=None, eps=None, n_samples=1):
+    """x: (S*Bx, Cin, *spatial) fp32; w: (S|1, Cout, Cin) or mu/rho/eps for the fused sample-on-load path."""
+    x = _f32c(x, "input")
+    w, bias, mu, rho, eps = (_f32c(t, n) for t, n in ((w, "w"), (bias, "bias"), (mu, "mu"), (rho, "rho"), (eps, "eps")))
+    ref = w if w is not None else mu
+    cout, cin = int(ref.shape[-2]), int(ref.shape[-1])
+    if x.dim() < 3 or x.shape[1] != cin:
+        raise RuntimeError(f"pointwise conv: input {tuple(x.shape)} does not match weight (.., {cout}, {cin})")
+    batch = x.shape[0]
+    P = x[0, 0].numel()
+    out = torch.empty((batch, cout) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+    p = _lib.BemBayesPointwiseParams(n_samples=n_samples, batch=batch, cin=cin, cout=cout, P=P, x=_lib.ptr(x),
+                                     w=_lib.ptr(w), mu=_lib.ptr(mu), rho=_lib.ptr(rho), eps=_lib.ptr(eps),
+                                     bias=_lib.ptr(bias), out=_lib.ptr(out))
+    with torch.cuda.device(x.device):
+        _lib.check(lib.bem_bayes_pointwise(C.byref(p), _lib.stream_ptr(x.device)), "bayes_pointwise")
+    return out
+
+
+class _PointwiseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, n_samples):
+        ctx.save_for_backward(x, w)
+        ctx.n_samples = n_samples
+        ctx.has_bias = bias is not None
+        return _pointwise_raw(x, w=w, bias=bias, n_samples=n_samples)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        S = ctx.n_samples
+        dout = dout.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _pointwise_raw(dout, w=w.transpose(-1, -2).contiguous(), n_samples=S)   # W^T dout with the same kernel
+        if ctx.needs_input_grad[1] or ctx.has_bias:
+            Bx = x.shape[0] // S
+            xs = x.reshape(S, Bx, x.shape[1], -1)
+            ds = dout.reshape(S, Bx, dout.shape[1], -1)
+            if ctx.needs_input_grad[1]:
+                dw = torch.einsum("sbop,sbip->soi", ds, xs).reshape(w.shape) if w.shape[0] == S else \
+                    torch.einsum("sbop,sbip->oi", ds, xs).reshape(w.shape)
+            if ctx.has_bias:
+                db = ds.sum(dim=(1, 3))
+        return dx, dw, db, None
+
+
+def pointwise_conv(x, w, bias=None, n_samples=1):
+    """out[img] = w[s(img)] @ x[img] + bias[s(img)]; w: (S, Cout, Cin), bias: (S, Cout) | None."""
+    if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or (bias is not None and bias.requires_grad)):
+        return _PointwiseFn.apply(x, w, bias, n_samples)
+    return _pointwise_raw(x, w=w, bias=bias, n_samples=n_samples)
+
+
+def pointwise_conv_sampled(x, mu, rho, eps, bias=None, n_samples=1):
+    """inference path: w = mu + softplus(rho) * eps is formed while the weight tile is loaded (never stored)."""
+    return _pointwise_raw(x, mu=mu, rho=rho, eps=eps, bias=bias, n_samples=n_samples)
+
+
+# ---------------------------------------------------------------------------------------------------
+def _depthwise_raw(x, w, bias, n_samples):
+    x = _f32c(x, "input")
+    w = _f32c(w, "w")
+    bias = _f32c(bias, "bias")
+    batch, Cc, H, W = x.shape
+    K = int(w.shape[-1])
+    out = torch.empty_like(x)
+    p = _lib.BemBayesDepthwiseParams(n_samples=n_samples, batch=batch, C=Cc, H=H, W=W, K=K, x=_lib.ptr(x), w=_lib.ptr(w),
+                                     bias=_lib.ptr(bias), out=_lib.ptr(out))
+    with torch.cuda.device(x.device):
+        _lib.check(lib.bem_bayes_depthwise(C.byref(p), _lib.stream_ptr(x.device)), "bayes_depthwise")
+    return out
+
+
+class _DepthwiseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, n_samples):
+        ctx.save_for_backward(x, w)
+        ctx.n_samples = n_samples
+        ctx.has_bias = bias is not None
+        return _depthwise_raw(x, w, bias, n_samples)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        S = ctx.n_samples
+        dout = dout.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _depthwise_raw(dout, torch.flip(w, dims=(-1, -2)).contiguous(), None, S)   # correlation with the flipped taps
+        if ctx.needs_input_grad[1]:
+            Bx = x.shape[0] // S
+            Cc, H, W = x.shape[1:]
+            xp = torch.nn.functional.pad(x, (1, 1, 1, 1)).reshape(S, Bx, Cc, H + 2, W + 2)
+            ds = dout.reshape(S, Bx, Cc, H, W)
+            taps = [(ds * xp[..., i:i + H, j:j + W]).sum(dim=(1, 3, 4)) for i in range(3) for j in range(3)]
+            dw = torch.stack(taps, dim=-1).reshape(S, Cc, 3, 3)
+            dw = dw.reshape(w.shape) if w.shape[0] == S else dw.sum(0).reshape(w.shape)
+        if ctx.has_bias:
+            db = dout.reshape(S, -1, dout.shape[1], dout.shape[2] * dout.shape[3]).sum(dim=(1, 3))
+        return dx, dw, db, None
+
+
+def depthwise_conv3x3(x, w, bias=None, n_samples=1):
+    """x: (S*Bx, C, H, W); w: (S, C, 3, 3) (or (S, C, 1, 3, 3)); bias: (S, C) | None; stride 1, zero padding 1."""
+    if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or (bias is not None and bias.requires_grad)):
+        return _DepthwiseFn.apply(x, w, bias, n_samples)
+    return _depthwise_raw(x, w, bias, n_samples)

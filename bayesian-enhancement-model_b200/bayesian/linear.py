@@ -1,0 +1,89 @@
+"""Linear2dReparameterization / LinearReparameterization — drop-ins for basicsr/bayesian/linear.py:8-104, 106-203."""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn import Parameter
+
+from . import functional as BF
+from .base_layer import BaseLayer_
+
+
+class _LinearBase(BaseLayer_):
+    def __init__(self, in_features, out_features, bias=True, sigma_init=0.05, decay=0.9998):
+        super().__init__()
+        self.deterministic = False   # set to True to get deterministic output
+        self.in_features = in_features
+        self.out_features = out_features
+        self.bias = bias
+        self.decay = decay
+        self.sigma_init = sigma_init
+        self.step = 0
+        self.mu_weight = Parameter(torch.Tensor(out_features, in_features))
+        self.rho_weight = Parameter(torch.Tensor(out_features, in_features))
+        self.register_buffer('eps_weight', torch.Tensor(out_features, in_features), persistent=False)
+        self.register_buffer('prior_mu_weight', torch.Tensor(out_features, in_features), persistent=False)
+        self.register_buffer('prior_rho_weight', torch.Tensor(out_features, in_features), persistent=False)
+        if bias:
+            self.mu_bias = Parameter(torch.Tensor(out_features))
+            self.rho_bias = Parameter(torch.Tensor(out_features))
+            self.register_buffer('eps_bias', torch.Tensor(out_features), persistent=False)
+            self.register_buffer('prior_mu_bias', torch.Tensor(out_features), persistent=False)
+            self.register_buffer('prior_rho_bias', torch.Tensor(out_features), persistent=False)
+        self.init_parameters()
+
+    def init_parameters(self):
+        rho_init = math.log(math.expm1(abs(self.sigma_init)) + 1e-20)
+        nn.init.xavier_uniform_(self.mu_weight)
+        self.rho_weight.data.fill_(rho_init)
+        self.prior_mu_weight.data.copy_(self.mu_weight.data)
+        self.prior_rho_weight.data.copy_(self.rho_weight.data)
+        if self.bias:
+            self.mu_bias.data.fill_(0)
+            self.rho_bias.data.fill_(rho_init)
+            self.prior_mu_bias.data.copy_(self.mu_bias.data)
+            self.prior_rho_bias.data.copy_(self.rho_bias.data)
+
+
+class Linear2dReparameterization(_LinearBase):
+    """1x1 convolution over (B, C, H, W) with a sampled (out, in) weight (linear.py:8-104) -> bem_bayes_pointwise."""
+
+    def _forward_uncertain(self, input, eps_weight=None, eps_bias=None):
+        if self.training:
+            self._update_prior()
+        S = self.mc_samples
+        needs_grad = torch.is_grad_enabled() and (self.mu_weight.requires_grad or input.requires_grad)
+        if (not needs_grad) and (self.eps_source == "torch" or eps_weight is not None):
+            eps_w = self._draw_eps("weight", eps_weight)
+            b = self._sample("bias", eps_bias)[0] if self.bias else None
+            return BF.pointwise_conv_sampled(input, self.mu_weight, self.rho_weight, eps_w, b, S)
+        w, _ = self._sample("weight", eps_weight)
+        b = self._sample("bias", eps_bias)[0] if self.bias else None
+        return BF.pointwise_conv(input, w, b, S)
+
+    def _forward_det(self, input):
+        return BF.pointwise_conv(input, self.mu_weight.unsqueeze(0), self.mu_bias.unsqueeze(0) if self.bias else None, 1)
+
+
+class LinearReparameterization(_LinearBase):
+    """F.linear on the last axis with a sampled weight (linear.py:106-203). No shipped arch instantiates it
+    (channel_first=True everywhere): the sample step runs on bem_bayes_sample, the contraction is the
+    library GEMM."""
+
+    def _forward_uncertain(self, input, eps_weight=None, eps_bias=None):
+        if self.training:
+            self._update_prior()
+        S = self.mc_samples
+        w, _ = self._sample("weight", eps_weight)
+        b = self._sample("bias", eps_bias)[0] if self.bias else None
+        if S == 1:
+            return F.linear(input, w[0], None if b is None else b[0])
+        xs = input.reshape(S, -1, self.in_features)
+        out = torch.baddbmm(b.unsqueeze(1), xs, w.transpose(1, 2)) if b is not None else torch.bmm(xs, w.transpose(1, 2))
+        return out.reshape(*input.shape[:-1], self.out_features)
+
+    def _forward_det(self, input):
+        return F.linear(input, self.mu_weight, self.mu_bias if self.bias else None)

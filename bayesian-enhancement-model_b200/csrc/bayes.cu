@@ -1,0 +1,262 @@
+// bayes.cu — reparameterised Bayesian layers for sm_100a.
+//
+// Replaces the eager chain of Conv2dReparameterization / Linear2dReparameterization._forward_uncertain
+// (basicsr/bayesian/conv.py:106-114, linear.py:82-90): sigma = log1p(exp(rho)), eps.normal_(), w = mu + sigma * eps
+// (4-6 tiny elementwise launches per layer per sample) followed by a library convolution.
+//   bem_bayes_sample     one launch for all S samples of a tensor; eps either given (parity with the reference) or
+//                        generated in-kernel by a counter-based Philox4x32-10 + Box-Muller stream keyed
+//                        (seed, tensor id, sample) so that results do not depend on how samples are sharded over GPUs
+//   bem_bayes_pointwise  S-batched 1x1 convolution, per-sample weights; with mu/rho/eps given the sample step is fused
+//                        into the weight-tile load (the sampled weights never exist in HBM)
+//   bem_bayes_depthwise  S-batched depthwise 3x3, per-sample weights
+// This file holds the fp32 CUDA-core kernels (bit-faithful fp32 accumulate: the 1e-5 parity tier);
+// the tcgen05 tensor-core variant of the pointwise contraction lives in bayes_tc.cu.
+#include "bem_kernels.h"
+
+namespace bem {
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), restated in oracle/philox.py
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+// 4 standard normals from one Philox block: Box-Muller on (x0,x1) and (x2,x3); u = (x >> 8 + 0.5) * 2^-24 in (0,1)
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t stream_id, uint64_t sample, uint64_t block, float (&n)[4]) {
+    const uint4 ctr = make_uint4((uint32_t)block, (uint32_t)(block >> 32), (uint32_t)sample, (uint32_t)stream_id);
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint4 r = philox4x32_10(ctr, key);
+    const float k = 5.9604644775390625e-08f;   // 2^-24
+    const float u0 = ((float)(r.x >> 8) + 0.5f) * k, u1 = ((float)(r.y >> 8) + 0.5f) * k;
+    const float u2 = ((float)(r.z >> 8) + 0.5f) * k, u3 = ((float)(r.w >> 8) + 0.5f) * k;
+    const float ra = sqrtf(-2.f * logf(u0)), rb = sqrtf(-2.f * logf(u2));
+    const float ta = 6.283185307179586f * u1, tb = 6.283185307179586f * u3;
+    n[0] = ra * cosf(ta);
+    n[1] = ra * sinf(ta);
+    n[2] = rb * cosf(tb);
+    n[3] = rb * sinf(tb);
+}
+
+__device__ __forceinline__ float sigma_of_rho(float rho) { return log1pf(expf(rho)); }   // conv.py:106
+
+__global__ void __launch_bounds__(256) bayes_sample_kernel(const BemBayesSampleParams p) {
+    const int64_t nblk = (p.numel + 3) / 4;
+    const int64_t total = nblk * p.n_samples;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = t / nblk, blk = t - s * nblk;
+        float e[4];
+        if (p.rho && !p.eps) philox_normal4(p.seed, p.stream_id, (uint64_t)(p.sample0 + s), (uint64_t)blk, e);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t i = blk * 4 + k;
+            if (i >= p.numel) break;
+            float w = p.mu[i];
+            if (p.rho) {
+                const float ev = p.eps ? p.eps[s * p.numel + i] : e[k];
+                w = fmaf(sigma_of_rho(p.rho[i]), ev, w);
+                if (p.eps_out) p.eps_out[s * p.numel + i] = ev;
+            }
+            p.w[s * p.numel + i] = w;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// S-batched pointwise (1x1) convolution, fp32 CUDA-core tiles.
+//   out[img, co, p] = sum_ci W[s(img)][co][ci] * x[img][ci][p] + bias[s(img)][co]
+// CTA tile: 64 output channels x 256 pixels, K step 16. 256 threads as (32 pixel lanes) x (8 channel groups):
+// each thread owns 8 channels x 8 pixels. Weight reads are warp-broadcasts, x reads conflict-free LDS.128.
+// ------------------------------------------------------------------------------------------------
+constexpr int PW_BM = 64, PW_BN = 256, PW_BK = 16;
+
+__global__ void __launch_bounds__(256) bayes_pointwise_kernel(const BemBayesPointwiseParams p) {
+    __shared__ __align__(16) float sW[PW_BK][PW_BM + 4];   // +4: the transposing store is 2-way instead of 16-way conflicted
+    __shared__ __align__(16) float sX[PW_BK][PW_BN];
+    const int img = blockIdx.z;
+    const int imgs_per_sample = p.batch / p.n_samples;
+    const int s = p.n_samples > 1 ? img / imgs_per_sample : 0;
+    const int co0 = blockIdx.y * PW_BM;
+    const int64_t p0 = (int64_t)blockIdx.x * PW_BN;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const float* x = p.x + (int64_t)img * p.cin * p.P;
+    const int64_t wofs = (int64_t)s * p.cout * p.cin;
+    const bool vec_ok = (p.P % 4 == 0);
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < p.cin; k0 += PW_BK) {
+        // weight tile (sampled on load when mu/rho/eps are given)
+#pragma unroll
+        for (int r = 0; r < (PW_BM * PW_BK) / 256; ++r) {
+            const int idx = tid + r * 256;
+            const int kk = idx % PW_BK, m = idx / PW_BK;   // consecutive threads walk ci: coalesced over a weight row
+            const int co = co0 + m, ci = k0 + kk;
+            float w = 0.f;
+            if (co < p.cout && ci < p.cin) {
+                const int64_t wi = (int64_t)co * p.cin + ci;
+                if (p.w) w = p.w[wofs + wi];
+                else {
+                    w = p.mu[wi];
+                    if (p.rho) w = fmaf(sigma_of_rho(p.rho[wi]), p.eps[wofs + wi], w);
+                }
+            }
+            sW[kk][m] = w;
+        }
+        // activation tile
+#pragma unroll
+        for (int r = 0; r < (PW_BK * PW_BN / 4) / 256; ++r) {
+            const int idx = tid + r * 256;
+            const int kk = idx / (PW_BN / 4), c4 = idx % (PW_BN / 4);
+            const int ci = k0 + kk;
+            const int64_t pp = p0 + c4 * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ci < p.cin) {
+                const float* src = x + (int64_t)ci * p.P + pp;
+                if (vec_ok && pp + 3 < p.P) v = *reinterpret_cast<const float4*>(src);
+                else {
+                    if (pp + 0 < p.P) v.x = src[0];
+                    if (pp + 1 < p.P) v.y = src[1];
+                    if (pp + 2 < p.P) v.z = src[2];
+                    if (pp + 3 < p.P) v.w = src[3];
+                }
+            }
+            *reinterpret_cast<float4*>(&sX[kk][c4 * 4]) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < PW_BK; ++kk) {
+            const float4 wa = *reinterpret_cast<const float4*>(&sW[kk][ty * 8]);
+            const float4 wb = *reinterpret_cast<const float4*>(&sW[kk][ty * 8 + 4]);
+            const float4 xa = *reinterpret_cast<const float4*>(&sX[kk][tx * 4]);
+            const float4 xb = *reinterpret_cast<const float4*>(&sX[kk][128 + tx * 4]);
+            const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* out = p.out + (int64_t)img * p.cout * p.P;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int co = co0 + ty * 8 + i;
+        if (co >= p.cout) continue;
+        const float b = p.bias ? p.bias[(int64_t)s * p.cout + co] : 0.f;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int64_t pp = p0 + half * 128 + tx * 4;
+            float* dst = out + (int64_t)co * p.P + pp;
+            const float4 v = make_float4(acc[i][half * 4 + 0] + b, acc[i][half * 4 + 1] + b, acc[i][half * 4 + 2] + b,
+                                         acc[i][half * 4 + 3] + b);
+            if (vec_ok && pp + 3 < p.P) *reinterpret_cast<float4*>(dst) = v;
+            else {
+                if (pp + 0 < p.P) dst[0] = v.x;
+                if (pp + 1 < p.P) dst[1] = v.y;
+                if (pp + 2 < p.P) dst[2] = v.z;
+                if (pp + 3 < p.P) dst[3] = v.w;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// S-batched depthwise 3x3 (stride 1, zero padding 1). One thread: 4 consecutive output pixels of one row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bayes_depthwise3_kernel(const BemBayesDepthwiseParams p) {
+    const int W4 = (p.W + 3) / 4;
+    const int64_t per_plane = (int64_t)p.H * W4;
+    const int plane = blockIdx.x;   // img * C + c
+    const int img = plane / p.C, c = plane - img * p.C;
+    const int imgs_per_sample = p.batch / p.n_samples;
+    const int s = p.n_samples > 1 ? img / imgs_per_sample : 0;
+    const float* wp = p.w + ((int64_t)s * p.C + c) * 9;
+    float w[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) w[i] = wp[i];
+    const float b = p.bias ? p.bias[(int64_t)s * p.C + c] : 0.f;
+    const float* x = p.x + (int64_t)plane * p.H * p.W;
+    float* out = p.out + (int64_t)plane * p.H * p.W;
+    for (int64_t t = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; t < per_plane; t += (int64_t)gridDim.y * blockDim.x) {
+        const int h = (int)(t / W4), w0 = (int)(t - (int64_t)h * W4) * 4;
+        float acc[4] = {b, b, b, b};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int hh = h + i - 1;
+            if (hh < 0 || hh >= p.H) continue;
+            const float* row = x + (int64_t)hh * p.W;
+            float v[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const int ww = w0 + j - 1;
+                v[j] = (ww >= 0 && ww < p.W) ? __ldg(row + ww) : 0.f;
+            }
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) acc[o] = fmaf(w[i * 3 + j], v[o + j], acc[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+            if (w0 + o < p.W) out[(int64_t)h * p.W + w0 + o] = acc[o];
+    }
+}
+
+}  // namespace bem
+
+using namespace bem;
+
+extern "C" {
+
+int bem_bayes_sample(const BemBayesSampleParams* p, void* stream) {
+    if (!p || !p->mu || !p->w || p->numel <= 0 || p->n_samples <= 0) return BEM_ERR_BAD_ARG;
+    const int64_t total = (p->numel + 3) / 4 * p->n_samples;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)device_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    bayes_sample_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+    return (int)cudaGetLastError();
+}
+
+int bem_bayes_pointwise(const BemBayesPointwiseParams* p, void* stream) {
+    if (!p || !p->x || !p->out || p->n_samples <= 0 || p->batch <= 0 || p->cin <= 0 || p->cout <= 0 || p->P <= 0)
+        return BEM_ERR_BAD_ARG;
+    if (p->batch % p->n_samples != 0) return BEM_ERR_BAD_ARG;
+    if (!p->w && !p->mu) return BEM_ERR_BAD_ARG;
+    if (!p->w && p->rho && !p->eps) return BEM_ERR_BAD_ARG;
+    if (p->batch > 65535) return BEM_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)((p->P + PW_BN - 1) / PW_BN), (unsigned)((p->cout + PW_BM - 1) / PW_BM), (unsigned)p->batch);
+    bayes_pointwise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+    return (int)cudaGetLastError();
+}
+
+int bem_bayes_depthwise(const BemBayesDepthwiseParams* p, void* stream) {
+    if (!p || !p->x || !p->w || !p->out || p->n_samples <= 0 || p->batch <= 0 || p->C <= 0 || p->H <= 0 || p->W <= 0)
+        return BEM_ERR_BAD_ARG;
+    if (p->batch % p->n_samples != 0) return BEM_ERR_BAD_ARG;
+    if (p->K != 3) return BEM_ERR_UNSUPPORTED;
+    const int64_t planes = (int64_t)p->batch * p->C;
+    if (planes > 0x7fffffff) return BEM_ERR_UNSUPPORTED;
+    const int64_t per_plane = (int64_t)p->H * ((p->W + 3) / 4);
+    int64_t by = (per_plane + 255) / 256;
+    if (by > 1024) by = 1024;
+    dim3 grid((unsigned)planes, (unsigned)by);
+    bayes_depthwise3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

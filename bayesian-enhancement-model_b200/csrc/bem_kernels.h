@@ -1,0 +1,83 @@
+// bem_kernels.h — internal declarations shared by the .cu files of libbem_b200.so (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bem_b200.h"
+
+namespace bem {
+
+// scan tiling: consumer warps per CTA, positions per lane (=> chunk length 32*ITEMS)
+constexpr int kScanWarps = 8;
+constexpr int kItemsF32 = 12;   // 48 B per lane: conflict-free LDS.128 with a blocked lane layout
+constexpr int kItems16 = 16;    // 32 B per lane for fp16 / bf16 (2-way LDS conflict, but fits 2 CTAs/SM in registers)
+constexpr int kMaxDstate = 16;  // states staged per pass (B/C chunk lives in shared memory)
+
+inline int scan_items(int dtype) { return dtype == BEM_F32 ? kItemsF32 : kItems16; }
+
+// workspace layout: [0,4) ticket, [4,8) error word, [128, ...) look-back descriptors (16 B each)
+constexpr int64_t kWsHeader = 128;
+
+struct ScanFwdArgs {
+    const void* u;
+    const void* delta;
+    const void* Bm;
+    const void* Cm;
+    const float* A;
+    const float* D;
+    const float* bias;
+    void* out;
+    float* x;
+    int64_t u_bs, u_ds, dl_bs, dl_ds, A_ds, A_ns, B_bs, B_gs, B_ns, C_bs, C_gs, C_ns, out_bs, out_ds;
+    int batch, dim, L, N, G, Dg;
+    int nchunks;       // ceil(L / CL)
+    int RB;            // row blocks (of kScanWarps rows) per group
+    int RT;            // row tiles per chunk = batch * G * RB
+    int total_tiles;   // nchunks * RT
+    int softplus;
+    int stages;
+    uint4* desc;
+    unsigned int* ticket;
+    unsigned int* err;
+};
+
+struct ScanBwdArgs {
+    const void* u;
+    const void* delta;
+    const void* Bm;
+    const void* Cm;
+    const float* A;
+    const float* D;
+    const float* bias;
+    const void* dout;
+    const float* x;
+    void* du;
+    void* ddelta;
+    float* dA;
+    float* dB;
+    float* dC;
+    float* dD;
+    float* dbias;
+    int64_t u_bs, u_ds, dl_bs, dl_ds, A_ds, A_ns, B_bs, B_gs, B_ns, C_bs, C_gs, C_ns, do_bs, do_ds, du_bs, du_ds, dd_bs,
+        dd_ds;
+    int batch, dim, L, N, G, Dg;
+    int nchunks;
+    int RS;            // row splits per group (CTAs sharing one (b, g, chunk) dB/dC slab)
+    int rows_per_split;
+    int RBS;           // row blocks per split
+    int ST;            // super tiles per chunk = batch * G * RS
+    int total_tiles;   // nchunks * ST
+    int softplus;
+    int stages;
+    int atomic_bc;     // 1: dB/dC accumulated with atomics (RS > 1 or general dstate), 0: plain stores
+    uint4* desc;
+    unsigned int* ticket;
+    unsigned int* err;
+};
+
+int scan_fwd_dispatch(const ScanFwdArgs& a, int dtype, int out_dtype, int sm_count, cudaStream_t stream);
+int scan_bwd_dispatch(ScanBwdArgs& a, int dtype, int dout_dtype, int sm_count, cudaStream_t stream);
+
+int device_sm_count();
+
+}  // namespace bem

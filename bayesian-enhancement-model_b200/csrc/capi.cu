@@ -1,0 +1,157 @@
+// capi.cu — the extern "C" surface of libbem_b200.so (include/bem_b200.h): argument validation, workspace carving,
+// launch parameter packing. No torch types, no allocation, no synchronisation.
+#include <cuda_runtime.h>
+
+#include "bem_kernels.h"
+
+namespace bem {
+
+int device_sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+static bool dtype_ok(int dt) { return dt == BEM_F32 || dt == BEM_F16 || dt == BEM_BF16; }
+
+}  // namespace bem
+
+using namespace bem;
+
+extern "C" {
+
+int bem_abi_version(void) { return BEM_ABI_VERSION; }
+
+const char* bem_error_string(int code) {
+    switch (code) {
+        case BEM_OK: return "ok";
+        case BEM_ERR_BAD_ARG: return "bem: bad argument (shape / dtype / NULL contract)";
+        case BEM_ERR_WORKSPACE: return "bem: workspace missing or too small";
+        case BEM_ERR_UNSUPPORTED: return "bem: configuration not built (see DESIGN.md)";
+        default: return cudaGetErrorString((cudaError_t)code);
+    }
+}
+
+int bem_scan_chunk_len(int dtype) { return dtype_ok(dtype) ? 32 * scan_items(dtype) : 0; }
+
+int64_t bem_scan_workspace_bytes(int batch, int dim, int seqlen, int dstate, int dtype) {
+    if (!dtype_ok(dtype) || batch <= 0 || dim <= 0 || seqlen <= 0 || dstate <= 0) return 0;
+    const int CL = bem_scan_chunk_len(dtype);
+    const int64_t nchunks = (seqlen + CL - 1) / CL;
+    const int64_t ns = dstate < kMaxDstate ? dstate : kMaxDstate;   // larger dstate runs in passes of kMaxDstate states
+    return kWsHeader + (int64_t)batch * dim * nchunks * ns * 16;
+}
+
+int bem_scan_fwd(const BemScanFwdParams* q, void* stream_) {
+    if (!q) return BEM_ERR_BAD_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!dtype_ok(q->dtype) || !(q->out_dtype == BEM_F32 || q->out_dtype == q->dtype)) return BEM_ERR_BAD_ARG;
+    if (q->batch <= 0 || q->dim <= 0 || q->seqlen <= 0 || q->dstate <= 0 || q->n_groups <= 0) return BEM_ERR_BAD_ARG;
+    if (q->dim % q->n_groups != 0) return BEM_ERR_BAD_ARG;
+    if (q->dstate > 256) return BEM_ERR_BAD_ARG;   // MAX_DSTATE of the reference (selective_scan_oflex.cpp:190)
+    if (!q->u || !q->delta || !q->A || !q->B || !q->C || !q->out) return BEM_ERR_BAD_ARG;
+    const int64_t need = bem_scan_workspace_bytes(q->batch, q->dim, q->seqlen, q->dstate, q->dtype);
+    if (!q->workspace || q->workspace_bytes < need || (reinterpret_cast<uintptr_t>(q->workspace) & 15)) return BEM_ERR_WORKSPACE;
+    if (q->dstate > kMaxDstate) return BEM_ERR_UNSUPPORTED;
+
+    const int CL = bem_scan_chunk_len(q->dtype);
+    ScanFwdArgs a{};
+    a.u = q->u; a.delta = q->delta; a.Bm = q->B; a.Cm = q->C; a.A = q->A; a.D = q->D; a.bias = q->delta_bias;
+    a.out = q->out; a.x = q->x;
+    a.u_bs = q->u_bs; a.u_ds = q->u_ds; a.dl_bs = q->delta_bs; a.dl_ds = q->delta_ds;
+    a.A_ds = q->A_ds; a.A_ns = q->A_ns;
+    a.B_bs = q->B_bs; a.B_gs = q->B_gs; a.B_ns = q->B_ns;
+    a.C_bs = q->C_bs; a.C_gs = q->C_gs; a.C_ns = q->C_ns;
+    a.out_bs = q->out_bs; a.out_ds = q->out_ds;
+    a.batch = q->batch; a.dim = q->dim; a.L = q->seqlen; a.N = q->dstate; a.G = q->n_groups; a.Dg = q->dim / q->n_groups;
+    a.nchunks = (q->seqlen + CL - 1) / CL;
+    a.RB = (a.Dg + kScanWarps - 1) / kScanWarps;
+    a.RT = a.batch * a.G * a.RB;
+    const int64_t total = (int64_t)a.nchunks * a.RT;
+    if (total > 0x7fffffff) return BEM_ERR_UNSUPPORTED;
+    a.total_tiles = (int)total;
+    a.softplus = q->delta_softplus ? 1 : 0;
+    unsigned char* ws = reinterpret_cast<unsigned char*>(q->workspace);
+    a.ticket = reinterpret_cast<unsigned int*>(ws);
+    a.err = reinterpret_cast<unsigned int*>(ws + 4);
+    a.desc = reinterpret_cast<uint4*>(ws + kWsHeader);
+    cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)need, stream);
+    if (e != cudaSuccess) return (int)e;
+    return scan_fwd_dispatch(a, q->dtype, q->out_dtype, device_sm_count(), stream);
+}
+
+int bem_scan_bwd(const BemScanBwdParams* q, void* stream_) {
+    if (!q) return BEM_ERR_BAD_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!dtype_ok(q->dtype) || !(q->dout_dtype == BEM_F32 || q->dout_dtype == q->dtype)) return BEM_ERR_BAD_ARG;
+    if (q->batch <= 0 || q->dim <= 0 || q->seqlen <= 0 || q->dstate <= 0 || q->n_groups <= 0) return BEM_ERR_BAD_ARG;
+    if (q->dim % q->n_groups != 0 || q->dstate > 256) return BEM_ERR_BAD_ARG;
+    if (!q->u || !q->delta || !q->A || !q->B || !q->C || !q->dout || !q->du || !q->ddelta || !q->dA || !q->dB || !q->dC)
+        return BEM_ERR_BAD_ARG;
+    const int CL = bem_scan_chunk_len(q->dtype);
+    const int nchunks = (q->seqlen + CL - 1) / CL;
+    if (nchunks > 1 && !q->x) return BEM_ERR_BAD_ARG;   // selective_scan_oflex.cpp:315
+    const int64_t need = bem_scan_workspace_bytes(q->batch, q->dim, q->seqlen, q->dstate, q->dtype);
+    if (!q->workspace || q->workspace_bytes < need || (reinterpret_cast<uintptr_t>(q->workspace) & 15)) return BEM_ERR_WORKSPACE;
+    if (q->dstate > kMaxDstate) return BEM_ERR_UNSUPPORTED;
+
+    ScanBwdArgs a{};
+    a.u = q->u; a.delta = q->delta; a.Bm = q->B; a.Cm = q->C; a.A = q->A; a.D = q->D; a.bias = q->delta_bias;
+    a.dout = q->dout; a.x = q->x; a.du = q->du; a.ddelta = q->ddelta;
+    a.dA = q->dA; a.dB = q->dB; a.dC = q->dC; a.dD = q->D ? q->dD : nullptr; a.dbias = q->delta_bias ? q->ddelta_bias : nullptr;
+    a.u_bs = q->u_bs; a.u_ds = q->u_ds; a.dl_bs = q->delta_bs; a.dl_ds = q->delta_ds;
+    a.A_ds = q->A_ds; a.A_ns = q->A_ns;
+    a.B_bs = q->B_bs; a.B_gs = q->B_gs; a.B_ns = q->B_ns;
+    a.C_bs = q->C_bs; a.C_gs = q->C_gs; a.C_ns = q->C_ns;
+    a.do_bs = q->dout_bs; a.do_ds = q->dout_ds;
+    a.du_bs = q->du_bs; a.du_ds = q->du_ds; a.dd_bs = q->ddelta_bs; a.dd_ds = q->ddelta_ds;
+    a.batch = q->batch; a.dim = q->dim; a.L = q->seqlen; a.N = q->dstate; a.G = q->n_groups; a.Dg = q->dim / q->n_groups;
+    a.nchunks = nchunks;
+    // Row splits: one CTA walks all rows of a (b, group, chunk) slab when that still fills the machine; otherwise the
+    // group's rows are split over RS CTAs whose dB/dC partial sums meet in global atomics.
+    const int sms = device_sm_count();
+    const int64_t slabs = (int64_t)a.batch * a.G * a.nchunks;
+    const int max_rs = (a.Dg + kScanWarps - 1) / kScanWarps;
+    int rs = 1;
+    while (rs < max_rs && slabs * rs < 4LL * sms) rs *= 2;
+    if (rs > max_rs) rs = max_rs;
+    a.RS = rs;
+    a.rows_per_split = ((a.Dg + rs - 1) / rs + kScanWarps - 1) / kScanWarps * kScanWarps;   // multiple of the warp count
+    a.RS = (a.Dg + a.rows_per_split - 1) / a.rows_per_split;
+    a.RBS = a.rows_per_split / kScanWarps;
+    a.ST = a.batch * a.G * a.RS;
+    const int64_t total = (int64_t)a.nchunks * a.ST;
+    if (total > 0x7fffffff) return BEM_ERR_UNSUPPORTED;
+    a.total_tiles = (int)total;
+    a.softplus = q->delta_softplus ? 1 : 0;
+    a.atomic_bc = (a.RS > 1 || a.N > 1) ? 1 : 0;
+    unsigned char* ws = reinterpret_cast<unsigned char*>(q->workspace);
+    a.ticket = reinterpret_cast<unsigned int*>(ws);
+    a.err = reinterpret_cast<unsigned int*>(ws + 4);
+    a.desc = reinterpret_cast<uint4*>(ws + kWsHeader);
+    cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)need, stream);
+    if (e != cudaSuccess) return (int)e;
+    return scan_bwd_dispatch(a, q->dtype, q->dout_dtype, sms, stream);
+}
+
+// Fused SS2D core (traversal-aware scan). Entry point reserved in the ABI; until the traversal-aware loader lands the
+// host side composes bem_cross_scan -> bem_scan_fwd -> bem_cross_merge (bem_b200/ss2d.py) and this reports UNSUPPORTED.
+int64_t bem_ss2d_workspace_bytes(int batch, int d_inner, int H, int W, int dstate, int dtype) {
+    return bem_scan_workspace_bytes(batch, 4 * d_inner, H * W, dstate, dtype);
+}
+int bem_ss2d_fwd(const BemSs2dFwdParams* p, void* stream) {
+    (void)p;
+    (void)stream;
+    return BEM_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

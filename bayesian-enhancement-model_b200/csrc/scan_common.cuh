@@ -1,0 +1,268 @@
+// scan_common.cuh — device helpers shared by the sm_100a selective-scan kernels.
+//
+// Building blocks (all hand-written, no CUB):
+//   * mbarrier + cp.async.bulk (TMA 1-D bulk copies) wrappers: global -> shared staging with transaction
+//     barriers, shared -> global bulk stores with bulk_group completion
+//   * the scan monoid of the SSM recurrence h_t = a_t h_{t-1} + b_t  (reference: SSMScanOp,
+//     kernels/selective_scan/csrc/selective_scan/selective_scan_common.h:91-96) as warp-shuffle scans
+//   * a decoupled look-back over per-(row, chunk, state) descriptors so the sequence dimension L is split
+//     across CTAs (the reference walks its 2048-chunks serially inside one CTA,
+//     cusoflex/selective_scan_fwd_kernel_oflex.cuh:110)
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bem {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU box. On timeout the error word is set and the wait
+// returns; the results are then garbage and the host reports BEM failure from the error word.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned int* err) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {   // ~2 s
+            atomicOr(err, 1u);
+            return;
+        }
+    }
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (complete_tx::bytes).
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// TMA 1-D bulk copy shared -> global, tracked by the issuing thread's bulk async-group.
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// softplus(x) = max(x,0) + log1p(exp(-|x|)); identical to the reference's `x <= 20 ? log1pf(expf(x)) : x`
+// (cusoflex/selective_scan_fwd_kernel_oflex.cuh:124-126, F.softplus threshold 20) to < 2e-7 absolute: beyond 20 the
+// correction term is below 2.1e-9.
+__device__ __forceinline__ float softplus_f(float x) {
+    const float z = ex2_approx(-fabsf(x) * kLog2e);
+    return fmaxf(x, 0.f) + kLn2 * lg2_approx(1.f + z);
+}
+// d softplus / dx = sigmoid(x); the reference switches to 1 above the threshold
+// (cusoflex/selective_scan_bwd_kernel_oflex.cuh:250-255)
+__device__ __forceinline__ float softplus_grad_f(float x) {
+    return x <= 20.f ? __fdividef(1.f, 1.f + ex2_approx(-x * kLog2e)) : 1.f;
+}
+
+// 128-bit descriptor access that is a single transaction at L2 (bypasses L1)
+__device__ __forceinline__ uint4 ld_desc(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_desc(uint4* p, float P, float V, uint32_t status) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(__float_as_uint(P)), "r"(__float_as_uint(V)),
+                 "r"(status), "r"(0u)
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// element type helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct ElemTraits;
+template <> struct ElemTraits<float> {
+    static constexpr int kPerVec = 4;
+    __device__ static __forceinline__ float to_f(float v) { return v; }
+    __device__ static __forceinline__ float from_f(float v) { return v; }
+};
+template <> struct ElemTraits<__half> {
+    static constexpr int kPerVec = 8;
+    __device__ static __forceinline__ float to_f(__half v) { return __half2float(v); }
+    __device__ static __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+};
+template <> struct ElemTraits<__nv_bfloat16> {
+    static constexpr int kPerVec = 8;
+    __device__ static __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+    __device__ static __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+
+// ITEMS consecutive elements from 16-byte aligned shared memory -> fp32 registers (LDS.128)
+template <typename T, int ITEMS>
+__device__ __forceinline__ void lds_items(const T* __restrict__ src, float (&dst)[ITEMS]) {
+    constexpr int V = ElemTraits<T>::kPerVec;
+    static_assert(ITEMS % V == 0, "ITEMS must be a multiple of the 128-bit vector width");
+#pragma unroll
+    for (int v = 0; v < ITEMS / V; ++v) {
+        const uint4 raw = reinterpret_cast<const uint4*>(src)[v];
+        const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+        for (int k = 0; k < V; ++k) dst[v * V + k] = ElemTraits<T>::to_f(e[k]);
+    }
+}
+// fp32 registers -> ITEMS consecutive elements in 16-byte aligned shared memory (STS.128)
+template <typename T, int ITEMS>
+__device__ __forceinline__ void sts_items(T* __restrict__ dst, const float (&src)[ITEMS]) {
+    constexpr int V = ElemTraits<T>::kPerVec;
+    static_assert(ITEMS % V == 0, "ITEMS must be a multiple of the 128-bit vector width");
+#pragma unroll
+    for (int v = 0; v < ITEMS / V; ++v) {
+        uint4 raw;
+        T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+        for (int k = 0; k < V; ++k) e[k] = ElemTraits<T>::from_f(src[v * V + k]);
+        reinterpret_cast<uint4*>(dst)[v] = raw;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// scan monoid: an affine map h -> P*h + V. combine(first, second) applies `first` then `second`.
+// ------------------------------------------------------------------------------------------------
+// inclusive scan over the warp in lane order (lane 0 is applied first)
+__device__ __forceinline__ void warp_scan_fwd(float& P, float& V, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float Pp = __shfl_up_sync(FULL, P, o);
+        const float Vp = __shfl_up_sync(FULL, V, o);
+        if (lane >= o) {
+            V = fmaf(P, Vp, V);
+            P = P * Pp;
+        }
+    }
+}
+// inclusive scan over the warp in REVERSE lane order (lane 31 is applied first)
+__device__ __forceinline__ void warp_scan_rev(float& P, float& V, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float Pp = __shfl_down_sync(FULL, P, o);
+        const float Vp = __shfl_down_sync(FULL, V, o);
+        if (lane + o < 32) {
+            V = fmaf(P, Vp, V);
+            P = P * Pp;
+        }
+    }
+}
+
+// Descriptor status
+enum : uint32_t { DESC_EMPTY = 0, DESC_AGGREGATE = 1, DESC_INCLUSIVE = 2 };
+
+// Decoupled look-back. Tile `c` of a row asks for the composition of all tiles that the flowing value passes
+// through BEFORE it: step = -1 -> tiles c-1, c-2, ... 0 (forward scan); step = +1 -> tiles c+1 ... nchunks-1
+// (reverse scan). desc0 points at this row's descriptor of tile 0 for this state; consecutive tiles are `dstride`
+// descriptors apart. Lane j of the warp inspects the tile j steps further away; a tile marked INCLUSIVE already holds
+// the whole composition beyond it and ends the walk. Returns (P, V) of the composition (identity (1,0) if none).
+__device__ __forceinline__ float2 lookback(const uint4* desc0, int64_t dstride, int c, int nchunks, int step, int lane,
+                                           unsigned int* err) {
+    float runP = 1.f, runV = 0.f;   // tiles already folded; applied AFTER whatever is still to be found
+    int j = c + step;               // nearest unexamined tile
+    while (true) {
+        const int idx = j + step * lane;
+        const bool inside = idx >= 0 && idx < nchunks;
+        float P = 1.f, V = 0.f;
+        uint32_t st = DESC_INCLUSIVE;   // beyond the end of the sequence: identity, terminates the walk
+        if (inside) st = DESC_EMPTY;
+        unsigned incl, need;
+        int spins = 0;
+        while (true) {
+            if (inside && st == DESC_EMPTY) {
+                const uint4 v = ld_desc(desc0 + (int64_t)idx * dstride);
+                st = v.z;
+                P = __uint_as_float(v.x);
+                V = __uint_as_float(v.y);
+            }
+            incl = __ballot_sync(FULL, st == DESC_INCLUSIVE);
+            const unsigned ready = __ballot_sync(FULL, st != DESC_EMPTY);
+            need = incl ? ((2u << (__ffs(incl) - 1)) - 1u) : FULL;   // lanes up to the nearest inclusive tile
+            if ((ready & need) == need) break;
+            if (++spins > 64) __nanosleep(64);
+            if (spins > (1 << 22)) {   // watchdog, see mbar_wait
+                if (lane == 0) atomicOr(err, 2u);
+                break;
+            }
+        }
+        if (!((need >> lane) & 1u)) {
+            P = 1.f;
+            V = 0.f;
+        }
+        // fold lanes: lane i ends with tiles [i, 32) where higher lanes are applied first
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float Pp = __shfl_down_sync(FULL, P, o);
+            const float Vp = __shfl_down_sync(FULL, V, o);
+            if (lane + o < 32) {
+                V = fmaf(P, Vp, V);
+                P = P * Pp;
+            }
+        }
+        const float Pw = __shfl_sync(FULL, P, 0), Vw = __shfl_sync(FULL, V, 0);
+        runV = fmaf(runP, Vw, runV);   // window first, then the nearer tiles folded so far
+        runP = runP * Pw;
+        if (incl) break;
+        j += step * 32;
+    }
+    return make_float2(runP, runV);
+}
+
+// ------------------------------------------------------------------------------------------------
+// work decomposition shared by fwd/bwd
+// ------------------------------------------------------------------------------------------------
+struct TileCoord {
+    int c;       // chunk index along L
+    int b, g;    // batch, B/C group
+    int row0;    // first channel row (within the group) of this step
+    int nrows;   // rows in this step (<= NW)
+};
+
+}  // namespace bem

@@ -1,0 +1,144 @@
+"""Monte-Carlo multi-sample inference + best-sample selection — the sample loop and selection of
+Enhancement/eval.py:199-222, 268-297, re-organised for one-process-per-GPU execution.
+
+Reference behaviour: `num_samples` sequential batch-1 forwards of the stage-1 network, every Bayesian layer drawing a
+fresh eps (eval.py:199-211); every prediction is scored, and the first index attaining the best score wins
+(`lst.index(max(lst))`, eval.py:270-274); optional Monte-Carlo mean (eval.py:224-225).
+
+Here: samples are independent given the input, so sample i is owned by rank i % world_size. With the
+counter-based eps source ("philox") sample i gets the same weights whatever the world size or batching, so the selected
+image does not depend on how many GPUs took part. The only exchange is an all_gather of one score per sample plus a
+broadcast of the winner (NCCL on GPUs; gloo in the CPU tests of the host logic).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, bayesian
+from ._lib import lib
+
+
+def select_best(scores: torch.Tensor, take_min: bool = False):
+    """scores: (n,) float32 CUDA tensor -> (index, value) 0-d CUDA tensors; first extremum, Python `list.index` semantics
+    including NaN handling (Enhancement/eval.py:270-274). Runs bem_select_best; no host sync."""
+    _lib.require_cuda(scores)
+    s = scores.reshape(-1).to(torch.float32).contiguous()
+    idx = torch.empty((), dtype=torch.int32, device=s.device)
+    val = torch.empty((), dtype=torch.float32, device=s.device)
+    with torch.cuda.device(s.device):
+        _lib.check(lib.bem_select_best(_lib.ptr(s), s.numel(), int(bool(take_min)), _lib.ptr(idx), _lib.ptr(val),
+                                       _lib.stream_ptr(s.device)), "select_best")
+    return idx, val
+
+
+def shard_samples(num_samples: int, rank: int, world_size: int) -> List[int]:
+    """global sample indices owned by `rank`: i with i % world_size == rank (100 samples on 8 ranks -> 13/12 split)."""
+    return list(range(rank, num_samples, world_size))
+
+
+def owner_of(sample: int, world_size: int) -> int:
+    return sample % world_size
+
+
+def default_score(pred: torch.Tensor) -> torch.Tensor:
+    """A device-resident no-reference score per image, (S, 3, H, W) -> (S,): luminance contrast (std) of the clamped
+    prediction penalised by clipping. Stand-in for the CLIP-IQA / NIQE scorers of eval.py:229-260, which are separate
+    pretrained models outside the hot path; any callable with this shape contract can be passed instead."""
+    p = pred.clamp(0, 1)
+    lum = 0.299 * p[:, 0] + 0.587 * p[:, 1] + 0.114 * p[:, 2]
+    clipped = ((lum <= 0.0) | (lum >= 1.0)).float().mean(dim=(1, 2))
+    return lum.std(dim=(1, 2)) - 0.5 * clipped
+
+
+class MCSampler:
+    """Draws Monte-Carlo predictions of a Bayesian network for one input.
+
+    net        : network whose Bayesian layers come from bem_b200.bayesian (e.g. network.build_bayesian_model())
+    seed       : Philox seed shared by all ranks
+    batch      : samples evaluated per forward (S-batched grouped kernels); 1 reproduces the reference loop
+    out_index  : which element of the network's output list is the prediction (eval.py:200 uses [-1])
+    """
+
+    def __init__(self, net, seed: int = 287128, batch: int = 1, eps_source: str = "philox", out_index: int = -1,
+                 post: Optional[Callable] = None):
+        self.net = net
+        self.seed = seed
+        self.batch = max(1, int(batch))
+        self.eps_source = eps_source
+        self.out_index = out_index
+        self.post = post or (lambda y: torch.clamp(y, 0, 1))   # eval.py:201
+        bayesian.set_prediction_type(net, deterministic=False)
+
+    @torch.no_grad()
+    def sample(self, x: torch.Tensor, sample_ids: Sequence[int]) -> torch.Tensor:
+        """x: (1, C, H, W) -> (len(sample_ids), C_out, H, W), one prediction per global sample index."""
+        outs = []
+        ids = list(sample_ids)
+        i = 0
+        while i < len(ids):
+            # batch runs of consecutive-by-stride ids cannot share a Philox `sample0` unless contiguous; batch only
+            # contiguous runs, otherwise go one at a time
+            j = i + 1
+            while j < len(ids) and j - i < self.batch and ids[j] == ids[j - 1] + 1:
+                j += 1
+            S = j - i
+            bayesian.set_mc_config(self.net, mc_samples=S, eps_source=self.eps_source, seed=self.seed, sample0=ids[i])
+            xin = x.expand(S, *x.shape[1:]).contiguous() if S > 1 else x
+            y = self.net(xin)
+            y = y[self.out_index] if isinstance(y, (list, tuple)) else y
+            outs.append(self.post(y))
+            i = j
+        bayesian.set_mc_config(self.net, mc_samples=1, sample0=0)
+        return torch.cat(outs, dim=0) if outs else x.new_empty((0,) + tuple(x.shape[1:]))
+
+
+@torch.no_grad()
+def mc_infer(sampler: MCSampler, x: torch.Tensor, num_samples: int, score_fn: Callable = default_score,
+             take_min: bool = False, monte_carlo_mean: bool = False, group=None):
+    """Distributed MC inference for one image. Every rank calls this with the same x / num_samples.
+
+    Returns dict(best=(C,H,W) tensor on every rank, index=int, scores=(num_samples,) tensor[, mean=(C,H,W)]).
+    Single process (no initialised process group) = all samples local.
+    """
+    distributed = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if distributed else 0
+    world = dist.get_world_size(group) if distributed else 1
+    mine = shard_samples(num_samples, rank, world)
+    preds = sampler.sample(x, mine)                                 # (len(mine), C, H, W)
+    local_scores = score_fn(preds).to(torch.float32) if len(mine) else preds.new_empty((0,), dtype=torch.float32)
+
+    # scores -> every rank, in GLOBAL sample order (ragged shards: pad to the largest shard)
+    per = (num_samples + world - 1) // world
+    padded = torch.full((per,), float("nan"), dtype=torch.float32, device=x.device)
+    padded[: len(mine)] = local_scores
+    if distributed:
+        gathered = [torch.empty_like(padded) for _ in range(world)]
+        dist.all_gather(gathered, padded, group=group)
+        table = torch.stack(gathered, dim=1).reshape(-1)[:num_samples]   # [j, r] -> sample j * world + r
+    else:
+        table = padded[:num_samples]
+    if x.is_cuda:
+        idx_t, _ = select_best(table, take_min)
+        index = int(idx_t.item())
+    else:   # host-logic tests on CPU (gloo): same semantics as bem_select_best
+        lst = table.tolist()
+        index = lst.index(min(lst) if take_min else max(lst))
+    owner = owner_of(index, world)
+    if owner == rank:
+        best = preds[mine.index(index)].clone()
+    else:   # receive buffer: every rank knows the prediction shape from its own shard (or from x when it has none)
+        shape = preds.shape[1:] if preds.numel() else x.shape[1:]
+        best = torch.empty(shape, dtype=preds.dtype, device=x.device)
+    if distributed:
+        dist.broadcast(best, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+    out = dict(best=best, index=index, scores=table)
+    if monte_carlo_mean:
+        acc = preds.sum(dim=0) if len(mine) else torch.zeros(x.shape[1:], dtype=x.dtype, device=x.device)
+        if distributed:
+            dist.all_reduce(acc, group=group)
+        out["mean"] = torch.clamp(acc / num_samples, 0, 1)           # eval.py:224-225
+    return out

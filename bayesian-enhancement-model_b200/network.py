@@ -1,0 +1,251 @@
+"""Host-side mirror of the stage-1 condition generator: `Network` of basicsr/archs/UNet_arch.py:365-474 and the blocks it
+is built from (VSSBlock vmamba.py:1241-1334, gdMlp vmamba.py:116-133, BasicBlock / SubNetwork / PatchMerging /
+DualUpSample UNet_arch.py:57-362).
+
+Why it exists: BASELINE configs 2/3 (MC-sample images/s of the stage-1 Bayesian UNet) must run on a box that has no copy
+of the reference. Module / parameter names and shapes equal the reference's, so `state_dict`s (including released
+`{'params': ...}` checkpoints and their `mu_*/rho_*` keys after `convert2bnn_selective`) load unchanged; tests/ pins the
+forward against vectors recorded from the reference model. Everything on the hot path (scan, traversal, Bayesian layers)
+runs on this package's kernels; the deterministic glue around it (LayerNorm, activations, resampling, the two 3x3 stem
+convolutions) is ordinary PyTorch and is outside the scope table.
+"""
+from __future__ import annotations
+
+from functools import partial
+
+import torch
+import torch.nn as nn
+
+from . import bayesian
+from .ss2d import SS2D, LayerNorm2d
+
+
+class gdMlp(nn.Module):
+    """Gated-Dconv MLP (vmamba.py:116-133)."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0, channels_first=False):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.project_in = nn.Conv2d(in_features, hidden_features * 2, kernel_size=1)
+        self.dwconv = nn.Conv2d(hidden_features * 2, hidden_features * 2, kernel_size=3, stride=1, padding=1,
+                                groups=hidden_features * 2)
+        self.project_out = nn.Conv2d(hidden_features, out_features, kernel_size=1)
+        self.act = act_layer()
+
+    def forward(self, x):
+        x = self.project_in(x)
+        x1, x2 = self.dwconv(x).chunk(2, dim=1)
+        x = self.act(x1) * x2
+        return self.project_out(x)
+
+
+class VSSBlock(nn.Module):
+    """VSSBlock._forwardv01 with post_norm=False, drop_path=0 (vmamba.py:1319-1334)."""
+
+    def __init__(self, hidden_dim=0, drop_path=0, norm_layer=LayerNorm2d, channel_first=True, ssm_d_state=16, ssm_ratio=2.0,
+                 ssm_dt_rank="auto", ssm_act_layer=nn.SiLU, ssm_conv=3, ssm_conv_bias=True, ssm_drop_rate=0, ssm_init="v0",
+                 forward_type="v05_noz", mlp_ratio=4.0, mlp_act_layer=nn.GELU, mlp_drop_rate=0.0, mlp_type="gdmlp",
+                 use_checkpoint=False, post_norm=False, **kwargs):
+        super().__init__()
+        if drop_path != 0 or post_norm or use_checkpoint or mlp_type != "gdmlp":
+            raise NotImplementedError("bem_b200.VSSBlock mirrors the BEM configuration only (UNet_arch.py:205-228)")
+        self.norm = norm_layer(hidden_dim)
+        self.op = SS2D(d_model=hidden_dim, d_state=ssm_d_state, ssm_ratio=ssm_ratio, dt_rank=ssm_dt_rank,
+                       act_layer=ssm_act_layer, d_conv=ssm_conv, conv_bias=ssm_conv_bias, dropout=ssm_drop_rate,
+                       initialize=ssm_init, forward_type=forward_type, channel_first=channel_first)
+        self.norm2 = norm_layer(hidden_dim)
+        self.mlp = gdMlp(in_features=hidden_dim, hidden_features=int(hidden_dim * mlp_ratio), act_layer=mlp_act_layer,
+                         drop=mlp_drop_rate, channels_first=channel_first)
+
+    def forward(self, x):
+        x = x + self.op(self.norm(x))
+        return x + self.mlp(self.norm2(x))
+
+
+class PatchMerging(nn.Module):
+    """UNet_arch.PatchMerging (UNet_arch.py:57-83)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+        self.norm = LayerNorm2d(4 * dim)
+        self.reduction = nn.Conv2d(4 * dim, 2 * dim, 1, 1, 0, bias=False)
+
+    def forward(self, x):
+        x = torch.cat([x[:, :, 0::2, 0::2], x[:, :, 1::2, 0::2], x[:, :, 0::2, 1::2], x[:, :, 1::2, 1::2]], 1)
+        return self.reduction(self.norm(x))
+
+
+class DualUpSample(nn.Module):
+    """UNet_arch.DualUpSample (UNet_arch.py:97-156), scale factors 2 and 4."""
+
+    def __init__(self, in_channels, scale_factor):
+        super().__init__()
+        self.factor = scale_factor
+        c = in_channels
+        if scale_factor == 2:
+            self.conv = nn.Conv2d(c, c // 2, 1, 1, 0, bias=False)
+            self.up_p = nn.Sequential(nn.Conv2d(c, 2 * c, 1, 1, 0, bias=False), nn.PReLU(), nn.PixelShuffle(2),
+                                      nn.Conv2d(c // 2, c // 2, 1, stride=1, padding=0, bias=False))
+            self.up_b = nn.Sequential(nn.Conv2d(c, c, 1, 1, 0), nn.PReLU(),
+                                      nn.Upsample(scale_factor=2, mode="bilinear", align_corners=False),
+                                      nn.Conv2d(c, c // 2, 1, stride=1, padding=0, bias=False))
+        elif scale_factor == 4:
+            self.conv = nn.Conv2d(2 * c, c, 1, 1, 0, bias=False)
+            self.up_p = nn.Sequential(nn.Conv2d(c, 16 * c, 1, 1, 0, bias=False), nn.PReLU(), nn.PixelShuffle(4),
+                                      nn.Conv2d(c, c, 1, stride=1, padding=0, bias=False))
+            self.up_b = nn.Sequential(nn.Conv2d(c, c, 1, 1, 0), nn.PReLU(),
+                                      nn.Upsample(scale_factor=4, mode="bilinear", align_corners=False),
+                                      nn.Conv2d(c, c, 1, stride=1, padding=0, bias=False))
+        else:
+            raise NotImplementedError(scale_factor)
+
+    def forward(self, x):
+        return self.conv(torch.cat([self.up_p(x), self.up_b(x)], dim=1))
+
+
+class BasicBlock(nn.Module):
+    """UNet_arch.BasicBlock (UNet_arch.py:179-243); `.bayesian` marks the region convert2bnn_selective converts."""
+
+    def __init__(self, dim, num_blocks=2, d_state=1, ssm_ratio=1, mlp_ratio=4, mlp_type="gdmlp", sam=False, condition=False,
+                 bayesian=False):
+        super().__init__()
+        if sam or condition:
+            raise NotImplementedError("SAM / condition blocks are not part of the stage-1 model (UNet_arch.py:477-487)")
+        self.bayesian = bayesian
+        self.sam = sam
+        self.condition = condition
+        self.blocks = nn.ModuleList([
+            VSSBlock(hidden_dim=dim, drop_path=0, norm_layer=LayerNorm2d, channel_first=True, ssm_d_state=d_state,
+                     ssm_ratio=ssm_ratio, ssm_dt_rank="auto", ssm_act_layer=nn.SiLU, ssm_conv=3, ssm_conv_bias=False,
+                     ssm_drop_rate=0, ssm_init="v0", forward_type="v05_noz", mlp_ratio=mlp_ratio, mlp_act_layer=nn.GELU,
+                     mlp_drop_rate=0.0, mlp_type=mlp_type, use_checkpoint=False, post_norm=False)
+            for _ in range(num_blocks)])
+
+    def forward(self, x):
+        for block in self.blocks:
+            x = block(x)
+        return x
+
+
+class SubNetwork(nn.Module):
+    """UNet_arch.SubNetwork (UNet_arch.py:246-362) with use_pixelshuffle=True (PatchMerging / DualUpSample)."""
+
+    def __init__(self, dim=31, num_blocks=(2, 4, 4), d_state=(1, 1, 1), ssm_ratio=1, mlp_ratio=4, mlp_type="gdmlp",
+                 use_pixelshuffle=True, drop_path=0.0, sam=False):
+        super().__init__()
+        if not use_pixelshuffle or drop_path > 0 or sam:
+            raise NotImplementedError("bem_b200.SubNetwork mirrors build_model()'s configuration (UNet_arch.py:477-487)")
+        self.dim = dim
+        level = len(num_blocks) - 1
+        self.level = level
+        self.encoder_layers = nn.ModuleList([])
+        self.drop_path = nn.Identity()
+        curr = dim
+        for i in range(level):
+            self.encoder_layers.append(nn.ModuleList([
+                BasicBlock(dim=curr, num_blocks=num_blocks[i], d_state=d_state[i], ssm_ratio=ssm_ratio, mlp_ratio=mlp_ratio,
+                           mlp_type=mlp_type, bayesian=True),
+                PatchMerging(curr)]))
+            curr *= 2
+        self.bottleneck = BasicBlock(dim=curr, num_blocks=num_blocks[-1], d_state=d_state[level], ssm_ratio=ssm_ratio,
+                                     mlp_ratio=mlp_ratio, bayesian=True)
+        self.decoder_layers = nn.ModuleList([])
+        for i in range(level):
+            self.decoder_layers.append(nn.ModuleList([
+                DualUpSample(curr, scale_factor=2),
+                nn.Conv2d(curr, curr // 2, 1, 1, bias=False),
+                BasicBlock(dim=curr // 2, num_blocks=num_blocks[level - 1 - i], d_state=d_state[level - 1 - i],
+                           ssm_ratio=ssm_ratio, mlp_ratio=mlp_ratio, bayesian=True)]))
+            curr //= 2
+        self.apply(self._init_weights)
+
+    @staticmethod
+    def _init_weights(m):
+        """UNet_arch.py:331-338: every nn.Linear (hence Linear2d in_proj / out_proj) and nn.LayerNorm is re-initialised."""
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=0.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.weight, 1.0)
+            nn.init.constant_(m.bias, 0)
+
+    def forward(self, x):
+        fea = x
+        skips = []
+        for en_block, down in self.encoder_layers:
+            fea = en_block(fea)
+            skips.append(fea)
+            fea = down(fea)
+        fea = self.bottleneck(fea)
+        for i, (up, fusion, de_block) in enumerate(self.decoder_layers):
+            fea = up(fea)
+            fea = fusion(torch.cat([fea, skips[self.level - 1 - i]], dim=1))
+            fea = de_block(fea)
+        return x + self.drop_path(fea)
+
+
+class Network(nn.Module):
+    """UNet_arch.Network (UNet_arch.py:365-474): first_conv -> `stage` SubNetworks -> proj; returns [x, out_1, ...]."""
+
+    def __init__(self, in_channels=3, out_channels=3, n_feat=40, stage=1, num_blocks=(1, 1, 1), d_state=1, ssm_ratio=1,
+                 mlp_ratio=4, mlp_type="gdmlp", use_pixelshuffle=False, drop_path=0.0, use_illu=False, sam=False,
+                 last_act=None):
+        super().__init__()
+        self.stage = stage
+        self.mask_token = nn.Parameter(torch.zeros(1, n_feat, 1, 1))
+        nn.init.trunc_normal_(self.mask_token, mean=0.0, std=0.02)
+        self.first_conv = nn.Conv2d(in_channels, n_feat, 3, 1, 1, bias=True)
+        nn.init.kaiming_normal_(self.first_conv.weight, mode="fan_out", nonlinearity="linear")
+        nn.init.zeros_(self.first_conv.bias)
+        self.subnets = nn.ModuleList([])
+        self.proj = nn.Conv2d(n_feat, out_channels, 3, 1, 1, bias=True)
+        nn.init.zeros_(self.proj.bias)
+        if last_act is None:
+            self.last_act = nn.Identity()
+        elif last_act == "relu":
+            self.last_act = nn.ReLU()
+        elif last_act == "softmax":
+            self.last_act = nn.Softmax(dim=1)
+        else:
+            raise NotImplementedError
+        if isinstance(d_state, int):
+            d_state = [d_state] * len(num_blocks)
+        for _ in range(stage):
+            self.subnets.append(SubNetwork(dim=n_feat, num_blocks=list(num_blocks), d_state=list(d_state),
+                                           ssm_ratio=ssm_ratio, mlp_ratio=mlp_ratio, mlp_type=mlp_type,
+                                           use_pixelshuffle=use_pixelshuffle, drop_path=drop_path, sam=sam))
+
+    def forward(self, x, mask=None):
+        out_list = [x]
+        fea = self.first_conv(x)
+        B, C, H, W = fea.size()
+        if self.training and mask is not None:
+            mask_tokens = self.mask_token.expand(B, -1, H, W)
+            w = mask.unsqueeze(1).type_as(mask_tokens)
+            fea = fea * (1.0 - w) + mask_tokens * w
+        for subnet in self.subnets:
+            fea = subnet(fea)
+            out_list.append(self.last_act(self.proj(fea)))
+        return out_list
+
+
+def build_model():
+    """UNet_arch.build_model (UNet_arch.py:477-487): the stage-1 configuration."""
+    return Network(stage=1, n_feat=40, num_blocks=[2, 2, 2], d_state=[1, 1, 1], ssm_ratio=1, mlp_ratio=4, mlp_type="gdmlp",
+                   use_pixelshuffle=True)
+
+
+def build_bayesian_model(sigma_init=0.05, decay=0.998, pretrain=False, selective=True):
+    """stage-1 Bayesian condition generator: build_model() + convert2bnn exactly as ConditionGenerator.__init__ does
+    (basicsr/models/condition_generator_model.py:50-59)."""
+    net = build_model()
+    cfg = {"sigma_init": sigma_init, "decay": decay, "pretrain": pretrain}
+    if selective:
+        bayesian.convert2bnn_selective(net, cfg)
+    else:
+        bayesian.convert2bnn(net, cfg)
+    bayesian.set_mc_config(net)   # assigns layer ids
+    return net

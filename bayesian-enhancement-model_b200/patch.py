@@ -1,0 +1,47 @@
+"""Install the sm_100a operators into an imported copy of the reference, so its models run unmodified on them.
+
+    import bem_b200
+    bem_b200.patch.install()            # patches whatever reference modules are already in sys.modules
+    bem_b200.patch.install(vmamba=mod)  # or pass modules explicitly
+
+What gets replaced:
+  * `csms6s.selective_scan_fn` and the name imported into vmamba.py (basicsr/vmamba/models/vmamba.py:27-30)
+  * `csm_triton.cross_scan_fn` / `cross_merge_fn` and the names imported into vmamba.py (:22-25)
+  * the top-level `bayesian` package that basicsr/bayesian/tools.py:1 and the model wrappers import
+"""
+from __future__ import annotations
+
+import sys
+
+
+def install(vmamba=None, csms6s=None, csm_triton=None, replace_bayesian=True):
+    from . import bayesian as _bayes
+    from .csm import cross_merge_fn, cross_scan_fn
+    from .selective_scan import SelectiveScanCuda, selective_scan_cuda_oflex, selective_scan_fn
+
+    patched = []
+    mods = dict(sys.modules)
+    for name, mod in mods.items():
+        if mod is None:
+            continue
+        base = name.rsplit(".", 1)[-1]
+        if (csms6s is None and base == "csms6s") or mod is csms6s:
+            mod.selective_scan_fn = selective_scan_fn
+            mod.SelectiveScanCuda = SelectiveScanCuda
+            mod.selective_scan_cuda_oflex = selective_scan_cuda_oflex
+            mod.WITH_SELECTIVESCAN_OFLEX = True
+            patched.append(name)
+        if (csm_triton is None and base == "csm_triton") or mod is csm_triton:
+            mod.cross_scan_fn = cross_scan_fn
+            mod.cross_merge_fn = cross_merge_fn
+            patched.append(name)
+        if (vmamba is None and base == "vmamba" and hasattr(mod, "SS2D")) or mod is vmamba:
+            mod.selective_scan_fn = selective_scan_fn
+            mod.cross_scan_fn = cross_scan_fn
+            mod.cross_merge_fn = cross_merge_fn
+            patched.append(name)
+    if replace_bayesian:
+        sys.modules["bayesian"] = _bayes
+        patched.append("bayesian")
+    sys.modules.setdefault("selective_scan_cuda_oflex", selective_scan_cuda_oflex)
+    return patched

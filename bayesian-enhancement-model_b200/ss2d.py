@@ -1,0 +1,143 @@
+"""SS2D core — the caller of the hot path: SS2Dv2.forward_corev2, scan_mode cross2d / unidi / bidi, `no_einsum=True`
+(basicsr/vmamba/models/vmamba.py:547-577, 656-698), as used by every BEM arch through forward_type "v05_noz"
+(basicsr/archs/UNet_arch.py:205-228).
+
+``ss2d_core`` is the function form (parameters passed explicitly) so it can be patched into the reference's SS2D
+(patch.py) and used by the mirror modules in network.py.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .csm import cross_merge_fn, cross_scan_fn
+from .selective_scan import selective_scan_fn
+
+_SCAN_MODES = dict(cross2d=0, unidi=1, bidi=2)
+
+
+def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias=None, out_norm=None,
+              scan_mode="cross2d", force_fp32=False, ssoflex=True, delta_softplus=True):
+    """x: (B, D, H, W) -> y: (B, D, H, W) (after `out_norm` when given), following vmamba.py:656-698 line by line:
+    cross_scan -> x_proj (grouped 1x1) -> split dt/B/C -> dt_proj (grouped 1x1) -> selective scan -> cross_merge."""
+    if scan_mode not in _SCAN_MODES:
+        raise RuntimeError(f"ss2d_core: scan_mode {scan_mode!r} is not built (cross2d / unidi / bidi)")
+    scans = _SCAN_MODES[scan_mode]
+    B, D, H, W = x.shape
+    N = A_logs.shape[1]
+    K, _, R = dt_projs_weight.shape
+    L = H * W
+    xs = cross_scan_fn(x, in_channel_first=True, out_channel_first=True, scans=scans)            # (B, 4, D, L)
+    x_dbl = F.conv1d(xs.view(B, -1, L), x_proj_weight.view(-1, D, 1),
+                     bias=(x_proj_bias.view(-1) if x_proj_bias is not None else None), groups=K)  # vmamba.py:659
+    x_dbl = x_dbl.view(B, K, -1, L)
+    dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)                                             # vmamba.py:660
+    dts = F.conv1d(dts.contiguous().view(B, -1, L), dt_projs_weight.view(K * D, -1, 1), groups=K)  # vmamba.py:661
+    xs = xs.view(B, -1, L)
+    dts = dts.contiguous().view(B, -1, L)
+    As = -A_logs.to(torch.float).exp()                  # (K * D, N)
+    Dsf = Ds.to(torch.float)
+    delta_bias = dt_projs_bias.view(-1).to(torch.float)
+    # Bs / Cs stay strided views of x_dbl (last-dim stride 1): the scan kernel takes 64-bit strides, the reference
+    # materialises them with .contiguous() (vmamba.py:666-667)
+    if force_fp32:
+        xs, dts, Bs, Cs = (t.to(torch.float32) for t in (xs, dts, Bs, Cs))
+    ys = selective_scan_fn(xs, dts, As, Bs, Cs, Dsf, delta_bias, delta_softplus, ssoflex).view(B, K, -1, H, W)
+    y = cross_merge_fn(ys, in_channel_first=True, out_channel_first=True, scans=scans)             # (B, D, L)
+    y = y.view(B, -1, H, W)
+    if out_norm is not None:
+        y = out_norm(y)
+    return y.to(x.dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# mirror modules (same parameter names / shapes / init as the reference, so state_dicts interchange)
+# ---------------------------------------------------------------------------------------------------------------------
+class Linear2d(nn.Linear):
+    """vmamba.Linear2d (vmamba.py:42-56): a Linear applied as a 1x1 convolution on (B, C, H, W)."""
+
+    def forward(self, x: torch.Tensor):
+        return F.conv2d(x, self.weight[:, :, None, None], self.bias)
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        state_dict[prefix + "weight"] = state_dict[prefix + "weight"].view(self.weight.shape)
+        return super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+
+
+class LayerNorm2d(nn.LayerNorm):
+    """vmamba.LayerNorm2d (vmamba.py:59-64)."""
+
+    def forward(self, x: torch.Tensor):
+        x = x.permute(0, 2, 3, 1)
+        x = F.layer_norm(x, self.normalized_shape, self.weight, self.bias, self.eps)
+        return x.permute(0, 3, 1, 2)
+
+
+def _dt_init(dt_rank, d_inner, dt_scale=1.0, dt_init="random", dt_min=0.001, dt_max=0.1, dt_init_floor=1e-4):
+    """mamba_init.dt_init (vmamba.py:224-249)"""
+    dt_proj = nn.Linear(dt_rank, d_inner, bias=True)
+    std = dt_rank ** -0.5 * dt_scale
+    if dt_init == "constant":
+        nn.init.constant_(dt_proj.weight, std)
+    elif dt_init == "random":
+        nn.init.uniform_(dt_proj.weight, -std, std)
+    else:
+        raise NotImplementedError
+    dt = torch.exp(torch.rand(d_inner) * (math.log(dt_max) - math.log(dt_min)) + math.log(dt_min)).clamp(min=dt_init_floor)
+    inv_dt = dt + torch.log(-torch.expm1(-dt))
+    with torch.no_grad():
+        dt_proj.bias.copy_(inv_dt)
+    return dt_proj
+
+
+class SS2D(nn.Module):
+    """The SS2D configuration every BEM arch instantiates: forward_type "v05_noz", channel_first, ssm_init "v0"
+    (vmamba.py:438-545 __initv2__, :700-716 forwardv2). Other forward types are out of scope and raise."""
+
+    def __init__(self, d_model=96, d_state=16, ssm_ratio=2.0, dt_rank="auto", act_layer=nn.SiLU, d_conv=3, conv_bias=True,
+                 dropout=0.0, bias=False, dt_min=0.001, dt_max=0.1, dt_init="random", dt_scale=1.0, dt_init_floor=1e-4,
+                 initialize="v0", forward_type="v05_noz", channel_first=True, **kwargs):
+        super().__init__()
+        if forward_type != "v05_noz" or not channel_first or initialize != "v0":
+            raise NotImplementedError("bem_b200.SS2D mirrors forward_type='v05_noz', channel_first=True, initialize='v0' only")
+        d_inner = int(ssm_ratio * d_model)
+        dt_rank = math.ceil(d_model / 16) if dt_rank == "auto" else dt_rank
+        self.channel_first = True
+        self.with_dconv = d_conv > 1
+        self.disable_z = True
+        k_group = 4
+        self.out_norm = LayerNorm2d(d_inner)
+        self.in_proj = Linear2d(d_model, d_inner, bias=bias)
+        self.act = act_layer()
+        if self.with_dconv:
+            self.conv2d = nn.Conv2d(d_inner, d_inner, groups=d_inner, bias=conv_bias, kernel_size=d_conv,
+                                    padding=(d_conv - 1) // 2)
+        x_proj = [nn.Linear(d_inner, dt_rank + d_state * 2, bias=False) for _ in range(k_group)]
+        self.x_proj_weight = nn.Parameter(torch.stack([t.weight for t in x_proj], dim=0))   # (K, R + 2N, D)
+        self.out_act = nn.Identity()
+        self.out_proj = Linear2d(d_inner, d_model, bias=bias)
+        self.dropout = nn.Dropout(dropout) if dropout > 0.0 else nn.Identity()
+        dt_projs = [_dt_init(dt_rank, d_inner, dt_scale, dt_init, dt_min, dt_max, dt_init_floor) for _ in range(k_group)]
+        self.dt_projs_weight = nn.Parameter(torch.stack([t.weight for t in dt_projs], dim=0))   # (K, D, R)
+        self.dt_projs_bias = nn.Parameter(torch.stack([t.bias for t in dt_projs], dim=0))       # (K, D)
+        A = torch.arange(1, d_state + 1, dtype=torch.float32).view(1, -1).repeat(d_inner, 1).contiguous()
+        self.A_logs = nn.Parameter(torch.log(A)[None].repeat(k_group, 1, 1).flatten(0, 1).contiguous())   # (K*D, N)
+        self.Ds = nn.Parameter(torch.ones(k_group * d_inner))
+        self.A_logs._no_weight_decay = True
+        self.Ds._no_weight_decay = True
+
+    def forward_core(self, x):
+        return ss2d_core(x, self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias, self.A_logs, self.Ds,
+                         x_proj_bias=getattr(self, "x_proj_bias", None), out_norm=self.out_norm)
+
+    def forward(self, x: torch.Tensor, **kwargs):
+        x = self.in_proj(x)
+        if self.with_dconv:
+            x = self.conv2d(x)
+        x = self.act(x)
+        y = self.forward_core(x)
+        y = self.out_act(y)
+        return self.dropout(self.out_proj(y))

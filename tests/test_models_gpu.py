@@ -1,0 +1,129 @@
+"""SS2D core / VSSBlock / stage-1 Network on the sm_100a operators vs outputs recorded from the reference models
+(tests/golden/models.npz: same state_dict, same input, Bayesian forward replayed with the reference's eps)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import nmax_err
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-5   # a chain of ~10 fp32 layers; each operator alone is held to 1e-5 in its own test
+
+
+def _sd(golden, prefix):
+    p = prefix + "/"
+    return {k[len(p):]: torch.tensor(golden[k]) for k in golden.z.files if k.startswith(p)}
+
+
+@pytest.mark.parametrize("tag,dim,ds", [("ss2d_n1", 8, 1), ("ss2d_n4", 16, 4)])
+def test_ss2d_core_and_block(golden_models, tag, dim, ds):
+    """forward_corev2 (vmamba.py:656-698), SS2D.forwardv2 (:700-716) and VSSBlock._forwardv01 (:1319-1334)"""
+    from bem_b200 import network
+    blk = network.VSSBlock(hidden_dim=dim, ssm_d_state=ds, ssm_ratio=1, ssm_conv_bias=False, mlp_ratio=4)
+    blk.load_state_dict(_sd(golden_models, f"{tag}/sd"), strict=True)
+    blk = blk.cuda().eval()
+    x = torch.tensor(golden_models[f"{tag}/x"], device="cuda")
+    with torch.no_grad(), torch.backends.cudnn.flags(allow_tf32=False):
+        core = blk.op.forward_core(x)
+        op = blk.op(x)
+        full = blk(x)
+    assert nmax_err(core.cpu().numpy(), golden_models[f"{tag}/core"]) < TOL
+    assert nmax_err(op.cpu().numpy(), golden_models[f"{tag}/op"]) < TOL
+    assert nmax_err(full.cpu().numpy(), golden_models[f"{tag}/block"]) < TOL
+
+
+def _small_net():
+    from bem_b200 import network
+    return network.Network(stage=1, n_feat=8, num_blocks=[1, 1, 1], d_state=[1, 1, 1], ssm_ratio=1, mlp_ratio=4,
+                           mlp_type="gdmlp", use_pixelshuffle=True)
+
+
+def test_network_plain_state_dict_and_forward(golden_models):
+    net = _small_net()
+    sd = _sd(golden_models, "net/sd_plain")
+    assert set(sd.keys()) == set(net.state_dict().keys())
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    x = torch.tensor(golden_models["net/x"], device="cuda")
+    with torch.no_grad(), torch.backends.cudnn.flags(allow_tf32=False):
+        y = net(x)[-1]
+    assert nmax_err(y.cpu().numpy(), golden_models["net/out_det_plain"]) < TOL
+
+
+def test_network_bayesian_conversion_and_mc_forward(golden_models):
+    """convert2bnn_selective as ConditionGenerator does it (condition_generator_model.py:51-59): same layer set, same
+    checkpoint keys, deterministic output, and the stochastic output when every layer replays the reference's eps"""
+    from bem_b200 import bayesian
+    net = _small_net()
+    bayesian.convert2bnn_selective(net, {"sigma_init": 0.05, "decay": 0.998, "pretrain": False})
+    mods = dict(net.named_modules())
+    names = [n for n, m in net.named_modules() if hasattr(m, "deterministic")]
+    assert names == list(golden_models["net/bnn_layers"])
+    assert [type(mods[n]).__name__ for n in names] == list(golden_models["net/bnn_types"])
+    sd = _sd(golden_models, "net/sd_bnn")
+    assert set(sd.keys()) == set(net.state_dict().keys())
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    x = torch.tensor(golden_models["net/x"], device="cuda")
+    bayesian.set_prediction_type(net, deterministic=True)
+    with torch.no_grad(), torch.backends.cudnn.flags(allow_tf32=False):
+        y = net(x)[-1]
+    assert nmax_err(y.cpu().numpy(), golden_models["net/out_det_bnn"]) < TOL
+    bayesian.set_prediction_type(net, deterministic=False)
+    for n in names:
+        inj = {"weight": torch.tensor(golden_models[f"net/eps/{n}.eps_weight"], device="cuda")}
+        if f"net/eps/{n}.eps_bias" in golden_models:
+            inj["bias"] = torch.tensor(golden_models[f"net/eps/{n}.eps_bias"], device="cuda")
+        mods[n]._injected_eps = inj
+    with torch.no_grad(), torch.backends.cudnn.flags(allow_tf32=False):
+        y = net(x)[-1]
+    assert nmax_err(y.cpu().numpy(), golden_models["net/out_mc"]) < TOL
+
+
+def test_mc_sampler_is_batch_and_shard_invariant():
+    """philox eps: sample i is the same prediction whether drawn alone, in a batch, or as part of another shard"""
+    from bem_b200 import mc, network
+    torch.manual_seed(0)
+    net = network.build_bayesian_model()
+    net = net.cuda().eval()
+    x = torch.rand(1, 3, 32, 48, device="cuda")
+    one = mc.MCSampler(net, seed=7, batch=1)
+    four = mc.MCSampler(net, seed=7, batch=4)
+    with torch.backends.cudnn.flags(allow_tf32=False):
+        a = one.sample(x, [0, 1, 2, 3, 4, 5])
+        b = four.sample(x, [0, 1, 2, 3, 4, 5])
+        c = one.sample(x, mc.shard_samples(6, 1, 2))      # rank 1 of 2 -> samples 1, 3, 5
+    assert a.shape == (6, 3, 32, 48)
+    assert nmax_err(b.cpu().numpy(), a.cpu().numpy()) < 1e-5
+    assert nmax_err(c.cpu().numpy(), a[[1, 3, 5]].cpu().numpy()) < 1e-6
+    assert float((a[0] - a[1]).abs().max()) > 0          # samples differ
+    res = mc.mc_infer(one, x, 6, monte_carlo_mean=True)
+    scores = mc.default_score(a)
+    assert res["index"] == int(torch.argmax(scores))     # no ties here
+    assert torch.equal(res["best"], a[res["index"]])
+    assert nmax_err(res["mean"].cpu().numpy(), a.mean(0).clamp(0, 1).cpu().numpy()) < 1e-6
+
+
+def test_select_best_golden(golden_select):
+    """bit-exact index: first max / first min with Python's NaN behaviour (Enhancement/eval.py:270-274)"""
+    from bem_b200 import mc
+    for name in golden_select.cases():
+        c = golden_select.case(name)
+        s = torch.tensor(c["scores"], device="cuda")
+        idx, val = mc.select_best(s)
+        assert int(idx.item()) == int(c["argmax"]), name
+        idx2, _ = mc.select_best(s, take_min=True)
+        assert int(idx2.item()) == int(c["argmin"]), name
+        v = float(val.item())
+        ref = float(c["scores"][int(c["argmax"])])
+        assert (v != v and ref != ref) or v == ref
+
+
+def test_select_best_large_ties():
+    from bem_b200 import mc
+    s = torch.zeros(5000, device="cuda")
+    s[1234] = 3.0
+    s[4000] = 3.0
+    assert int(mc.select_best(s)[0].item()) == 1234
+    assert int(mc.select_best(-s, take_min=True)[0].item()) == 1234
+    assert int(mc.select_best(torch.zeros(777, device="cuda"))[0].item()) == 0
