@@ -139,3 +139,55 @@ def scan_error_word(device: torch.device) -> int:
     if ws is None:
         return 0
     return int(ws[4:8].view(torch.int32).item())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# launch accounting (bench.py): every C-ABI call goes through `launch`, which counts kernels and, when a profile is armed,
+# brackets the call with CUDA events recorded on the launching stream.
+# ---------------------------------------------------------------------------------------------------------------------
+class _Profile:
+    def __init__(self):
+        self.launches = 0          # kernels of libbem_b200.so launched since the last reset
+        self.armed = False
+        self.records = []          # (name, key, start_event, end_event, algorithmic_bytes)
+
+    def reset(self, armed=False):
+        self.launches = 0
+        self.armed = armed
+        self.records = []
+
+    def summary(self):
+        """{name: dict(calls, ms, bytes)} — synchronises; call after the timed region."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, key, e0, e1, nbytes in self.records:
+            d = out.setdefault(name, dict(calls=0, ms=0.0, bytes=0, by_key={}))
+            ms = e0.elapsed_time(e1)
+            d["calls"] += 1
+            d["ms"] += ms
+            d["bytes"] += nbytes
+            k = d["by_key"].setdefault(str(key), dict(calls=0, ms=0.0, bytes=0))
+            k["calls"] += 1
+            k["ms"] += ms
+            k["bytes"] += nbytes
+        return out
+
+
+profile = _Profile()
+
+
+def launch(name, fn, params, device, key=None, nbytes=0, kernels=1):
+    """run one C-ABI entry point on `device`'s current stream, check its return code, account for it"""
+    with torch.cuda.device(device):
+        st = stream_ptr(device)
+        if profile.armed:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            code = fn(C.byref(params), st)
+            e1.record()
+            profile.records.append((name, key, e0, e1, nbytes))
+        else:
+            code = fn(C.byref(params), st)
+    profile.launches += kernels
+    check(code, name)

@@ -112,7 +112,9 @@ class Conv2dReparameterization(BaseLayer_):
             # inference fast path: the sampled weight never exists in memory
             eps_w = self._draw_eps("weight", eps_weight)
             b = self._sample("bias", eps_bias)[0] if self.bias else None
-            return BF.pointwise_conv_sampled(input, self.mu_weight, self.rho_weight, eps_w, b, S)
+            oc, ic = self.out_channels, self.in_channels
+            return BF.pointwise_conv_sampled(input, self.mu_weight.view(oc, ic), self.rho_weight.view(oc, ic),
+                                             eps_w.reshape(S, oc, ic), b, S)
         w, _ = self._sample("weight", eps_weight)
         b = self._sample("bias", eps_bias)[0] if self.bias else None
         return self._conv(input, w, b, S)

@@ -9,8 +9,6 @@ data gradients; the tiny weight-gradient reductions use torch ops.
 """
 from __future__ import annotations
 
-import ctypes as C
-
 import torch
 
 from .. import _lib
@@ -38,8 +36,7 @@ def _sample_raw(mu, rho, eps, n_samples, seed, stream_id, sample0, want_eps):
     p = _lib.BemBayesSampleParams(numel=numel, n_samples=n_samples, mu=_lib.ptr(mu), rho=_lib.ptr(rho), eps=_lib.ptr(eps),
                                   w=_lib.ptr(w), eps_out=_lib.ptr(eps_out), seed=int(seed) & (2 ** 64 - 1),
                                   stream_id=int(stream_id), sample0=int(sample0))
-    with torch.cuda.device(mu.device):
-        _lib.check(lib.bem_bayes_sample(C.byref(p), _lib.stream_ptr(mu.device)), "bayes_sample")
+    _lib.launch("bayes_sample", lib.bem_bayes_sample, p, mu.device, nbytes=4 * numel * (2 + n_samples))
     used = eps.view_as(w) if eps is not None else eps_out
     return w, used
 
@@ -83,8 +80,8 @@ def _pointwise_raw(x, w=None, bias=None, mu=None, rho=None, eps=None, n_samples=
     p = _lib.BemBayesPointwiseParams(n_samples=n_samples, batch=batch, cin=cin, cout=cout, P=P, x=_lib.ptr(x),
                                      w=_lib.ptr(w), mu=_lib.ptr(mu), rho=_lib.ptr(rho), eps=_lib.ptr(eps),
                                      bias=_lib.ptr(bias), out=_lib.ptr(out))
-    with torch.cuda.device(x.device):
-        _lib.check(lib.bem_bayes_pointwise(C.byref(p), _lib.stream_ptr(x.device)), "bayes_pointwise")
+    _lib.launch("bayes_pointwise", lib.bem_bayes_pointwise, p, x.device, key=(batch, cin, cout, P),
+                nbytes=4 * batch * P * (cin + cout))
     return out
 
 
@@ -138,8 +135,7 @@ def _depthwise_raw(x, w, bias, n_samples):
     out = torch.empty_like(x)
     p = _lib.BemBayesDepthwiseParams(n_samples=n_samples, batch=batch, C=Cc, H=H, W=W, K=K, x=_lib.ptr(x), w=_lib.ptr(w),
                                      bias=_lib.ptr(bias), out=_lib.ptr(out))
-    with torch.cuda.device(x.device):
-        _lib.check(lib.bem_bayes_depthwise(C.byref(p), _lib.stream_ptr(x.device)), "bayes_depthwise")
+    _lib.launch("bayes_depthwise", lib.bem_bayes_depthwise, p, x.device, key=(batch, Cc, H, W), nbytes=8 * x.numel())
     return out
 
 

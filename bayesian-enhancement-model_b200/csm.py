@@ -7,8 +7,6 @@ uses it to pick its PyTorch implementation, which computes the same thing bit fo
 """
 from __future__ import annotations
 
-import ctypes as C
-
 import torch
 
 from . import _lib
@@ -21,8 +19,7 @@ def _launch(fn, what, src, dst, B, Cc, H, W, img_cf, seq_cf, one_by_one, scans):
     p = _lib.BemCsmParams(B=B, C=Cc, H=H, W=W, dtype=_lib.dtype_code(src.dtype), img_channel_first=int(img_cf),
                           seq_channel_first=int(seq_cf), one_by_one=int(one_by_one), scans=int(scans),
                           src=_lib.ptr(src), dst=_lib.ptr(dst))
-    with torch.cuda.device(src.device):
-        _lib.check(fn(C.byref(p), _lib.stream_ptr(src.device)), what)
+    _lib.launch(what, fn, p, src.device, key=(B, Cc, H, W), nbytes=src.numel() * src.element_size() + dst.numel() * dst.element_size())
 
 
 def _img_dims(x, channel_first, one_by_one):

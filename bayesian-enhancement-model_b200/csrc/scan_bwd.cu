@@ -19,6 +19,7 @@ namespace bem {
 template <typename T, typename DT, int ITEMS, int NW, bool N1>
 __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1) scan_bwd_kernel(const ScanBwdArgs p) {
     constexpr int CL = 32 * ITEMS;
+    constexpr bool kAcc = sizeof(T) == 4;   // fp32 inputs: <= 1 ulp decay factors (scan_common.cuh decay_m1)
     constexpr int ROW_SLOT = 2 * CL * (int)sizeof(T) + CL * (int)sizeof(DT);   // [u | delta | dout]; du, ddelta overlay u, delta
     extern __shared__ __align__(128) unsigned char smem[];
 
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
 
             if constexpr (N1) {
                 const float Av = p.A[d * p.A_ds];
-                const float A2 = Av * kLog2e;
+                const float A2 = Av;
                 float a[ITEMS], h[ITEMS], gl[ITEMS], rp[ITEMS];
                 float Pth, Rth;
                 {
@@ -215,15 +216,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                     for (int i = 0; i < ITEMS; ++i) {
                         float x = dl[i] + bias;
                         if (p.softplus) x = softplus_f(x);
-                        float ai = ex2_approx(x * A2);
+                        float ei = decay_m1<kAcc>(x * A2);
                         float bi = x * uv[i] * Bv[i];
                         if (partial && e0 + i >= len) {
-                            ai = 1.f;
+                            ei = 0.f;
                             bi = 0.f;
                         }
-                        a[i] = ai;
-                        V = fmaf(ai, V, bi);
-                        P *= ai;
+                        a[i] = ei;   // decay minus one
+                        decay_step(ei, bi, P, V);
                         h[i] = V;    // local inclusive state
                         rp[i] = P;   // local inclusive decay (temporarily)
                     }
@@ -249,8 +249,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                         const float cd = (partial && e0 + i >= len) ? 0.f : Cv[i] * dy[i];
                         gl[i] = cd + r;   // g_t with zero incoming adjoint
                         rp[i] = RP;       // d g_t / d incoming
-                        r = a[i] * gl[i];
-                        RP *= a[i];
+                        r = fmaf(a[i], gl[i], gl[i]);
+                        RP = fmaf(a[i], RP, RP);
                     }
                     Rth = r;
                 }
@@ -351,17 +351,18 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                 // pass 1: chunk aggregates of the reverse scan, one state per lane
                 float aggP = 1.f, aggR = 0.f;
                 for (int n = 0; n < N; ++n) {
-                    const float A2 = p.A[d * p.A_ds + n * p.A_ns] * kLog2e;
+                    const float A2 = p.A[d * p.A_ds + n * p.A_ns];
                     float Cv[ITEMS];
                     lds_items<T, ITEMS>(sC + n * CL + e0, Cv);
                     float r = 0.f, RP = 1.f;
 #pragma unroll
                     for (int i = ITEMS - 1; i >= 0; --i) {
                         const bool valid = !(partial && e0 + i >= len);
-                        const float ai = valid ? ex2_approx(dl[i] * A2) : 1.f;
+                        const float ei = valid ? decay_m1<kAcc>(dl[i] * A2) : 0.f;
                         const float cd = valid ? Cv[i] * dy[i] : 0.f;
-                        r = ai * (cd + r);
-                        RP *= ai;
+                        const float gsum = cd + r;
+                        r = fmaf(ei, gsum, gsum);
+                        RP = fmaf(ei, RP, RP);
                     }
                     warp_scan_rev(RP, r, lane);
                     const float Pa = __shfl_sync(FULL, RP, 0), Ra = __shfl_sync(FULL, r, 0);
@@ -387,18 +388,17 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                 // pass 2: per state, forward states from the carry, reverse adjoints from the look-back
                 for (int n = 0; n < N; ++n) {
                     const float Av = p.A[d * p.A_ds + n * p.A_ns];
-                    const float A2 = Av * kLog2e;
+                    const float A2 = Av;
                     float a[ITEMS], h[ITEMS], gl[ITEMS], rp[ITEMS], Bv[ITEMS];
                     lds_items<T, ITEMS>(sB + n * CL + e0, Bv);
                     float P = 1.f, V = 0.f;
 #pragma unroll
                     for (int i = 0; i < ITEMS; ++i) {
                         const bool valid = !(partial && e0 + i >= len);
-                        const float ai = valid ? ex2_approx(dl[i] * A2) : 1.f;
+                        const float ei = valid ? decay_m1<kAcc>(dl[i] * A2) : 0.f;
                         const float bi = valid ? dl[i] * uv[i] * Bv[i] : 0.f;
-                        a[i] = ai;
-                        V = fmaf(ai, V, bi);
-                        P *= ai;
+                        a[i] = ei;   // decay minus one
+                        decay_step(ei, bi, P, V);
                         h[i] = V;
                         rp[i] = P;
                     }
@@ -423,8 +423,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                             const float cd = valid ? Cv[i] * dy[i] : 0.f;
                             gl[i] = cd + r;
                             rp[i] = RP;
-                            r = a[i] * gl[i];
-                            RP *= a[i];
+                            r = fmaf(a[i], gl[i], gl[i]);
+                            RP = fmaf(a[i], RP, RP);
                         }
                     }
                     float Pr = Pth, Rr = r;

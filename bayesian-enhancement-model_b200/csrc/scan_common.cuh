@@ -94,6 +94,29 @@ __device__ __forceinline__ float lg2_approx(float x) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// Decay of the recurrence, returned as e = exp(y) - 1 with y = delta * A <= 0, and applied as h <- fma(e, h, h) + b.
+// Why not a = exp(y): the recurrence multiplies ~1/(1-a) consecutive decays. (i) A correlated 2-ulp error of
+// ex2.approx on near-unit decays is amplified to ~1e-4 of the state in slow channels (|A| small); (ii) even a
+// correctly rounded a = 1 - 4e-5 carries only ~10 significant bits of the decay RATE. For y > -1/8, e comes from a
+// degree-5 Taylor polynomial of expm1 (truncation < 4.5e-8 relative), so the rate keeps full fp32 precision; faster
+// decays have a short memory and use the single MUFU instruction (a - 1 is exact for a in [0.5, 1]).
+// kAccurate = false (16-bit inputs, 1e-2 tolerance) always takes the MUFU branch.
+template <bool kAccurate>
+__device__ __forceinline__ float decay_m1(float y) {
+    const float fast = ex2_approx(y * kLog2e) - 1.f;
+    if constexpr (!kAccurate) return fast;
+    float p = fmaf(y, 1.f / 120.f, 1.f / 24.f);
+    p = fmaf(y, p, 1.f / 6.f);
+    p = fmaf(y, p, 0.5f);
+    const float e = fmaf(y * y, p, y);
+    return y > -0.125f ? e : fast;
+}
+// one step of the affine map composition with the decay given as e = a - 1: (P, V) <- (a P, a V + b)
+__device__ __forceinline__ void decay_step(float e, float b, float& P, float& V) {
+    V = fmaf(e, V, V) + b;
+    P = fmaf(e, P, P);
+}
+
 // softplus(x) = max(x,0) + log1p(exp(-|x|)); identical to the reference's `x <= 20 ? log1pf(expf(x)) : x`
 // (cusoflex/selective_scan_fwd_kernel_oflex.cuh:124-126, F.softplus threshold 20) to < 2e-7 absolute: beyond 20 the
 // correction term is below 2.1e-9.

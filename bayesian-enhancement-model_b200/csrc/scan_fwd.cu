@@ -19,6 +19,7 @@ namespace bem {
 template <typename T, typename OutT, int ITEMS, int NW, bool N1>
 __global__ void __launch_bounds__((NW + 1) * 32) scan_fwd_kernel(const ScanFwdArgs p) {
     constexpr int CL = 32 * ITEMS;
+    constexpr bool kAcc = sizeof(T) == 4;   // fp32 inputs: <= 1 ulp decay factors (scan_common.cuh decay_m1)
     constexpr int ROW_SLOT = 2 * CL * (int)sizeof(T);   // [u chunk | delta chunk]; y (OutT) is written over it
     static_assert(CL * sizeof(OutT) <= (size_t)ROW_SLOT, "output overlay must fit the row slot");
     extern __shared__ __align__(128) unsigned char smem[];
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__((NW + 1) * 32) scan_fwd_kernel(const ScanFwdAr
             float y[ITEMS];
 
             if constexpr (N1) {
-                const float A2 = p.A[d * p.A_ds] * kLog2e;
+                const float A2 = p.A[d * p.A_ds];
                 float cumA[ITEMS], hloc[ITEMS];
                 {
                     float Bv[ITEMS];
@@ -195,14 +196,13 @@ __global__ void __launch_bounds__((NW + 1) * 32) scan_fwd_kernel(const ScanFwdAr
                     float P = 1.f, V = 0.f;
 #pragma unroll
                     for (int i = 0; i < ITEMS; ++i) {
-                        float a = ex2_approx(dl[i] * A2);
+                        float e = decay_m1<kAcc>(dl[i] * A2);
                         float b = dl[i] * uv[i] * Bv[i];
                         if (partial && e0 + i >= len) {   // identity padding so the carried state stays exact
-                            a = 1.f;
+                            e = 0.f;
                             b = 0.f;
                         }
-                        V = fmaf(a, V, b);
-                        P *= a;
+                        decay_step(e, b, P, V);
                         hloc[i] = V;
                         cumA[i] = P;
                     }
@@ -249,20 +249,19 @@ __global__ void __launch_bounds__((NW + 1) * 32) scan_fwd_kernel(const ScanFwdAr
                 }
                 float aggP = 1.f, aggV = 0.f;   // lane n keeps the chunk aggregate of state n
                 for (int n = 0; n < N; ++n) {
-                    const float A2 = p.A[d * p.A_ds + n * p.A_ns] * kLog2e;
+                    const float A2 = p.A[d * p.A_ds + n * p.A_ns];
                     float Bv[ITEMS];
                     lds_items<T, ITEMS>(sB + n * CL + e0, Bv);
                     float P = 1.f, V = 0.f;
 #pragma unroll
                     for (int i = 0; i < ITEMS; ++i) {
-                        float a = ex2_approx(dl[i] * A2);
+                        float e = decay_m1<kAcc>(dl[i] * A2);
                         float b = du[i] * Bv[i];
                         if (partial && e0 + i >= len) {
-                            a = 1.f;
+                            e = 0.f;
                             b = 0.f;
                         }
-                        V = fmaf(a, V, b);
-                        P *= a;
+                        decay_step(e, b, P, V);
                     }
                     warp_scan_fwd(P, V, lane);
                     const float Pa = __shfl_sync(FULL, P, 31), Va = __shfl_sync(FULL, V, 31);
@@ -293,21 +292,20 @@ __global__ void __launch_bounds__((NW + 1) * 32) scan_fwd_kernel(const ScanFwdAr
                     }
                 }
                 for (int n = 0; n < N; ++n) {
-                    const float A2 = p.A[d * p.A_ds + n * p.A_ns] * kLog2e;
+                    const float A2 = p.A[d * p.A_ds + n * p.A_ns];
                     float Bv[ITEMS];
                     lds_items<T, ITEMS>(sB + n * CL + e0, Bv);
                     float cumA[ITEMS], hloc[ITEMS];
                     float P = 1.f, V = 0.f;
 #pragma unroll
                     for (int i = 0; i < ITEMS; ++i) {
-                        float a = ex2_approx(dl[i] * A2);
+                        float e = decay_m1<kAcc>(dl[i] * A2);
                         float b = du[i] * Bv[i];
                         if (partial && e0 + i >= len) {
-                            a = 1.f;
+                            e = 0.f;
                             b = 0.f;
                         }
-                        V = fmaf(a, V, b);
-                        P *= a;
+                        decay_step(e, b, P, V);
                         hloc[i] = V;
                         cumA[i] = P;
                     }

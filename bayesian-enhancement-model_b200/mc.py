@@ -32,6 +32,7 @@ def select_best(scores: torch.Tensor, take_min: bool = False):
     with torch.cuda.device(s.device):
         _lib.check(lib.bem_select_best(_lib.ptr(s), s.numel(), int(bool(take_min)), _lib.ptr(idx), _lib.ptr(val),
                                        _lib.stream_ptr(s.device)), "select_best")
+    _lib.profile.launches += 1
     return idx, val
 
 

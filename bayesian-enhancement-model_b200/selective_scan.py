@@ -10,8 +10,6 @@ Every path ends in the sm_100a kernels; CPU tensors raise.
 """
 from __future__ import annotations
 
-import ctypes as C
-
 import torch
 
 from . import _lib
@@ -81,8 +79,9 @@ def fwd(u, delta, A, B, C, D_, delta_bias_, delta_softplus, nrows=1, out_float=T
         A_ds=A.stride(0), A_ns=A.stride(1),
         B_bs=B.stride(0), B_gs=B.stride(1), B_ns=B.stride(2), C_bs=C.stride(0), C_gs=C.stride(1), C_ns=C.stride(2),
         out_bs=out.stride(0), out_ds=out.stride(1), workspace=_lib.ptr(ws), workspace_bytes=ws.numel())
-    with torch.cuda.device(dev):
-        _lib.check(lib.bem_scan_fwd(C.byref(p), _lib.stream_ptr(dev)), "scan_fwd")
+    es, eo = u.element_size(), out.element_size()
+    nbytes = batch * dim * seqlen * (2 * es + eo) + 2 * batch * n_groups * dstate * seqlen * es   # SURVEY 8d, boundary form
+    _lib.launch("scan_fwd", lib.bem_scan_fwd, p, dev, key=(batch, dim, dstate, seqlen, str(u.dtype)), nbytes=nbytes)
     return [out, x]
 
 
@@ -123,8 +122,9 @@ def bwd(u, delta, A, B, C, D_, delta_bias_, dout, x_, delta_softplus, nrows=1):
         B_bs=B.stride(0), B_gs=B.stride(1), B_ns=B.stride(2), C_bs=C.stride(0), C_gs=C.stride(1), C_ns=C.stride(2),
         dout_bs=dout.stride(0), dout_ds=dout.stride(1), du_bs=du.stride(0), du_ds=du.stride(1),
         ddelta_bs=ddelta.stride(0), ddelta_ds=ddelta.stride(1), workspace=_lib.ptr(ws), workspace_bytes=ws.numel())
-    with torch.cuda.device(dev):
-        _lib.check(lib.bem_scan_bwd(C.byref(p), _lib.stream_ptr(dev)), "scan_bwd")
+    es, eo = u.element_size(), dout.element_size()
+    nbytes = batch * dim * seqlen * (4 * es + eo) + 4 * batch * n_groups * dstate * seqlen * es
+    _lib.launch("scan_bwd", lib.bem_scan_bwd, p, dev, key=(batch, dim, dstate, seqlen, str(u.dtype)), nbytes=nbytes)
     return [du, ddelta, dA, dB.to(B.dtype), dC.to(C.dtype), dD, ddelta_bias]   # casts as in selective_scan_oflex.cpp:356
 
 

@@ -94,8 +94,8 @@ def test_mc_sampler_is_batch_and_shard_invariant():
         b = four.sample(x, [0, 1, 2, 3, 4, 5])
         c = one.sample(x, mc.shard_samples(6, 1, 2))      # rank 1 of 2 -> samples 1, 3, 5
     assert a.shape == (6, 3, 32, 48)
-    assert nmax_err(b.cpu().numpy(), a.cpu().numpy()) < 1e-5
-    assert nmax_err(c.cpu().numpy(), a[[1, 3, 5]].cpu().numpy()) < 1e-6
+    assert nmax_err(b.cpu().numpy(), a.cpu().numpy()) < 5e-5   # library convs pick batch-size dependent algorithms
+    assert nmax_err(c.cpu().numpy(), a[[1, 3, 5]].cpu().numpy()) < 5e-5   # eps is bit-identical (test_bayes_gpu); library convs are not bitwise run-to-run
     assert float((a[0] - a[1]).abs().max()) > 0          # samples differ
     res = mc.mc_infer(one, x, 6, monte_carlo_mean=True)
     scores = mc.default_score(a)

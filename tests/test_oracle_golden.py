@@ -135,3 +135,23 @@ def test_select_matches_python_list_index(golden_select):
         c = golden_select.case(name)
         assert oracle.select_best_oracle(c["scores"]) == int(c["argmax"]), name
         assert oracle.select_best_oracle(c["scores"], take_min=True) == int(c["argmin"]), name
+
+
+def _sd(golden, prefix):
+    p = prefix + "/"
+    return {k[len(p):]: golden[k] for k in golden.z.files if k.startswith(p)}
+
+
+def test_network_oracle_matches_reference_model(golden_models):
+    """oracle/network.py (the CPU baseline of bench.py) against the REAL reference Network: plain weights, Bayesian
+    weights in deterministic mode, and the stochastic forward replaying the reference's eps"""
+    from oracle import network as onet
+    x = golden_models["net/x"]
+    y = onet.network_forward(_sd(golden_models, "net/sd_plain"), x)
+    assert nmax_err(y.numpy(), golden_models["net/out_det_plain"]) < 1e-5
+    sd = _sd(golden_models, "net/sd_bnn")
+    y = onet.network_forward(sd, x, deterministic=True)
+    assert nmax_err(y.numpy(), golden_models["net/out_det_bnn"]) < 1e-5
+    eps = _sd(golden_models, "net/eps")
+    y = onet.network_forward(sd, x, eps=eps)
+    assert nmax_err(y.numpy(), golden_models["net/out_mc"]) < 1e-5
