@@ -7,15 +7,18 @@
 
 namespace bem {
 
-// scan tiling: consumer warps per CTA, positions per lane (=> chunk length 32*ITEMS)
+// scan tiling: consumer warps per CTA, positions per lane (=> tile length 32*ITEMS)
 constexpr int kScanWarps = 8;
-constexpr int kItemsF32 = 12;   // 48 B per lane: conflict-free LDS.128 with a blocked lane layout
-constexpr int kItems16 = 16;    // 32 B per lane for fp16 / bf16 (2-way LDS conflict, but fits 2 CTAs/SM in registers)
-constexpr int kMaxDstate = 16;  // states staged per pass (B/C chunk lives in shared memory)
+constexpr int kItemsF32 = 12;        // 48 B per lane: conflict-free LDS.128 with a blocked lane layout
+constexpr int kItems16 = 16;         // 32 B per lane for fp16 / bf16 (2-way LDS conflict, but fits 2 CTAs/SM in registers)
+constexpr int kFwdItemsF32N1 = 24;   // forward, fp32, dstate 1: 768-position tiles amortise the per-tile overhead
+constexpr int kCarryF32 = 32 * kItemsF32;   // positions per carry chunk of `x` (fp32): the backward kernel's tile
+constexpr int kCarry16 = 32 * kItems16;     // ... for fp16 / bf16
+constexpr int kMaxDstate = 16;       // states staged per pass (B/C chunk lives in shared memory)
 
 inline int scan_items(int dtype) { return dtype == BEM_F32 ? kItemsF32 : kItems16; }
 
-// workspace layout: [0,4) ticket, [4,8) error word, [128, ...) look-back descriptors (16 B each)
+// workspace layout: [0,4) ticket, [4,8) error word, [128, ...) look-back descriptors (16 B each): aggregates, then inclusives
 constexpr int64_t kWsHeader = 128;
 
 struct ScanFwdArgs {
@@ -30,13 +33,16 @@ struct ScanFwdArgs {
     float* x;
     int64_t u_bs, u_ds, dl_bs, dl_ds, A_ds, A_ns, B_bs, B_gs, B_ns, C_bs, C_gs, C_ns, out_bs, out_ds;
     int batch, dim, L, N, G, Dg;
-    int nchunks;       // ceil(L / CL)
+    int nchunks;       // tiles per row = ceil(L / CL)            (filled by the launcher)
+    int nxchunks;      // carry chunks per row of `x` = ceil(L / kCarry)
     int RB;            // row blocks (of kScanWarps rows) per group
     int RT;            // row tiles per chunk = batch * G * RB
     int total_tiles;   // nchunks * RT
     int softplus;
     int stages;
+    int lb_dynamic;    // A/B knob: classic timing-dependent look-back instead of the deterministic one
     uint4* desc;
+    uint4* desc_incl;
     unsigned int* ticket;
     unsigned int* err;
 };
@@ -71,6 +77,7 @@ struct ScanBwdArgs {
     int stages;
     int atomic_bc;     // 1: dB/dC accumulated with atomics (RS > 1 or general dstate), 0: plain stores
     uint4* desc;
+    uint4* desc_incl;
     unsigned int* ticket;
     unsigned int* err;
 };

@@ -19,7 +19,6 @@ int device_sm_count() {
     return cached[dev];
 }
 
-static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 static bool dtype_ok(int dt) { return dt == BEM_F32 || dt == BEM_F16 || dt == BEM_BF16; }
 
@@ -45,10 +44,10 @@ int bem_scan_chunk_len(int dtype) { return dtype_ok(dtype) ? 32 * scan_items(dty
 
 int64_t bem_scan_workspace_bytes(int batch, int dim, int seqlen, int dstate, int dtype) {
     if (!dtype_ok(dtype) || batch <= 0 || dim <= 0 || seqlen <= 0 || dstate <= 0) return 0;
-    const int CL = bem_scan_chunk_len(dtype);
+    const int CL = bem_scan_chunk_len(dtype);   // the finest tiling any kernel uses
     const int64_t nchunks = (seqlen + CL - 1) / CL;
     const int64_t ns = dstate < kMaxDstate ? dstate : kMaxDstate;   // larger dstate runs in passes of kMaxDstate states
-    return kWsHeader + (int64_t)batch * dim * nchunks * ns * 16;
+    return kWsHeader + 2 * (int64_t)batch * dim * nchunks * ns * 16;   // aggregate + inclusive descriptors
 }
 
 int bem_scan_fwd(const BemScanFwdParams* q, void* stream_) {
@@ -73,19 +72,12 @@ int bem_scan_fwd(const BemScanFwdParams* q, void* stream_) {
     a.C_bs = q->C_bs; a.C_gs = q->C_gs; a.C_ns = q->C_ns;
     a.out_bs = q->out_bs; a.out_ds = q->out_ds;
     a.batch = q->batch; a.dim = q->dim; a.L = q->seqlen; a.N = q->dstate; a.G = q->n_groups; a.Dg = q->dim / q->n_groups;
-    a.nchunks = (q->seqlen + CL - 1) / CL;
-    a.RB = (a.Dg + kScanWarps - 1) / kScanWarps;
-    a.RT = a.batch * a.G * a.RB;
-    const int64_t total = (int64_t)a.nchunks * a.RT;
-    if (total > 0x7fffffff) return BEM_ERR_UNSUPPORTED;
-    a.total_tiles = (int)total;
+    a.nxchunks = (q->seqlen + CL - 1) / CL;   // carries of `x`; the tile count is set by the launcher
     a.softplus = q->delta_softplus ? 1 : 0;
     unsigned char* ws = reinterpret_cast<unsigned char*>(q->workspace);
     a.ticket = reinterpret_cast<unsigned int*>(ws);
     a.err = reinterpret_cast<unsigned int*>(ws + 4);
     a.desc = reinterpret_cast<uint4*>(ws + kWsHeader);
-    cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)need, stream);
-    if (e != cudaSuccess) return (int)e;
     return scan_fwd_dispatch(a, q->dtype, q->out_dtype, device_sm_count(), stream);
 }
 
@@ -138,6 +130,7 @@ int bem_scan_bwd(const BemScanBwdParams* q, void* stream_) {
     a.ticket = reinterpret_cast<unsigned int*>(ws);
     a.err = reinterpret_cast<unsigned int*>(ws + 4);
     a.desc = reinterpret_cast<uint4*>(ws + kWsHeader);
+    a.desc_incl = a.desc + (int64_t)a.batch * a.dim * a.nchunks * a.N;
     cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)need, stream);
     if (e != cudaSuccess) return (int)e;
     return scan_bwd_dispatch(a, q->dtype, q->dout_dtype, sms, stream);

@@ -262,16 +262,19 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                     Rs = 0.f;
                 }
                 const float Pa = __shfl_sync(FULL, P, 0), Ra = __shfl_sync(FULL, R, 0);
-                uint4* drow = p.desc + row * p.nchunks;
+                uint4* aggrow = p.desc + row * p.nchunks;
+                uint4* inclrow = p.desc_incl + row * p.nchunks;
+                const LookbackPlan plan = lookback_plan(p.nchunks - 1 - c, p.nchunks);
+                if (lane == 0 && plan.publish_agg) st_desc(aggrow + c, Pa, Ra, DESC_READY);
+                drain_prev();
                 float r_in = 0.f, Psuf = 1.f;
-                if (c + 1 < p.nchunks) {
-                    if (lane == 0 && c > 0) st_desc(drow + c, Pa, Ra, DESC_AGGREGATE);
-                    drain_prev();
-                    const float2 suf = lookback(drow, 1, c, p.nchunks, +1, lane, p.err);
+                if (plan.nlanes) {
+                    const uint4* lb_addr = lookback_addr(aggrow, inclrow, 1, c, +1, plan, lane);
+                    const float2 suf = lookback_finish(lb_addr, lookback_prefetch(lb_addr), plan.nlanes, lane, p.err);
                     Psuf = suf.x;
                     r_in = suf.y;
                 }
-                if (lane == 0 && c > 0) st_desc(drow + c, Pa * Psuf, fmaf(Pa, r_in, Ra), DESC_INCLUSIVE);
+                if (lane == 0 && plan.publish_incl) st_desc(inclrow + c, Pa * Psuf, fmaf(Pa, r_in, Ra), DESC_READY);
                 const float rin_t = fmaf(Ps, r_in, Rs);   // adjoint entering this lane's last position
                 {
                     // outputs, one 128-bit vector of T at a time. du / ddelta overwrite u / delta IN PLACE (same lane,
@@ -371,20 +374,34 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                         aggR = Ra;
                     }
                 }
-                uint4* drow = p.desc + (row * p.nchunks) * N;
+                uint4* aggrow = p.desc + (row * p.nchunks) * N;
+                uint4* inclrow = p.desc_incl + (row * p.nchunks) * N;
+                const LookbackPlan plan = lookback_plan(p.nchunks - 1 - c, p.nchunks);
+                if (lane < N && plan.publish_agg) st_desc(aggrow + (int64_t)c * N + lane, aggP, aggR, DESC_READY);
+                drain_prev();
                 float sufP = 1.f, sufR = 0.f;
-                if (c + 1 < p.nchunks) {
-                    if (lane < N && c > 0) st_desc(drow + (int64_t)c * N + lane, aggP, aggR, DESC_AGGREGATE);
-                    drain_prev();
-                    for (int n = 0; n < N; ++n) {
-                        const float2 suf = lookback(drow + n, N, c, p.nchunks, +1, lane, p.err);
-                        if (lane == n) {
-                            sufP = suf.x;
-                            sufR = suf.y;
+                if (plan.nlanes) {
+                    for (int n0 = 0; n0 < N; n0 += 4) {   // four states' descriptors in flight at a time
+                        const uint4* addr[4];
+                        uint4 first[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            addr[q] = (n0 + q < N) ? lookback_addr(aggrow + n0 + q, inclrow + n0 + q, N, c, +1, plan, lane) : nullptr;
+                            first[q] = lookback_prefetch(addr[q]);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (n0 + q < N) {
+                                const float2 suf = lookback_finish(addr[q], first[q], plan.nlanes, lane, p.err);
+                                if (lane == n0 + q) {
+                                    sufP = suf.x;
+                                    sufR = suf.y;
+                                }
+                            }
                         }
                     }
                 }
-                if (lane < N && c > 0) st_desc(drow + (int64_t)c * N + lane, aggP * sufP, fmaf(aggP, sufR, aggR), DESC_INCLUSIVE);
+                if (lane < N && plan.publish_incl) st_desc(inclrow + (int64_t)c * N + lane, aggP * sufP, fmaf(aggP, sufR, aggR), DESC_READY);
                 // pass 2: per state, forward states from the carry, reverse adjoints from the look-back
                 for (int n = 0; n < N; ++n) {
                     const float Av = p.A[d * p.A_ds + n * p.A_ns];
@@ -581,8 +598,15 @@ static int launch_bwd(ScanBwdArgs& a, int sm_count, cudaStream_t stream) {
     }
     a.stages = stages;
     const int smem_bytes = stages * stage_bytes + red_bytes + stages * (2 * 8 + 8) + 64;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) return (int)e;
+    static int cached_smem[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (cached_smem[dev] != smem_bytes) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) return (int)e;
+        cached_smem[dev] = smem_bytes;
+    }
     const int grid = min(a.total_tiles, sm_count * ctas_per_sm);
     kernel<<<grid, (NW + 1) * 32, smem_bytes, stream>>>(a);
     return (int)cudaGetLastError();

@@ -49,13 +49,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// try_wait with a suspend-time hint (ns): the warp sleeps in hardware instead of re-issuing the probe
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug must not hang the GPU box. On timeout the error word is set and the wait
 // returns; the results are then garbage and the host reports BEM failure from the error word.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned int* err) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {   // ~2 s
+    int tries = 0;
+    while (!mbar_try_wait(bar, parity)) {   // each probe suspends the warp in hardware for a bounded time
+        if (++tries > (1 << 24)) {
             atomicOr(err, 1u);
             return;
         }
@@ -219,38 +231,111 @@ __device__ __forceinline__ void warp_scan_rev(float& P, float& V, int lane) {
 }
 
 // Descriptor status
-enum : uint32_t { DESC_EMPTY = 0, DESC_AGGREGATE = 1, DESC_INCLUSIVE = 2 };
+enum : uint32_t { DESC_EMPTY = 0, DESC_READY = 1 };
+constexpr int kAnchor = 16;   // every kAnchor-th tile of a row also publishes its INCLUSIVE composition
 
-// Decoupled look-back. Tile `c` of a row asks for the composition of all tiles that the flowing value passes
-// through BEFORE it: step = -1 -> tiles c-1, c-2, ... 0 (forward scan); step = +1 -> tiles c+1 ... nchunks-1
-// (reverse scan). desc0 points at this row's descriptor of tile 0 for this state; consecutive tiles are `dstride`
-// descriptors apart. Lane j of the warp inspects the tile j steps further away; a tile marked INCLUSIVE already holds
-// the whole composition beyond it and ends the walk. Returns (P, V) of the composition (identity (1,0) if none).
-__device__ __forceinline__ float2 lookback(const uint4* desc0, int64_t dstride, int c, int nchunks, int step, int lane,
-                                           unsigned int* err) {
-    float runP = 1.f, runV = 0.f;   // tiles already folded; applied AFTER whatever is still to be found
-    int j = c + step;               // nearest unexamined tile
+// Deterministic decoupled look-back.
+// Tile c of a row needs the composition of all tiles the flowing value passes through BEFORE it: step = -1 -> tiles
+// c-1 ... 0 (forward scan), step = +1 -> tiles c+1 ... nt-1 (reverse scan). Every tile publishes its own AGGREGATE
+// (descriptor array `agg`) as soon as its local scan is done, before it looks back itself; tiles whose distance from
+// the sequence start (end, for the reverse scan) is a multiple of kAnchor additionally publish their INCLUSIVE
+// composition (array `incl`) once they know it. Tile c combines, in a FIXED order, the aggregates of the tiles back
+// to an anchor that lies kAnchor .. 2*kAnchor-1 tiles behind it with that anchor's inclusive value: at most 31
+// descriptors, one per lane, one round trip. Choosing an anchor at least kAnchor tiles back means that in steady state
+// it belongs to an earlier wave of tiles and is long finished, so nothing ever waits on a concurrently running tile's
+// look-back (decoupled); and because the association tree depends only on c, results are bit-reproducible (the
+// classic look-back stops at whichever predecessor happens to be inclusive already and is not).
+// dist = number of tiles before c in flow order: c (forward) or nt-1-c (reverse).
+struct LookbackPlan {
+    int nlanes;         // descriptors to read (0 = nothing before this tile)
+    bool anchor_incl;   // the last participating lane reads an anchor's inclusive descriptor (else tile 0's aggregate)
+    bool publish_agg;   // a later tile will read our aggregate
+    bool publish_incl;  // we are an anchor that later tiles will read
+};
+__device__ __forceinline__ LookbackPlan lookback_plan(int dist, int ntiles) {
+    LookbackPlan pl;
+    const int anchor = dist >= kAnchor ? (dist / kAnchor - 1) * kAnchor : -1;   // in [dist-2*kAnchor+1, dist-kAnchor]
+    pl.anchor_incl = anchor >= 0;
+    pl.nlanes = anchor >= 0 ? dist - anchor : dist;   // tiles dist-1 ... anchor (or ... 0)
+    pl.publish_agg = dist + 1 < ntiles;
+    pl.publish_incl = (dist % kAnchor) == 0 && dist + kAnchor < ntiles;
+    return pl;
+}
+// lane j inspects the tile j+1 steps before c in flow order; with an anchor, the last participating lane reads the
+// anchor's inclusive descriptor. Returns this lane's descriptor pointer (nullptr for idle lanes).
+__device__ __forceinline__ const uint4* lookback_addr(const uint4* agg0, const uint4* incl0, int64_t dstride, int c, int step,
+                                                      const LookbackPlan& pl, int lane) {
+    if (lane >= pl.nlanes) return nullptr;
+    const int idx = c + step * (lane + 1);
+    return ((pl.anchor_incl && lane == pl.nlanes - 1) ? incl0 : agg0) + (int64_t)idx * dstride;
+}
+__device__ __forceinline__ uint4 lookback_prefetch(const uint4* addr) {
+    return addr ? ld_desc(addr) : make_uint4(0u, 0u, DESC_READY, 0u);
+}
+// `first` is the result of an early lookback_prefetch of this lane's descriptor (issued before the tile's arithmetic).
+__device__ __forceinline__ float2 lookback_finish(const uint4* addr, uint4 first, int nlanes, int lane, unsigned int* err) {
+    uint4 v = first;
+    // warp-convergent poll: one instruction stream for the whole warp, only the lanes still waiting reload
+    // (per-lane spin loops would diverge into up to 31 independent loops that hog the scheduler's issue slots)
+    bool pending = addr != nullptr && v.z == DESC_EMPTY;
+    int spins = 0;
+    while (__any_sync(FULL, pending)) {
+        if (pending) {
+            v = ld_desc(addr);
+            pending = v.z == DESC_EMPTY;
+        }
+        if (++spins > 16) __nanosleep(64);
+        if (spins > (1 << 22)) {   // watchdog, see mbar_wait
+            if (lane == 0) atomicOr(err, 2u);
+            break;
+        }
+    }
+    __syncwarp();
+    float P = 1.f, V = 0.f;
+    if (lane < nlanes) {
+        P = __uint_as_float(v.x);
+        V = __uint_as_float(v.y);
+    }
+    // fold lanes: lane i ends with tiles [i, 32) where higher lanes (further away) are applied first
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float Pp = __shfl_down_sync(FULL, P, o);
+        const float Vp = __shfl_down_sync(FULL, V, o);
+        if (lane + o < 32) {
+            V = fmaf(P, Vp, V);
+            P = P * Pp;
+        }
+    }
+    return make_float2(__shfl_sync(FULL, P, 0), __shfl_sync(FULL, V, 0));
+}
+
+// Classic (timing-dependent) decoupled look-back, kept for A/B measurements: walks back over windows of 32 tiles and
+// stops at the first tile that has published an inclusive value. `agg0` holds status 1 = aggregate, 2 = inclusive.
+__device__ __forceinline__ float2 lookback_dynamic(const uint4* desc0, int64_t dstride, int c, int nchunks, int step, int lane,
+                                                   unsigned int* err) {
+    float runP = 1.f, runV = 0.f;
+    int j = c + step;
     while (true) {
         const int idx = j + step * lane;
         const bool inside = idx >= 0 && idx < nchunks;
         float P = 1.f, V = 0.f;
-        uint32_t st = DESC_INCLUSIVE;   // beyond the end of the sequence: identity, terminates the walk
-        if (inside) st = DESC_EMPTY;
+        uint32_t st = 2u;
+        if (inside) st = 0u;
         unsigned incl, need;
         int spins = 0;
         while (true) {
-            if (inside && st == DESC_EMPTY) {
+            if (inside && st == 0u) {
                 const uint4 v = ld_desc(desc0 + (int64_t)idx * dstride);
                 st = v.z;
                 P = __uint_as_float(v.x);
                 V = __uint_as_float(v.y);
             }
-            incl = __ballot_sync(FULL, st == DESC_INCLUSIVE);
-            const unsigned ready = __ballot_sync(FULL, st != DESC_EMPTY);
-            need = incl ? ((2u << (__ffs(incl) - 1)) - 1u) : FULL;   // lanes up to the nearest inclusive tile
+            incl = __ballot_sync(FULL, st == 2u);
+            const unsigned ready = __ballot_sync(FULL, st != 0u);
+            need = incl ? ((2u << (__ffs(incl) - 1)) - 1u) : FULL;
             if ((ready & need) == need) break;
-            if (++spins > 64) __nanosleep(64);
-            if (spins > (1 << 22)) {   // watchdog, see mbar_wait
+            if (++spins > 16) __nanosleep(64);
+            if (spins > (1 << 22)) {
                 if (lane == 0) atomicOr(err, 2u);
                 break;
             }
@@ -259,7 +344,6 @@ __device__ __forceinline__ float2 lookback(const uint4* desc0, int64_t dstride, 
             P = 1.f;
             V = 0.f;
         }
-        // fold lanes: lane i ends with tiles [i, 32) where higher lanes are applied first
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const float Pp = __shfl_down_sync(FULL, P, o);
@@ -270,7 +354,7 @@ __device__ __forceinline__ float2 lookback(const uint4* desc0, int64_t dstride, 
             }
         }
         const float Pw = __shfl_sync(FULL, P, 0), Vw = __shfl_sync(FULL, V, 0);
-        runV = fmaf(runP, Vw, runV);   // window first, then the nearer tiles folded so far
+        runV = fmaf(runP, Vw, runV);
         runP = runP * Pw;
         if (incl) break;
         j += step * 32;
@@ -282,10 +366,12 @@ __device__ __forceinline__ float2 lookback(const uint4* desc0, int64_t dstride, 
 // work decomposition shared by fwd/bwd
 // ------------------------------------------------------------------------------------------------
 struct TileCoord {
-    int c;       // chunk index along L
+    int c;       // tile index along L
     int b, g;    // batch, B/C group
     int row0;    // first channel row (within the group) of this step
-    int nrows;   // rows in this step (<= NW)
+    int nrows;   // rows in this step (<= NW); < 0 marks the end of work
+    int len;     // valid positions in this tile
+    int aux0, aux1;
 };
 
 }  // namespace bem

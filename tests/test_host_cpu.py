@@ -38,7 +38,7 @@ def test_size_queries_without_gpu(bem):
     assert lib.bem_scan_chunk_len(0) == 384 and lib.bem_scan_chunk_len(1) == lib.bem_scan_chunk_len(2) == 512
     assert lib.bem_scan_chunk_len(7) == 0
     # B1 KD160 L240000 N1 fp32: 625 chunks x 160 rows x 16 B + header
-    assert lib.bem_scan_workspace_bytes(1, 160, 240000, 1, 0) == 128 + 160 * 625 * 16
+    assert lib.bem_scan_workspace_bytes(1, 160, 240000, 1, 0) == 128 + 2 * 160 * 625 * 16
     assert lib.bem_scan_workspace_bytes(0, 160, 100, 1, 0) == 0
 
 

@@ -97,10 +97,11 @@ def test_mc_sampler_is_batch_and_shard_invariant():
     assert nmax_err(b.cpu().numpy(), a.cpu().numpy()) < 5e-5   # library convs pick batch-size dependent algorithms
     assert nmax_err(c.cpu().numpy(), a[[1, 3, 5]].cpu().numpy()) < 5e-5   # eps is bit-identical (test_bayes_gpu); library convs are not bitwise run-to-run
     assert float((a[0] - a[1]).abs().max()) > 0          # samples differ
-    res = mc.mc_infer(one, x, 6, monte_carlo_mean=True)
+    with torch.backends.cudnn.flags(allow_tf32=False):
+        res = mc.mc_infer(one, x, 6, monte_carlo_mean=True)
     scores = mc.default_score(a)
     assert res["index"] == int(torch.argmax(scores))     # no ties here
-    assert torch.equal(res["best"], a[res["index"]])
+    assert nmax_err(res["best"].cpu().numpy(), a[res["index"]].cpu().numpy()) < 5e-5
     assert nmax_err(res["mean"].cpu().numpy(), a.mean(0).clamp(0, 1).cpu().numpy()) < 1e-6
 
 
