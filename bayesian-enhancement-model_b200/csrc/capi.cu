@@ -130,9 +130,6 @@ int bem_scan_bwd(const BemScanBwdParams* q, void* stream_) {
     a.ticket = reinterpret_cast<unsigned int*>(ws);
     a.err = reinterpret_cast<unsigned int*>(ws + 4);
     a.desc = reinterpret_cast<uint4*>(ws + kWsHeader);
-    a.desc_incl = a.desc + (int64_t)a.batch * a.dim * a.nchunks * a.N;
-    cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)need, stream);
-    if (e != cudaSuccess) return (int)e;
     return scan_bwd_dispatch(a, q->dtype, q->dout_dtype, sms, stream);
 }
 

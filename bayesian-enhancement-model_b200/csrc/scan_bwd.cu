@@ -5,12 +5,16 @@
 //   g_t = C_t dout_t + a_{t+1} g_{t+1}            (reverse scan, :205-210)
 //   du = D dout + g delta B;  ddelta = g u B + g A (h_t - b_t);  dA += g delta (h_t - b_t)
 //   dB = g delta u;  dC = dout h;  dD += dout u;  ddelta *= sigmoid(delta_raw) when softplus   (:214-257)
-// Organisation: same persistent producer/consumer CTA as the forward kernel. The forward state at a
-// chunk start comes from the carries `x` written by the forward pass (as in the reference, :200); the reverse scan
-// crosses chunks with a decoupled look-back over SUCCESSOR chunks (tiles are handed out last chunk first).
+// Organisation: same persistent producer/consumer CTA as the forward kernel. The producer stages u / delta /
+// dout rows and the B / C chunk with TMA bulk copies and publishes, per tile, the coordinates, the rows' scalars
+// (A, D, bias) and the forward state at the tile start (the carries `x` written by the forward pass, as in the
+// reference, :200). The reverse scan crosses tiles with the deterministic decoupled look-back over SUCCESSOR tiles
+// (tickets are handed out last chunk first). du / ddelta leave straight from registers (128-bit stores).
 // dB/dC: the reference issues 2*N*L fp32 atomics per channel row (:224-237). Here (dstate == 1) every warp sums its
 // rows' contributions in its own shared-memory rows while the CTA walks all rows of a group split; the warps are then
 // added up and each (b, g, chunk) slab is written once (plain store when the split covers the whole group).
+#include <type_traits>
+
 #include "bem_kernels.h"
 #include "scan_common.cuh"
 
@@ -19,22 +23,25 @@ namespace bem {
 template <typename T, typename DT, int ITEMS, int NW, bool N1>
 __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1) scan_bwd_kernel(const ScanBwdArgs p) {
     constexpr int CL = 32 * ITEMS;
-    constexpr bool kAcc = sizeof(T) == 4;   // fp32 inputs: <= 1 ulp decay factors (scan_common.cuh decay_m1)
-    constexpr int ROW_SLOT = 2 * CL * (int)sizeof(T) + CL * (int)sizeof(DT);   // [u | delta | dout]; du, ddelta overlay u, delta
+    constexpr bool kAcc = sizeof(T) == 4;   // fp32 inputs: full-precision decay rate (scan_common.cuh decay_m1)
+    constexpr int ROW_SLOT = 2 * CL * (int)sizeof(T) + CL * (int)sizeof(DT);   // [u | delta | dout]
+    constexpr int VT = ElemTraits<T>::kPerVec;
     extern __shared__ __align__(128) unsigned char smem[];
 
     const int N = N1 ? 1 : p.N;
     const int S = p.stages;
+    const int nsc = 2 * N + 2;   // per-row scalars: A[N], D, bias, h_in[N]
     const int bc_bytes = N * CL * (int)sizeof(T);
-    const int stage_bytes = NW * ROW_SLOT + 2 * bc_bytes;
+    const int hdr_bytes = 128 + ((NW * nsc * 4 + 127) / 128) * 128;
+    const int stage_bytes = hdr_bytes + NW * ROW_SLOT + 2 * bc_bytes;
     float* red = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes);   // [2][NW][CL] (dstate == 1 only)
     const int red_bytes = N1 ? 2 * NW * CL * (int)sizeof(float) : 0;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes + red_bytes);
     uint64_t* empty = full + S;
-    int2* tile_slot = reinterpret_cast<int2*>(empty + S);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int nt = p.nchunks;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -46,50 +53,77 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
     }
     __syncthreads();
 
-    const int ST = p.ST;
-    const int GRS = p.G * p.RS;
-
-    // super tile t -> (chunk, batch, group, row split); chunks are handed out LAST FIRST so that every tile a
-    // reverse look-back waits on holds a smaller ticket
-    auto decode = [&](int t, int& c, int& b, int& g, int& rs) {
-        const int q = t / ST;
-        c = p.nchunks - 1 - q;
-        const int r = t - q * ST;
-        b = r / GRS;
-        const int rem = r - b * GRS;
-        g = rem / p.RS;
-        rs = rem - g * p.RS;
-    };
-
     if (warp == NW) {
         // ======================================= producer warp =======================================
-        uint32_t it = 0;
+        const int ST = p.ST;
+        const int GRS = p.G * p.RS;
+        constexpr int kMaxSc = (NW * (2 * kMaxDstate + 2) + 31) / 32;
+        unsigned int t = 0;
+        if (lane == 0) t = atomicAdd(p.ticket, 1u);
+        t = __shfl_sync(FULL, t, 0);
+        int s = 0;
+        uint32_t use = 0;
         while (true) {
-            unsigned int t = 0;
-            if (lane == 0) t = atomicAdd(p.ticket, 1u);
-            t = __shfl_sync(FULL, t, 0);
-            const bool done = t >= (unsigned)p.total_tiles;
-            int c = 0, b = 0, g = 0, rs = 0;
-            if (!done) decode((int)t, c, b, g, rs);
-            const int nsteps = done ? 1 : p.RBS;
-            for (int j = 0; j < nsteps; ++j, ++it) {
-                const int s = it % S;
-                const uint32_t use = it / S;
+            if (t >= (unsigned)p.total_tiles) {
                 if (use > 0) mbar_wait(&empty[s], (use - 1) & 1, p.err);
-                if (done) {
-                    if (lane == 0) {
-                        tile_slot[s] = make_int2(-1, 0);
-                        mbar_arrive(&full[s]);
-                    }
-                    break;
+                if (lane == 0) {
+                    reinterpret_cast<TileCoord*>(smem + (size_t)s * stage_bytes)->nrows = -1;
+                    mbar_arrive(&full[s]);
                 }
-                const int l0 = c * CL;
-                const int len = min(CL, p.L - l0);
-                const int row0 = rs * p.rows_per_split + j * NW;                 // within the group
-                const int row_end = min((rs + 1) * p.rows_per_split, p.Dg);
-                const int nrows = max(0, min(NW, row_end - row0));
+                break;
+            }
+            // super tile t -> (chunk, batch, group, row split); chunks are handed out LAST FIRST so that every tile a
+            // reverse look-back waits on holds a smaller ticket
+            const int q = (int)t / ST;
+            const int c = nt - 1 - q;
+            const int r = (int)t - q * ST;
+            const int b = r / GRS;
+            const int rem = r - b * GRS;
+            const int g = rem / p.RS;
+            const int rs = rem - g * p.RS;
+            const int l0 = c * CL;
+            const int len = min(CL, p.L - l0);
+            unsigned int t_next = 0;
+            for (int j = 0; j < p.RBS; ++j) {
                 unsigned char* st = smem + (size_t)s * stage_bytes;
+                TileCoord tc;
+                tc.c = c;
+                tc.b = b;
+                tc.g = g;
+                tc.row0 = rs * p.rows_per_split + j * NW;   // within the group
+                const int row_end = min((rs + 1) * p.rows_per_split, p.Dg);
+                tc.nrows = max(0, min(NW, row_end - tc.row0));
+                tc.len = len;
+                tc.aux0 = j;
+                tc.aux1 = (j == p.RBS - 1) ? 1 : 0;
+                // per-row scalars, requested before blocking on the slot
+                float scv[kMaxSc];
+#pragma unroll
+                for (int qq = 0; qq < kMaxSc; ++qq) {
+                    const int i = lane + 32 * qq;
+                    float v = 0.f;
+                    if (i < tc.nrows * nsc) {
+                        const int rr = i / nsc, k = i - rr * nsc;
+                        const int64_t d = (int64_t)g * p.Dg + tc.row0 + rr;
+                        if (k < N) v = p.A[d * p.A_ds + k * p.A_ns];
+                        else if (k == N) v = p.D ? p.D[d] : 0.f;
+                        else if (k == N + 1) v = p.bias ? p.bias[d] : 0.f;
+                        else if (c > 0 && p.x) v = p.x[((((int64_t)b * p.dim + d) * nt + (c - 1)) * N + (k - N - 2)) * 2 + 1];
+                    }
+                    scv[qq] = v;
+                }
+                if (use > 0) mbar_wait(&empty[s], (use - 1) & 1, p.err);
+                if (j == p.RBS - 1 && lane == 0) t_next = atomicAdd(p.ticket, 1u);
+                if (lane == 0) *reinterpret_cast<TileCoord*>(st) = tc;
+                float* sc = reinterpret_cast<float*>(st + 128);
+#pragma unroll
+                for (int qq = 0; qq < kMaxSc; ++qq) {
+                    const int i = lane + 32 * qq;
+                    if (i < tc.nrows * nsc) sc[i] = scv[qq];
+                }
+                unsigned char* rows = st + hdr_bytes;
                 // jobs: u rows, delta rows, dout rows, then N B rows and N C rows (re-staged every step: L2 hits)
+                const int nrows = tc.nrows;
                 const int njobs = 3 * nrows + 2 * N;
                 uint32_t my_bytes = 0;
                 for (int pass = 0; pass < 2; ++pass) {
@@ -99,9 +133,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                         int esz;
                         if (jj < 3 * nrows) {
                             const int which = jj / nrows;
-                            const int r = jj - which * nrows;
-                            const int64_t d = (int64_t)g * p.Dg + row0 + r;
-                            unsigned char* slot = st + r * ROW_SLOT;
+                            const int rr = jj - which * nrows;
+                            const int64_t d = (int64_t)g * p.Dg + tc.row0 + rr;
+                            unsigned char* slot = rows + rr * ROW_SLOT;
                             if (which == 0) {
                                 src = reinterpret_cast<const unsigned char*>(reinterpret_cast<const T*>(p.u) + b * p.u_bs + d * p.u_ds + l0);
                                 dst = slot;
@@ -122,7 +156,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                             src = reinterpret_cast<const unsigned char*>(
                                 isc ? reinterpret_cast<const T*>(p.Cm) + b * p.C_bs + g * p.C_gs + n * p.C_ns + l0
                                     : reinterpret_cast<const T*>(p.Bm) + b * p.B_bs + g * p.B_gs + n * p.B_ns + l0);
-                            dst = st + NW * ROW_SLOT + (isc ? bc_bytes : 0) + n * CL * sizeof(T);
+                            dst = rows + NW * ROW_SLOT + (isc ? bc_bytes : 0) + n * CL * sizeof(T);
                             esz = sizeof(T);
                         }
                         const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
@@ -147,149 +181,160 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
                         __syncwarp();
                         if (lane == 0) {
-                            tile_slot[s] = make_int2((int)t, j);
                             if (tot > 0) mbar_arrive_expect_tx(&full[s], tot);
                             else mbar_arrive(&full[s]);
                         }
                         __syncwarp();
                     }
                 }
+                if (++s == S) {
+                    s = 0;
+                    ++use;
+                }
             }
-            if (done) break;
+            t = __shfl_sync(FULL, t_next, 0);
         }
         return;
     }
 
     // ========================================= consumer warps =========================================
-    int pend_stage = -1;
-    for (uint32_t it = 0;; ++it) {
-        const int s = it % S;
-        mbar_wait(&full[s], (it / S) & 1, p.err);
-        const int2 slot = tile_slot[s];
-        if (slot.x < 0) break;
-        int c, b, g, rs;
-        decode(slot.x, c, b, g, rs);
-        const int j = slot.y;
-        const int l0 = c * CL;
-        const int len = min(CL, p.L - l0);
-        const bool partial = len < CL;
-        const int row_in_group = rs * p.rows_per_split + j * NW + warp;
-        const bool active = row_in_group < min((rs + 1) * p.rows_per_split, p.Dg);
+    int s = -1;
+    uint32_t phase = 1;
+    while (true) {
+        if (++s == S) s = 0;
+        if (s == 0) phase ^= 1;
+        mbar_wait(&full[s], phase, p.err);
         unsigned char* st = smem + (size_t)s * stage_bytes;
+        const TileCoord tc = *reinterpret_cast<const TileCoord*>(st);
+        if (tc.nrows < 0) break;
+        const int c = tc.c, b = tc.b, g = tc.g;
+        const int j = tc.aux0;
+        const int l0 = c * CL;
+        const int len = tc.len;
+        const bool partial = len < CL;
+        const bool active = warp < tc.nrows;
         const int e0 = lane * ITEMS;
-        bool drained = false;
-        auto drain_prev = [&]() {
-            if (!drained && pend_stage >= 0 && lane == 0) {
-                bulk_wait_read<0>();
-                mbar_arrive(&empty[pend_stage]);
-            }
-            drained = true;
-        };
 
         if (active) {
-            const int64_t d = (int64_t)g * p.Dg + row_in_group;
+            const int64_t d = (int64_t)g * p.Dg + tc.row0 + warp;
             const int64_t row = (int64_t)b * p.dim + d;
-            unsigned char* rslot = st + warp * ROW_SLOT;
+            const float* sc = reinterpret_cast<const float*>(st + 128) + warp * nsc;
+            unsigned char* rows = st + hdr_bytes;
+            unsigned char* rslot = rows + warp * ROW_SLOT;
             const T* su = reinterpret_cast<const T*>(rslot);
             const T* sd = su + CL;
             const DT* sdo = reinterpret_cast<const DT*>(rslot + 2 * CL * sizeof(T));
-            const T* sB = reinterpret_cast<const T*>(st + NW * ROW_SLOT);
-            const T* sC = reinterpret_cast<const T*>(st + NW * ROW_SLOT + bc_bytes);
-            const float bias = p.bias ? p.bias[d] : 0.f;
-            const float Dv = p.D ? p.D[d] : 0.f;
-
-            float du[ITEMS], dd[ITEMS];   // general-dstate path only (dstate == 1 writes in place)
+            const T* sB = reinterpret_cast<const T*>(rows + NW * ROW_SLOT);
+            const T* sC = reinterpret_cast<const T*>(rows + NW * ROW_SLOT + bc_bytes);
+            const float Dv = sc[N], bias = sc[N + 1];
+            const LookbackPlan plan = lookback_plan(nt - 1 - c, nt);
+            T* gdu = reinterpret_cast<T*>(p.du) + b * p.du_bs + d * p.du_ds + l0;
+            T* gdd = reinterpret_cast<T*>(p.ddelta) + b * p.dd_bs + d * p.dd_ds + l0;
+            const bool vec_store = !partial && ((reinterpret_cast<uintptr_t>(gdu) | reinterpret_cast<uintptr_t>(gdd)) & 15) == 0;
             float dD_acc = 0.f, dbias_acc = 0.f;
 
             if constexpr (N1) {
-                const float Av = p.A[d * p.A_ds];
-                const float A2 = Av;
+                uint4* aggrow = p.desc + row * nt;
+                uint4* inclrow = p.desc_incl + row * nt;
+                const uint4* lb_addr = lookback_addr(aggrow, inclrow, 1, c, +1, plan, lane);
+                const uint4 lb_first = lookback_prefetch(lb_addr);   // in flight during the local scans
+                const float Av = sc[0];
+                const float h_in = sc[3];
                 float a[ITEMS], h[ITEMS], gl[ITEMS], rp[ITEMS];
-                float Pth, Rth;
-                {
-                    float uv[ITEMS], dl[ITEMS], Bv[ITEMS];
-                    lds_items<T, ITEMS>(su + e0, uv);
-                    lds_items<T, ITEMS>(sd + e0, dl);
-                    lds_items<T, ITEMS>(sB + e0, Bv);
-                    float P = 1.f, V = 0.f;
+                float P = 1.f, Vv = 0.f;
+                auto fwd_local = [&](auto tag) {
+                    constexpr bool PART = decltype(tag)::value;
 #pragma unroll
-                    for (int i = 0; i < ITEMS; ++i) {
-                        float x = dl[i] + bias;
-                        if (p.softplus) x = softplus_f(x);
-                        float ei = decay_m1<kAcc>(x * A2);
-                        float bi = x * uv[i] * Bv[i];
-                        if (partial && e0 + i >= len) {
-                            ei = 0.f;
-                            bi = 0.f;
+                    for (int v = 0; v < ITEMS / VT; ++v) {
+                        float uv[VT], dl[VT], Bv[VT];
+                        lds_items<T, VT>(su + e0 + v * VT, uv);
+                        lds_items<T, VT>(sd + e0 + v * VT, dl);
+                        lds_items<T, VT>(sB + e0 + v * VT, Bv);
+#pragma unroll
+                        for (int k = 0; k < VT; ++k) {
+                            const int i = v * VT + k;
+                            float x = dl[k] + bias;
+                            if (p.softplus) x = softplus_f(x);
+                            float ei = decay_m1<kAcc>(x * Av);
+                            float bi = x * uv[k] * Bv[k];
+                            if (PART && e0 + i >= len) {
+                                ei = 0.f;
+                                bi = 0.f;
+                                x = 0.f;
+                            }
+                            dl[k] = x;
+                            a[i] = ei;   // decay minus one
+                            decay_step(ei, bi, P, Vv);
+                            h[i] = Vv;   // local inclusive state
+                            rp[i] = P;   // local inclusive decay (temporarily)
                         }
-                        a[i] = ei;   // decay minus one
-                        decay_step(ei, bi, P, V);
-                        h[i] = V;    // local inclusive state
-                        rp[i] = P;   // local inclusive decay (temporarily)
+                        // keep the activated delta (fp32 accuracy matters only for fp32 inputs) for the output pass:
+                        // same lane, same addresses, so no cross-lane hazard
+                        if constexpr (sizeof(T) == 4) sts_items<T, VT>(const_cast<T*>(sd) + e0 + v * VT, dl);
                     }
-                    Pth = P;
-                    warp_scan_fwd(P, V, lane);
-                    float Pe = __shfl_up_sync(FULL, P, 1), Ve = __shfl_up_sync(FULL, V, 1);
-                    if (lane == 0) {
-                        Pe = 1.f;
-                        Ve = 0.f;
-                    }
-                    const float h_in = (c > 0 && p.x) ? p.x[(row * p.nchunks + (c - 1)) * 2 + 1] : 0.f;
-                    const float seed = fmaf(Pe, h_in, Ve);
-#pragma unroll
-                    for (int i = 0; i < ITEMS; ++i) h[i] = fmaf(rp[i], seed, h[i]);   // true forward state h_t
+                };
+                if (partial) fwd_local(std::true_type{});
+                else fwd_local(std::false_type{});
+                const float Pth = P;
+                warp_scan_fwd(P, Vv, lane);
+                float Pe = __shfl_up_sync(FULL, P, 1), Ve = __shfl_up_sync(FULL, Vv, 1);
+                if (lane == 0) {
+                    Pe = 1.f;
+                    Ve = 0.f;
                 }
-                {
-                    float Cv[ITEMS], dy[ITEMS];
-                    lds_items<T, ITEMS>(sC + e0, Cv);
-                    lds_items<DT, ITEMS>(sdo + e0, dy);
-                    float r = 0.f, RP = 1.f;
+                const float seed = fmaf(Pe, h_in, Ve);
 #pragma unroll
-                    for (int i = ITEMS - 1; i >= 0; --i) {
-                        const float cd = (partial && e0 + i >= len) ? 0.f : Cv[i] * dy[i];
-                        gl[i] = cd + r;   // g_t with zero incoming adjoint
-                        rp[i] = RP;       // d g_t / d incoming
-                        r = fmaf(a[i], gl[i], gl[i]);
-                        RP = fmaf(a[i], RP, RP);
+                for (int i = 0; i < ITEMS; ++i) h[i] = fmaf(rp[i], seed, h[i]);   // true forward state h_t
+                // reverse local scan of g'_t = a_t (C_t dout_t + g'_{t+1})
+                float rr = 0.f, RP = 1.f;
+                auto rev_local = [&](auto tag) {
+                    constexpr bool PART = decltype(tag)::value;
+#pragma unroll
+                    for (int v = ITEMS / VT - 1; v >= 0; --v) {
+                        float Cv[VT], dy[VT];
+                        lds_items<T, VT>(sC + e0 + v * VT, Cv);
+                        lds_items<DT, VT>(sdo + e0 + v * VT, dy);
+#pragma unroll
+                        for (int k = VT - 1; k >= 0; --k) {
+                            const int i = v * VT + k;
+                            const float cd = (PART && e0 + i >= len) ? 0.f : Cv[k] * dy[k];
+                            gl[i] = cd + rr;   // g_t with zero incoming adjoint
+                            rp[i] = RP;        // d g_t / d incoming
+                            rr = fmaf(a[i], gl[i], gl[i]);
+                            RP = fmaf(a[i], RP, RP);
+                        }
                     }
-                    Rth = r;
-                }
-                float P = Pth, R = Rth;
-                warp_scan_rev(P, R, lane);
-                float Ps = __shfl_down_sync(FULL, P, 1), Rs = __shfl_down_sync(FULL, R, 1);
+                };
+                if (partial) rev_local(std::true_type{});
+                else rev_local(std::false_type{});
+                float Pr = Pth, Rr = rr;
+                warp_scan_rev(Pr, Rr, lane);
+                float Ps = __shfl_down_sync(FULL, Pr, 1), Rs = __shfl_down_sync(FULL, Rr, 1);
                 if (lane == 31) {
                     Ps = 1.f;
                     Rs = 0.f;
                 }
-                const float Pa = __shfl_sync(FULL, P, 0), Ra = __shfl_sync(FULL, R, 0);
-                uint4* aggrow = p.desc + row * p.nchunks;
-                uint4* inclrow = p.desc_incl + row * p.nchunks;
-                const LookbackPlan plan = lookback_plan(p.nchunks - 1 - c, p.nchunks);
+                const float Pa = __shfl_sync(FULL, Pr, 0), Ra = __shfl_sync(FULL, Rr, 0);
                 if (lane == 0 && plan.publish_agg) st_desc(aggrow + c, Pa, Ra, DESC_READY);
-                drain_prev();
                 float r_in = 0.f, Psuf = 1.f;
                 if (plan.nlanes) {
-                    const uint4* lb_addr = lookback_addr(aggrow, inclrow, 1, c, +1, plan, lane);
-                    const float2 suf = lookback_finish(lb_addr, lookback_prefetch(lb_addr), plan.nlanes, lane, p.err);
+                    const float2 suf = lookback_finish(lb_addr, lb_first, plan.nlanes, lane, p.err);
                     Psuf = suf.x;
                     r_in = suf.y;
                 }
                 if (lane == 0 && plan.publish_incl) st_desc(inclrow + c, Pa * Psuf, fmaf(Pa, r_in, Ra), DESC_READY);
                 const float rin_t = fmaf(Ps, r_in, Rs);   // adjoint entering this lane's last position
-                {
-                    // outputs, one 128-bit vector of T at a time. du / ddelta overwrite u / delta IN PLACE (same lane,
-                    // same addresses), dB / dC contributions are accumulated into this warp's rows of `red`.
-                    constexpr int VT = ElemTraits<T>::kPerVec;
-                    T* s_du = reinterpret_cast<T*>(rslot);
-                    T* s_dd = s_du + CL;
-                    float* accB = red + warp * CL + e0;
-                    float* accC = red + NW * CL + warp * CL + e0;
-                    float dA_acc = 0.f;
+                // outputs, one 128-bit vector of T at a time; dB / dC contributions go to this warp's rows of `red`
+                float* accB = red + warp * CL + e0;
+                float* accC = red + NW * CL + warp * CL + e0;
+                float dA_acc = 0.f;
+                auto outputs = [&](auto tag) {
+                    constexpr bool PART = decltype(tag)::value;
 #pragma unroll
                     for (int v = 0; v < ITEMS / VT; ++v) {
                         float uv[VT], dl[VT], Bv[VT], dy[VT], cB[VT], cC[VT], duv[VT], ddv[VT];
                         lds_items<T, VT>(su + e0 + v * VT, uv);
-                        lds_items<T, VT>(sd + e0 + v * VT, dl);
+                        lds_items<T, VT>(sd + e0 + v * VT, dl);   // fp32: already activated (written back above)
                         lds_items<T, VT>(sB + e0 + v * VT, Bv);
                         lds_items<DT, VT>(sdo + e0 + v * VT, dy);
                         if (j > 0) {
@@ -302,9 +347,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
 #pragma unroll
                         for (int k = 0; k < VT; ++k) {
                             const int i = v * VT + k;
-                            const bool valid = !(partial && e0 + i >= len);
-                            const float raw = valid ? dl[k] + bias : 0.f;
-                            const float x = p.softplus ? softplus_f(raw) : raw;
+                            const bool valid = !(PART && e0 + i >= len);
+                            float x;
+                            if constexpr (sizeof(T) == 4) {
+                                x = dl[k];
+                            } else {
+                                const float raw = valid ? dl[k] + bias : 0.f;   // stale smem beyond the end may hold NaN patterns
+                                x = p.softplus ? softplus_f(raw) : raw;
+                            }
                             const float ui = valid ? uv[k] : 0.f;
                             const float dyi = valid ? dy[k] : 0.f;
                             const float Bi = valid ? Bv[k] : 0.f;
@@ -317,22 +367,46 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                             cB[k] = fmaf(gt * x, ui, cB[k]);
                             cC[k] = fmaf(dyi, h[i], cC[k]);
                             dD_acc = fmaf(dyi, ui, dD_acc);
-                            if (p.softplus) ddl *= softplus_grad_f(raw);
+                            // d softplus = sigmoid(raw) = 1 - exp(-softplus(raw)); equals the reference's switch to 1
+                            // above raw = 20 (bwd_kernel_oflex.cuh:250-255) to 2e-9
+                            if (p.softplus) ddl *= 1.f - ex2_approx(-x * kLog2e);
                             if (!valid) ddl = 0.f;
                             dbias_acc += ddl;
                             ddv[k] = ddl;
                         }
-                        sts_items<T, VT>(s_du + e0 + v * VT, duv);
-                        sts_items<T, VT>(s_dd + e0 + v * VT, ddv);
                         sts_items<float, VT>(accB + v * VT, cB);
                         sts_items<float, VT>(accC + v * VT, cC);
-                    }
+                        if (vec_store) {
+                            uint4 ru, rd;
+                            T* eu = reinterpret_cast<T*>(&ru);
+                            T* ed = reinterpret_cast<T*>(&rd);
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) dA_acc += __shfl_xor_sync(FULL, dA_acc, o);
-                    if (lane == 0) atomicAdd(p.dA + d, dA_acc);
-                }
+                            for (int k = 0; k < VT; ++k) {
+                                eu[k] = ElemTraits<T>::from_f(duv[k]);
+                                ed[k] = ElemTraits<T>::from_f(ddv[k]);
+                            }
+                            reinterpret_cast<uint4*>(gdu + e0)[v] = ru;
+                            reinterpret_cast<uint4*>(gdd + e0)[v] = rd;
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < VT; ++k) {
+                                const int e = e0 + v * VT + k;
+                                if (e < len) {
+                                    gdu[e] = ElemTraits<T>::from_f(duv[k]);
+                                    gdd[e] = ElemTraits<T>::from_f(ddv[k]);
+                                }
+                            }
+                        }
+                    }
+                };
+                if (partial) outputs(std::true_type{});
+                else outputs(std::false_type{});
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) dA_acc += __shfl_xor_sync(FULL, dA_acc, o);
+                if (lane == 0) atomicAdd(p.dA + d, dA_acc);
             } else {
                 // ------------------------------ general dstate ------------------------------
+                float du[ITEMS], dd[ITEMS];
                 float uv[ITEMS], dl[ITEMS], dy[ITEMS];
                 lds_items<T, ITEMS>(su + e0, uv);
                 lds_items<T, ITEMS>(sd + e0, dl);
@@ -351,17 +425,17 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                     dd[i] = 0.f;
                     dD_acc = fmaf(dy[i], uv[i], dD_acc);
                 }
-                // pass 1: chunk aggregates of the reverse scan, one state per lane
+                // pass 1: tile aggregates of the reverse scan, one state per lane
                 float aggP = 1.f, aggR = 0.f;
                 for (int n = 0; n < N; ++n) {
-                    const float A2 = p.A[d * p.A_ds + n * p.A_ns];
+                    const float An = sc[n];
                     float Cv[ITEMS];
                     lds_items<T, ITEMS>(sC + n * CL + e0, Cv);
                     float r = 0.f, RP = 1.f;
 #pragma unroll
                     for (int i = ITEMS - 1; i >= 0; --i) {
                         const bool valid = !(partial && e0 + i >= len);
-                        const float ei = valid ? decay_m1<kAcc>(dl[i] * A2) : 0.f;
+                        const float ei = valid ? decay_m1<kAcc>(dl[i] * An) : 0.f;
                         const float cd = valid ? Cv[i] * dy[i] : 0.f;
                         const float gsum = cd + r;
                         r = fmaf(ei, gsum, gsum);
@@ -374,11 +448,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                         aggR = Ra;
                     }
                 }
-                uint4* aggrow = p.desc + (row * p.nchunks) * N;
-                uint4* inclrow = p.desc_incl + (row * p.nchunks) * N;
-                const LookbackPlan plan = lookback_plan(p.nchunks - 1 - c, p.nchunks);
+                uint4* aggrow = p.desc + (row * nt) * N;
+                uint4* inclrow = p.desc_incl + (row * nt) * N;
                 if (lane < N && plan.publish_agg) st_desc(aggrow + (int64_t)c * N + lane, aggP, aggR, DESC_READY);
-                drain_prev();
                 float sufP = 1.f, sufR = 0.f;
                 if (plan.nlanes) {
                     for (int n0 = 0; n0 < N; n0 += 4) {   // four states' descriptors in flight at a time
@@ -404,30 +476,28 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                 if (lane < N && plan.publish_incl) st_desc(inclrow + (int64_t)c * N + lane, aggP * sufP, fmaf(aggP, sufR, aggR), DESC_READY);
                 // pass 2: per state, forward states from the carry, reverse adjoints from the look-back
                 for (int n = 0; n < N; ++n) {
-                    const float Av = p.A[d * p.A_ds + n * p.A_ns];
-                    const float A2 = Av;
+                    const float Av = sc[n];
                     float a[ITEMS], h[ITEMS], gl[ITEMS], rp[ITEMS], Bv[ITEMS];
                     lds_items<T, ITEMS>(sB + n * CL + e0, Bv);
                     float P = 1.f, V = 0.f;
 #pragma unroll
                     for (int i = 0; i < ITEMS; ++i) {
                         const bool valid = !(partial && e0 + i >= len);
-                        const float ei = valid ? decay_m1<kAcc>(dl[i] * A2) : 0.f;
+                        const float ei = valid ? decay_m1<kAcc>(dl[i] * Av) : 0.f;
                         const float bi = valid ? dl[i] * uv[i] * Bv[i] : 0.f;
                         a[i] = ei;   // decay minus one
                         decay_step(ei, bi, P, V);
                         h[i] = V;
                         rp[i] = P;
                     }
-                    float Pth = P;
+                    const float Pth = P;
                     warp_scan_fwd(P, V, lane);
                     float Pe = __shfl_up_sync(FULL, P, 1), Ve = __shfl_up_sync(FULL, V, 1);
                     if (lane == 0) {
                         Pe = 1.f;
                         Ve = 0.f;
                     }
-                    const float h_in = (c > 0 && p.x) ? p.x[((row * p.nchunks + (c - 1)) * N + n) * 2 + 1] : 0.f;
-                    const float seed = fmaf(Pe, h_in, Ve);
+                    const float seed = fmaf(Pe, sc[N + 2 + n], Ve);
 #pragma unroll
                     for (int i = 0; i < ITEMS; ++i) h[i] = fmaf(rp[i], seed, h[i]);
                     float r = 0.f, RP = 1.f;
@@ -475,17 +545,39 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                     if (lane == 0) atomicAdd(p.dA + d * N + n, dA_acc);
                 }
                 // softplus chain rule needs the raw delta again
-                {
-                    float raw[ITEMS];
-                    lds_items<T, ITEMS>(sd + e0, raw);
+                float raw[ITEMS];
+                lds_items<T, ITEMS>(sd + e0, raw);
+#pragma unroll
+                for (int i = 0; i < ITEMS; ++i) {
+                    const bool valid = !(partial && e0 + i >= len);
+                    float ddl = dd[i];
+                    if (p.softplus) ddl *= softplus_grad_f(valid ? raw[i] + bias : 0.f);
+                    if (!valid) ddl = 0.f;
+                    dd[i] = ddl;
+                    dbias_acc += ddl;
+                }
+                if (vec_store) {
+#pragma unroll
+                    for (int v = 0; v < ITEMS / VT; ++v) {
+                        uint4 ru, rd;
+                        T* eu = reinterpret_cast<T*>(&ru);
+                        T* ed = reinterpret_cast<T*>(&rd);
+#pragma unroll
+                        for (int k = 0; k < VT; ++k) {
+                            eu[k] = ElemTraits<T>::from_f(du[v * VT + k]);
+                            ed[k] = ElemTraits<T>::from_f(dd[v * VT + k]);
+                        }
+                        reinterpret_cast<uint4*>(gdu + e0)[v] = ru;
+                        reinterpret_cast<uint4*>(gdd + e0)[v] = rd;
+                    }
+                } else {
 #pragma unroll
                     for (int i = 0; i < ITEMS; ++i) {
-                        const bool valid = !(partial && e0 + i >= len);
-                        float ddl = dd[i];
-                        if (p.softplus) ddl *= softplus_grad_f(raw[i] + bias);
-                        if (!valid) ddl = 0.f;
-                        dd[i] = ddl;
-                        dbias_acc += ddl;
+                        const int e = e0 + i;
+                        if (e < len) {
+                            gdu[e] = ElemTraits<T>::from_f(du[i]);
+                            gdd[e] = ElemTraits<T>::from_f(dd[i]);
+                        }
                     }
                 }
             }
@@ -499,37 +591,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                 if (p.dD) atomicAdd(p.dD + d, dD_acc);
                 if (p.dbias) atomicAdd(p.dbias + d, dbias_acc);
             }
-
-            // ---------------- du / ddelta: in place over the u / delta slots, TMA bulk store ----------------
-            drain_prev();
-            T* gdu = reinterpret_cast<T*>(p.du) + b * p.du_bs + d * p.du_ds + l0;
-            T* gdd = reinterpret_cast<T*>(p.ddelta) + b * p.dd_bs + d * p.dd_ds + l0;
-            const bool al_u = (reinterpret_cast<uintptr_t>(gdu) & 15) == 0;
-            const bool al_d = (reinterpret_cast<uintptr_t>(gdd) & 15) == 0;
-            const uint32_t vb_u = al_u ? ((uint32_t)(len * sizeof(T)) & ~15u) : 0u;
-            const uint32_t vb_d = al_d ? ((uint32_t)(len * sizeof(T)) & ~15u) : 0u;
-            T* s_du = reinterpret_cast<T*>(rslot);
-            T* s_dd = s_du + CL;
-            if constexpr (!N1) {
-                sts_items<T, ITEMS>(s_du + e0, du);
-                sts_items<T, ITEMS>(s_dd + e0, dd);
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-                if (vb_u) bulk_s2g(gdu, s_du, vb_u);
-                if (vb_d) bulk_s2g(gdd, s_dd, vb_d);
-            }
-            const int ve_u = vb_u / sizeof(T), ve_d = vb_d / sizeof(T);
-            if (ve_u < len || ve_d < len) {   // ragged tail / unaligned rows: this lane's own positions, straight from its slot
-                for (int i = 0; i < ITEMS; ++i) {
-                    const int e = e0 + i;
-                    if (e >= ve_u && e < len) gdu[e] = s_du[e];
-                    if (e >= ve_d && e < len) gdd[e] = s_dd[e];
-                }
-            }
         } else {
-            drain_prev();
             if constexpr (N1) {
                 if (j == 0) {   // this warp has no row in the first step: its dB/dC rows start at zero
                     float z[ITEMS];
@@ -540,11 +602,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                 }
             }
         }
-        if (lane == 0) bulk_commit();
-        pend_stage = s;
+        __syncwarp();   // every lane is done reading the stage
+        if (lane == 0) mbar_arrive(&empty[s]);
 
         if constexpr (N1) {
-            if (j == p.RBS - 1) {
+            if (tc.aux1) {
                 // ---------------- flush dB / dC of this (b, g, split, chunk) slab ----------------
                 float* redB = red;
                 float* redC = red + NW * CL;
@@ -553,19 +615,19 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                 float* gB = p.dB + ((int64_t)b * p.G + g) * p.L + l0;
                 float* gC = p.dC + ((int64_t)b * p.G + g) * p.L + l0;
                 for (int e = warp * PER_WARP + lane; e < (warp + 1) * PER_WARP; e += 32) {
-                    float sb = 0.f, sc = 0.f;
+                    float sb = 0.f, scc = 0.f;
 #pragma unroll
                     for (int r = 0; r < NW; ++r) {
                         sb += redB[r * CL + e];
-                        sc += redC[r * CL + e];
+                        scc += redC[r * CL + e];
                     }
                     if (e < len) {
                         if (p.atomic_bc) {
                             atomicAdd(gB + e, sb);
-                            atomicAdd(gC + e, sc);
+                            atomicAdd(gC + e, scc);
                         } else {
                             gB[e] = sb;
-                            gC[e] = sc;
+                            gC[e] = scc;
                         }
                     }
                 }
@@ -573,7 +635,6 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
             }
         }
     }
-    if (lane == 0) bulk_wait_read<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -582,14 +643,15 @@ static int launch_bwd(ScanBwdArgs& a, int sm_count, cudaStream_t stream) {
     constexpr int NW = kScanWarps;
     constexpr int CL = 32 * ITEMS;
     auto kernel = scan_bwd_kernel<T, DT, ITEMS, NW, N1>;
-    const int stage_bytes = NW * (2 * CL * (int)sizeof(T) + CL * (int)sizeof(DT)) + 2 * a.N * CL * (int)sizeof(T);
+    const int hdr_bytes = 128 + ((NW * (2 * a.N + 2) * 4 + 127) / 128) * 128;
+    const int stage_bytes = hdr_bytes + NW * (2 * CL * (int)sizeof(T) + CL * (int)sizeof(DT)) + 2 * a.N * CL * (int)sizeof(T);
     const int red_bytes = N1 ? 2 * NW * CL * (int)sizeof(float) : 0;
     const int fixed = red_bytes + 512;
     const int budget2 = (227 * 1024) / 2 - 1024;
     const bool two_ok = N1 && sizeof(T) == 4;   // matches __launch_bounds__ of the kernel
     int stages, ctas_per_sm;
     if (two_ok && 2 * stage_bytes + fixed <= budget2) {
-        stages = min(4, (budget2 - fixed) / stage_bytes);
+        stages = min(3, (budget2 - fixed) / stage_bytes);
         ctas_per_sm = 2;
     } else {
         stages = min(4, (227 * 1024 - fixed) / stage_bytes);
@@ -597,7 +659,7 @@ static int launch_bwd(ScanBwdArgs& a, int sm_count, cudaStream_t stream) {
         if (stages < 2) return BEM_ERR_UNSUPPORTED;
     }
     a.stages = stages;
-    const int smem_bytes = stages * stage_bytes + red_bytes + stages * (2 * 8 + 8) + 64;
+    const int smem_bytes = stages * stage_bytes + red_bytes + stages * 2 * 8 + 64;
     static int cached_smem[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -607,6 +669,10 @@ static int launch_bwd(ScanBwdArgs& a, int sm_count, cudaStream_t stream) {
         if (e != cudaSuccess) return (int)e;
         cached_smem[dev] = smem_bytes;
     }
+    const int64_t ndesc = (int64_t)a.batch * a.dim * a.nchunks * a.N;
+    a.desc_incl = a.desc + ndesc;
+    cudaError_t me = cudaMemsetAsync(a.ticket, 0, (size_t)(kWsHeader + 2 * ndesc * 16), stream);
+    if (me != cudaSuccess) return (int)me;
     const int grid = min(a.total_tiles, sm_count * ctas_per_sm);
     kernel<<<grid, (NW + 1) * 32, smem_bytes, stream>>>(a);
     return (int)cudaGetLastError();
