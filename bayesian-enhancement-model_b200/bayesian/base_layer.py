@@ -22,17 +22,32 @@ class BaseLayer_(nn.Module):
     def __init__(self):
         super().__init__()
 
-    def forward(self, input, eps_weight=None, eps_bias=None):
+    def forward(self, input, eps_weight=None, eps_bias=None, pre_norm=None):
         """eps_weight / eps_bias (extension): inject the noise instead of drawing it — used by the parity tests to replay
-        the eps the reference layer left in its eps_* buffers."""
+        the eps the reference layer left in its eps_* buffers.
+        pre_norm (extension): a LayerNorm2d-like module (weight, bias, eps over the channel dim) that precedes this layer;
+        1x1 layers fuse it into the kernel when no gradient is needed, otherwise it is simply applied first."""
         inj = getattr(self, "_injected_eps", None)   # tests: {"weight": t, "bias": t} replayed from the reference
         if inj:
             eps_weight = inj.get("weight", eps_weight)
             eps_bias = inj.get("bias", eps_bias)
-        if not self.deterministic:
-            return self._forward_uncertain(input, eps_weight, eps_bias)
-        else:
-            return self._forward_det(input)
+        self._ln = None
+        if pre_norm is not None:
+            needs_grad = torch.is_grad_enabled() and (input.requires_grad or self.mu_weight.requires_grad)
+            if self._fuses_norm() and not needs_grad:
+                self._ln = (pre_norm.weight, pre_norm.bias, pre_norm.eps)
+            else:
+                input = pre_norm(input)
+        try:
+            if not self.deterministic:
+                return self._forward_uncertain(input, eps_weight, eps_bias)
+            else:
+                return self._forward_det(input)
+        finally:
+            self._ln = None
+
+    def _fuses_norm(self):
+        return False
 
     @abstractmethod
     def _forward_uncertain(self, input, eps_weight=None, eps_bias=None):
@@ -59,6 +74,19 @@ class BaseLayer_(nn.Module):
     @property
     def sigma_bias(self):
         return torch.log1p(torch.exp(self.rho_bias))
+
+    def _sigma_cached(self, which="weight"):
+        """detached log1p(exp(rho)) for the inference kernels, recomputed only when rho changes (optimizer steps and
+        load_state_dict bump the tensor version)"""
+        rho = getattr(self, "rho_" + which)
+        key = (rho._version, rho.data_ptr(), rho.device)
+        cache = self.__dict__.setdefault("_sigma_cache", {})
+        hit = cache.get(which)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                hit = (key, torch.log1p(torch.exp(rho.detach())).contiguous())
+            cache[which] = hit
+        return hit[1]
 
     def kl_loss(self):
         kl = self.kl_div(self.mu_weight, self.sigma_weight, self.prior_mu_weight, self.prior_sigma_weight)

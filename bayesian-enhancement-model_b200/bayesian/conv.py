@@ -91,7 +91,7 @@ class Conv2dReparameterization(BaseLayer_):
         """w: (S, Cout, Cin/g, kh, kw), b: (S, Cout) | None"""
         geo = self._geometry()
         if geo == "pointwise":
-            return BF.pointwise_conv(input, w.reshape(S, self.out_channels, self.in_channels), b, S)
+            return BF.pointwise_conv(input, w.reshape(S, self.out_channels, self.in_channels), b, S, ln=self._ln)
         if geo == "depthwise3":
             return BF.depthwise_conv3x3(input, w.reshape(S, self.out_channels, 3, 3), b, S)
         # geometry outside the BEM hot path: library convolution on the sampled weights (S samples as S x groups groups)
@@ -113,11 +113,14 @@ class Conv2dReparameterization(BaseLayer_):
             eps_w = self._draw_eps("weight", eps_weight)
             b = self._sample("bias", eps_bias)[0] if self.bias else None
             oc, ic = self.out_channels, self.in_channels
-            return BF.pointwise_conv_sampled(input, self.mu_weight.view(oc, ic), self.rho_weight.view(oc, ic),
-                                             eps_w.reshape(S, oc, ic), b, S)
+            return BF.pointwise_conv_sampled(input, self.mu_weight.view(oc, ic), self._sigma_cached().view(oc, ic),
+                                             eps_w.reshape(S, oc, ic), b, S, ln=self._ln)
         w, _ = self._sample("weight", eps_weight)
         b = self._sample("bias", eps_bias)[0] if self.bias else None
         return self._conv(input, w, b, S)
+
+    def _fuses_norm(self):
+        return self._geometry() == "pointwise"
 
     def _forward_det(self, input):
         w = self.mu_weight.unsqueeze(0)

@@ -66,10 +66,11 @@ def sample_weights(mu, rho, eps=None, n_samples=1, seed=0, stream_id=0, sample0=
 
 
 # ---------------------------------------------------------------------------------------------------
-def _pointwise_raw(x, w=None, bias=None, mu=None, rho=None, eps=None, n_samples=1):
-    """x: (S*Bx, Cin, *spatial) fp32; w: (S|1, Cout, Cin) or mu/rho/eps for the fused sample-on-load path."""
+def _pointwise_raw(x, w=None, bias=None, mu=None, sigma=None, eps=None, n_samples=1, ln=None, force_simt=False):
+    """x: (S*Bx, Cin, *spatial) fp32; w: (S|1, Cout, Cin) or mu/sigma/eps for the fused sample-on-load path;
+    ln = (gamma, beta, eps): LayerNorm over the channels of every pixel fused into the activation staging."""
     x = _f32c(x, "input")
-    w, bias, mu, rho, eps = (_f32c(t, n) for t, n in ((w, "w"), (bias, "bias"), (mu, "mu"), (rho, "rho"), (eps, "eps")))
+    w, bias, mu, sigma, eps = (_f32c(t, n) for t, n in ((w, "w"), (bias, "bias"), (mu, "mu"), (sigma, "sigma"), (eps, "eps")))
     ref = w if w is not None else mu
     cout, cin = int(ref.shape[-2]), int(ref.shape[-1])
     if x.dim() < 3 or x.shape[1] != cin:
@@ -77,9 +78,16 @@ def _pointwise_raw(x, w=None, bias=None, mu=None, rho=None, eps=None, n_samples=
     batch = x.shape[0]
     P = x[0, 0].numel()
     out = torch.empty((batch, cout) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+    g = b = None
+    ln_eps = 0.0
+    if ln is not None:
+        g, b, ln_eps = _f32c(ln[0], "ln weight"), _f32c(ln[1], "ln bias"), float(ln[2])
+        if g.numel() != cin:
+            raise RuntimeError(f"fused LayerNorm expects {cin} channels, got {g.numel()}")
     p = _lib.BemBayesPointwiseParams(n_samples=n_samples, batch=batch, cin=cin, cout=cout, P=P, x=_lib.ptr(x),
-                                     w=_lib.ptr(w), mu=_lib.ptr(mu), rho=_lib.ptr(rho), eps=_lib.ptr(eps),
-                                     bias=_lib.ptr(bias), out=_lib.ptr(out))
+                                     w=_lib.ptr(w), mu=_lib.ptr(mu), rho=None, eps=_lib.ptr(eps), bias=_lib.ptr(bias),
+                                     out=_lib.ptr(out), sigma=_lib.ptr(sigma), ln_gamma=_lib.ptr(g), ln_beta=_lib.ptr(b),
+                                     ln_eps=ln_eps, force_simt=int(bool(force_simt)))
     _lib.launch("bayes_pointwise", lib.bem_bayes_pointwise, p, x.device, key=(batch, cin, cout, P),
                 nbytes=4 * batch * P * (cin + cout))
     return out
@@ -113,16 +121,20 @@ class _PointwiseFn(torch.autograd.Function):
         return dx, dw, db, None
 
 
-def pointwise_conv(x, w, bias=None, n_samples=1):
-    """out[img] = w[s(img)] @ x[img] + bias[s(img)]; w: (S, Cout, Cin), bias: (S, Cout) | None."""
+def pointwise_conv(x, w, bias=None, n_samples=1, ln=None, force_simt=False):
+    """out[img] = w[s(img)] @ LN(x[img]) + bias[s(img)]; w: (S, Cout, Cin), bias: (S, Cout) | None.
+    ln = (gamma, beta, eps) fuses the preceding LayerNorm2d (inference only)."""
     if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or (bias is not None and bias.requires_grad)):
+        if ln is not None:
+            raise RuntimeError("the fused LayerNorm path has no backward; apply the norm module separately when training")
         return _PointwiseFn.apply(x, w, bias, n_samples)
-    return _pointwise_raw(x, w=w, bias=bias, n_samples=n_samples)
+    return _pointwise_raw(x, w=w, bias=bias, n_samples=n_samples, ln=ln, force_simt=force_simt)
 
 
-def pointwise_conv_sampled(x, mu, rho, eps, bias=None, n_samples=1):
-    """inference path: w = mu + softplus(rho) * eps is formed while the weight tile is loaded (never stored)."""
-    return _pointwise_raw(x, mu=mu, rho=rho, eps=eps, bias=bias, n_samples=n_samples)
+def pointwise_conv_sampled(x, mu, sigma, eps, bias=None, n_samples=1, ln=None, force_simt=False):
+    """inference path: w = mu + sigma * eps (sigma = log1p(exp(rho)) precomputed once per layer) is formed while the
+    weight tile is staged — the sampled weight never exists in HBM."""
+    return _pointwise_raw(x, mu=mu, sigma=sigma, eps=eps, bias=bias, n_samples=n_samples, ln=ln, force_simt=force_simt)
 
 
 # ---------------------------------------------------------------------------------------------------

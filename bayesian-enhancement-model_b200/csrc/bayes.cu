@@ -10,7 +10,7 @@
 //                        into the weight-tile load (the sampled weights never exist in HBM)
 //   bem_bayes_depthwise  S-batched depthwise 3x3, per-sample weights
 // This file holds the fp32 CUDA-core kernels (bit-faithful fp32 accumulate: the 1e-5 parity tier);
-// the tcgen05 tensor-core variant of the pointwise contraction lives in bayes_tc.cu.
+// the tcgen05 tensor-core kernel of the pointwise contraction (the default) lives in bayes_tc.cu.
 #include "bem_kernels.h"
 
 namespace bem {
@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(256) bayes_pointwise_kernel(const BemBayesPoin
                 if (p.w) w = p.w[wofs + wi];
                 else {
                     w = p.mu[wi];
-                    if (p.rho) w = fmaf(sigma_of_rho(p.rho[wi]), p.eps[wofs + wi], w);
+                    if (p.sigma) w = fmaf(p.sigma[wi], p.eps[wofs + wi], w);
+                    else if (p.rho) w = fmaf(sigma_of_rho(p.rho[wi]), p.eps[wofs + wi], w);
                 }
             }
             sW[kk][m] = w;
@@ -237,8 +238,10 @@ int bem_bayes_pointwise(const BemBayesPointwiseParams* p, void* stream) {
         return BEM_ERR_BAD_ARG;
     if (p->batch % p->n_samples != 0) return BEM_ERR_BAD_ARG;
     if (!p->w && !p->mu) return BEM_ERR_BAD_ARG;
-    if (!p->w && p->rho && !p->eps) return BEM_ERR_BAD_ARG;
+    if (!p->w && (p->rho || p->sigma) && !p->eps) return BEM_ERR_BAD_ARG;
     if (p->batch > 65535) return BEM_ERR_UNSUPPORTED;
+    if (!p->force_simt) return bayes_pointwise_tc_launch(*p, (cudaStream_t)stream);
+    if (p->ln_gamma) return BEM_ERR_UNSUPPORTED;   // the LayerNorm fusion lives in the tensor-core kernel
     dim3 grid((unsigned)((p->P + PW_BN - 1) / PW_BN), (unsigned)((p->cout + PW_BM - 1) / PW_BM), (unsigned)p->batch);
     bayes_pointwise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
     return (int)cudaGetLastError();

@@ -68,7 +68,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
     int tries = 0;
     while (!mbar_try_wait(bar, parity)) {   // each probe suspends the warp in hardware for a bounded time
         if (++tries > (1 << 24)) {
-            atomicOr(err, 1u);
+            if (err) atomicOr(err, 1u);
             return;
         }
     }

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import bayesian
-from .ss2d import SS2D, LayerNorm2d
+from .ss2d import SS2D, LayerNorm2d, apply_1x1
 
 
 class gdMlp(nn.Module):
@@ -33,8 +33,8 @@ class gdMlp(nn.Module):
         self.project_out = nn.Conv2d(hidden_features, out_features, kernel_size=1)
         self.act = act_layer()
 
-    def forward(self, x):
-        x = self.project_in(x)
+    def forward(self, x, pre_norm=None):
+        x = apply_1x1(self.project_in, x, pre_norm)
         x1, x2 = self.dwconv(x).chunk(2, dim=1)
         x = self.act(x1) * x2
         return self.project_out(x)
@@ -59,8 +59,8 @@ class VSSBlock(nn.Module):
                          drop=mlp_drop_rate, channels_first=channel_first)
 
     def forward(self, x):
-        x = x + self.op(self.norm(x))
-        return x + self.mlp(self.norm2(x))
+        x = x + self.op(x, pre_norm=self.norm)
+        return x + self.mlp(x, pre_norm=self.norm2)
 
 
 class PatchMerging(nn.Module):

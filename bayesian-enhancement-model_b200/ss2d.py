@@ -129,15 +129,32 @@ class SS2D(nn.Module):
         self.A_logs._no_weight_decay = True
         self.Ds._no_weight_decay = True
 
-    def forward_core(self, x):
+    def forward_core(self, x, apply_out_norm=True):
         return ss2d_core(x, self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias, self.A_logs, self.Ds,
-                         x_proj_bias=getattr(self, "x_proj_bias", None), out_norm=self.out_norm)
+                         x_proj_bias=getattr(self, "x_proj_bias", None), out_norm=self.out_norm if apply_out_norm else None)
 
-    def forward(self, x: torch.Tensor, **kwargs):
-        x = self.in_proj(x)
+    def forward(self, x: torch.Tensor, pre_norm=None, **kwargs):
+        """forwardv2 (vmamba.py:700-716). `pre_norm`: the block's LayerNorm2d; when in_proj / out_proj are Bayesian 1x1
+        layers of this package both the block norm and `out_norm` are fused into their kernels."""
+        x = apply_1x1(self.in_proj, x, pre_norm)
         if self.with_dconv:
             x = self.conv2d(x)
         x = self.act(x)
-        y = self.forward_core(x)
+        fuse_out = fuses_norm(self.out_proj) and isinstance(self.out_act, nn.Identity) and not torch.is_grad_enabled()
+        y = self.forward_core(x, apply_out_norm=not fuse_out)
         y = self.out_act(y)
-        return self.dropout(self.out_proj(y))
+        return self.dropout(apply_1x1(self.out_proj, y, self.out_norm if fuse_out else None))
+
+
+def fuses_norm(layer) -> bool:
+    f = getattr(layer, "_fuses_norm", None)
+    return bool(f and f())
+
+
+def apply_1x1(layer, x, norm):
+    """norm -> 1x1 layer; the normalisation is handed to the layer when it can fuse it (bem_b200.bayesian 1x1 layers)."""
+    if norm is None:
+        return layer(x)
+    if fuses_norm(layer):
+        return layer(x, pre_norm=norm)
+    return layer(norm(x))

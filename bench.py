@@ -243,7 +243,7 @@ def main_ours(args):
         per_launch_bytes = rec["bytes"] / rec["calls"]
         per_launch_ms = rec["ms"] / rec["calls"]
         ach = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "scan_fwd_kernel<float,float,12,8,N1> " + key, "achieved": ach, "peak": peak,
+        roof = {"bound": "hbm", "kernel": "scan_fwd_kernel<float,float,24,8,N1> " + key, "achieved": ach, "peak": peak,
                 "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                 "bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms, "launches_timed": rec["calls"]}
     shares = {k: {"calls": v["calls"], "ms_per_step": v["ms"] / args.steps,

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define BEM_ABI_VERSION 1
+#define BEM_ABI_VERSION 2
 
 /* element types of u/delta/B/C/x-activations */
 enum { BEM_F32 = 0, BEM_F16 = 1, BEM_BF16 = 2 };
@@ -190,9 +190,10 @@ int bem_ss2d_fwd(const BemSs2dFwdParams* p, void* stream);
  *                     (sample0 + s, i / 4), Box-Muller; element i takes lane i % 4.  The generator is restated in
  *                     oracle/philox.py so the same eps can be fed to the reference layer.
  *     eps_out != NULL -> the eps used is also written there (what the reference leaves in eps_weight).
- * bem_bayes_pointwise : 1x1 convolution / Linear2d with per-sample weights
+ * bem_bayes_pointwise : 1x1 convolution / Linear2d with per-sample weights on tcgen05 (3xTF32: fp32-accurate)
  *     x : (S*Bx, Cin, P)  w : (S or 1, Cout, Cin)  bias : (S or 1, Cout) or NULL  out : (S*Bx, Cout, P), fp32
- *     mu/rho/eps given instead of w  -> the sample step is fused into the weight load.
+ *     mu/sigma/eps given instead of w  -> the sample step w = mu + sigma * eps is fused into the weight load;
+ *     ln_gamma given -> the LayerNorm2d that precedes the layer (vmamba.py:59-64, eps = ln_eps) is fused in as well.
  * bem_bayes_depthwise : depthwise KxK (groups == channels, stride 1, dilation 1, zero padding K/2), K in {3}
  *     x : (S*Bx, C, H, W)  w : (S or 1, C, K, K)  bias : (S or 1, C) or NULL
  * ---------------------------------------------------------------------------------------------- */
@@ -216,12 +217,17 @@ typedef struct BemBayesPointwiseParams {
     int32_t cin, cout;
     int64_t P;           /* pixels per image */
     const float* x;
-    const float* w;      /* (S, cout, cin) or NULL when mu/rho/eps are given */
+    const float* w;      /* (S, cout, cin) or NULL when mu (+ sigma|rho, eps) are given */
     const float* mu;     /* (cout, cin) */
-    const float* rho;    /* (cout, cin) */
+    const float* rho;    /* (cout, cin): sigma = log1p(exp(rho)) evaluated in the kernel (slow; prefer `sigma`) */
     const float* eps;    /* (S, cout, cin) */
     const float* bias;   /* (S, cout) or NULL */
     float* out;
+    const float* sigma;     /* (cout, cin) precomputed log1p(exp(rho)), or NULL */
+    const float* ln_gamma;  /* (cin) or NULL: LayerNorm over the input channels of every pixel is applied to x first */
+    const float* ln_beta;   /* (cin) or NULL */
+    float ln_eps;
+    int32_t force_simt;     /* 1: fp32 CUDA-core tiles instead of the tcgen05 path (A/B measurements, no LayerNorm) */
 } BemBayesPointwiseParams;
 int bem_bayes_pointwise(const BemBayesPointwiseParams* p, void* stream);
 

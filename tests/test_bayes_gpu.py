@@ -217,3 +217,52 @@ def test_full_size_pointwise_and_depthwise_linearity():
     y = BF.depthwise_conv3x3(out, wd, b, 1)
     refd = torch.nn.functional.conv2d(out[:, :, :16].double(), wd[0].unsqueeze(1).double(), b[0].double(), padding=1, groups=320)
     assert nmax_err(y[0, :, :15].cpu().numpy(), refd[0, :, :15].cpu().numpy()) < TOL
+
+
+@pytest.mark.parametrize("cin,cout,P,S,Bx", [(40, 40, 1000, 1, 1), (40, 320, 777, 1, 2), (160, 40, 513, 3, 1), (80, 640, 300, 2, 1),
+                                              (8, 16, 130, 1, 1), (24, 7, 64, 1, 1), (640, 160, 200, 1, 1), (5, 300, 129, 1, 1)])
+def test_tcgen05_pointwise_matches_fp64_and_simt(cin, cout, P, S, Bx):
+    """3xTF32 tensor-core contraction: fp32-tier accuracy (1e-5) against an fp64 einsum, for ragged channel counts,
+    pixel tails and per-sample weights; and agreement with the fp32 CUDA-core kernel"""
+    from bem_b200.bayesian import functional as BF
+    g = torch.Generator(device="cpu").manual_seed(cin * 1000 + cout)
+    x = torch.randn(S * Bx, cin, P, generator=g).cuda()
+    w = (torch.randn(S, cout, cin, generator=g) / cin ** 0.5).cuda()
+    b = torch.randn(S, cout, generator=g).cuda()
+    out = BF.pointwise_conv(x, w, b, S)
+    ref = torch.einsum("soc,sbcp->sbop", w.double(), x.double().view(S, Bx, cin, P)) + b.double()[:, None, :, None]
+    assert nmax_err(out.cpu().numpy(), ref.reshape(S * Bx, cout, P).cpu().numpy()) < TOL
+    simt = BF.pointwise_conv(x, w, b, S, force_simt=True)
+    assert nmax_err(out.cpu().numpy(), simt.cpu().numpy()) < TOL
+
+
+@pytest.mark.parametrize("cin,cout,H,W", [(40, 40, 20, 30), (160, 40, 9, 13), (80, 640, 8, 8)])
+def test_fused_layernorm_pointwise(cin, cout, H, W):
+    """LayerNorm2d (vmamba.py:59-64) fused into the staging pass == F.layer_norm followed by the layer"""
+    import torch.nn.functional as F
+    from bem_b200 import bayesian
+    from bem_b200.ss2d import LayerNorm2d
+    torch.manual_seed(cin + cout)
+    norm = LayerNorm2d(cin).cuda()
+    with torch.no_grad():
+        norm.weight.normal_(1.0, 0.3)
+        norm.bias.normal_(0.0, 0.3)
+    layer = bayesian.Conv2dReparameterization(cin, cout, 1, bias=True).cuda().eval()
+    x = (torch.randn(2, cin, H, W, device="cuda") * 3 + 1.5)
+    eps_w = torch.randn_like(layer.eps_weight)
+    eps_b = torch.randn_like(layer.eps_bias)
+    with torch.no_grad():
+        fused = layer(x, eps_weight=eps_w, eps_bias=eps_b, pre_norm=norm)
+        xn = F.layer_norm(x.double().permute(0, 2, 3, 1), (cin,), norm.weight.double(), norm.bias.double(), norm.eps).permute(0, 3, 1, 2)
+        wv = (layer.mu_weight.double() + torch.log1p(torch.exp(layer.rho_weight.double())) * eps_w.double()).view(cout, cin)
+        bv = layer.mu_bias.double() + torch.log1p(torch.exp(layer.rho_bias.double())) * eps_b.double()
+        ref = torch.einsum("oc,bchw->bohw", wv, xn) + bv[None, :, None, None]
+        two_step = layer(norm(x), eps_weight=eps_w, eps_bias=eps_b)
+    assert nmax_err(fused.cpu().numpy(), ref.cpu().numpy()) < TOL
+    assert nmax_err(two_step.cpu().numpy(), ref.cpu().numpy()) < TOL
+    lin = bayesian.Linear2dReparameterization(cin, cin, bias=False).cuda().eval()
+    lin.deterministic = True
+    with torch.no_grad():
+        a = lin(x, pre_norm=norm)
+        bref = lin(norm(x))
+    assert nmax_err(a.cpu().numpy(), bref.cpu().numpy()) < TOL
