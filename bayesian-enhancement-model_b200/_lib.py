@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libbem_b200.so")
 
 BEM_F32, BEM_F16, BEM_BF16 = 0, 1, 2
 BEM_OK, BEM_ERR_BAD_ARG, BEM_ERR_WORKSPACE, BEM_ERR_UNSUPPORTED = 0, 10001, 10002, 10003
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 i32, i64, u64, vp = C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
 
@@ -53,7 +53,8 @@ class BemBayesSampleParams(C.Structure):
 class BemBayesPointwiseParams(C.Structure):
     _fields_ = [(n, i32) for n in ("n_samples", "batch", "cin", "cout")] + [("P", i64)] + \
                [(n, vp) for n in ("x", "w", "mu", "rho", "eps", "bias", "out", "sigma", "ln_gamma", "ln_beta")] + \
-               [("ln_eps", C.c_float), ("force_simt", i32)]
+               [("ln_eps", C.c_float), ("force_simt", i32), ("x_img_stride", i64), ("sample_interleave", i32),
+                ("workspace", vp), ("workspace_bytes", i64)]
 
 
 class BemBayesDepthwiseParams(C.Structure):
@@ -73,6 +74,7 @@ SYMBOLS = {
     "bem_ss2d_workspace_bytes": (i64, [C.c_int] * 6),
     "bem_ss2d_fwd": (C.c_int, [C.POINTER(BemSs2dFwdParams), vp]),
     "bem_bayes_sample": (C.c_int, [C.POINTER(BemBayesSampleParams), vp]),
+    "bem_bayes_pointwise_workspace_bytes": (i64, [C.c_int] * 3),
     "bem_bayes_pointwise": (C.c_int, [C.POINTER(BemBayesPointwiseParams), vp]),
     "bem_bayes_depthwise": (C.c_int, [C.POINTER(BemBayesDepthwiseParams), vp]),
     "bem_select_best": (C.c_int, [vp, i32, i32, vp, vp, vp]),
@@ -122,10 +124,10 @@ def require_cuda(*tensors):
 _workspaces: dict = {}
 
 
-def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    """Scratch for the scan look-back descriptors, cached per (device, stream): launches on one stream are ordered,
-    so they may share it; different streams get their own."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+def workspace(device: torch.device, nbytes: int, kind: str = "scan") -> torch.Tensor:
+    """Scratch (scan look-back descriptors / packed weight tiles), cached per (kind, device, stream): launches on one
+    stream are ordered, so they may share it; different streams get their own."""
+    key = (kind, device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
@@ -135,7 +137,7 @@ def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
 
 def scan_error_word(device: torch.device) -> int:
     """Watchdog word of the last scan launch on the current stream (0 = clean). Synchronises; tests only."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    key = ("scan", device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None:
         return 0

@@ -66,10 +66,14 @@ def sample_weights(mu, rho, eps=None, n_samples=1, seed=0, stream_id=0, sample0=
 
 
 # ---------------------------------------------------------------------------------------------------
-def _pointwise_raw(x, w=None, bias=None, mu=None, sigma=None, eps=None, n_samples=1, ln=None, force_simt=False):
-    """x: (S*Bx, Cin, *spatial) fp32; w: (S|1, Cout, Cin) or mu/sigma/eps for the fused sample-on-load path;
-    ln = (gamma, beta, eps): LayerNorm over the channels of every pixel fused into the activation staging."""
-    x = _f32c(x, "input")
+def _pointwise_raw(x, w=None, bias=None, mu=None, sigma=None, eps=None, n_samples=1, ln=None, force_simt=False,
+                   interleave=False):
+    """x: (S*Bx, Cin, *spatial) fp32 — any image stride, channels P apart; w: (S|1, Cout, Cin) or mu/sigma/eps for the
+    fused sample-on-load path; ln = (gamma, beta, eps): LayerNorm over the channels of every pixel fused into the
+    activation staging; interleave: image i uses weight set i % S instead of i // Bx."""
+    _lib.require_cuda(x)
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"bem_b200.bayesian: input must be float32 (got {x.dtype})")
     w, bias, mu, sigma, eps = (_f32c(t, n) for t, n in ((w, "w"), (bias, "bias"), (mu, "mu"), (sigma, "sigma"), (eps, "eps")))
     ref = w if w is not None else mu
     cout, cin = int(ref.shape[-2]), int(ref.shape[-1])
@@ -77,6 +81,11 @@ def _pointwise_raw(x, w=None, bias=None, mu=None, sigma=None, eps=None, n_sample
         raise RuntimeError(f"pointwise conv: input {tuple(x.shape)} does not match weight (.., {cout}, {cin})")
     batch = x.shape[0]
     P = x[0, 0].numel()
+    # accepted without a copy: pixels contiguous, channels P apart, any image stride (e.g. a channel slice of x_dbl)
+    inner_ok = x[0, 0].is_contiguous() and (cin == 1 or x.stride(1) == P)
+    if not inner_ok:
+        x = x.contiguous()
+    img_stride = x.stride(0) if batch > 1 else cin * P
     out = torch.empty((batch, cout) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
     g = b = None
     ln_eps = 0.0
@@ -84,12 +93,14 @@ def _pointwise_raw(x, w=None, bias=None, mu=None, sigma=None, eps=None, n_sample
         g, b, ln_eps = _f32c(ln[0], "ln weight"), _f32c(ln[1], "ln bias"), float(ln[2])
         if g.numel() != cin:
             raise RuntimeError(f"fused LayerNorm expects {cin} channels, got {g.numel()}")
+    ws = _lib.workspace(x.device, lib.bem_bayes_pointwise_workspace_bytes(n_samples, cin, cout), kind="pointwise")
     p = _lib.BemBayesPointwiseParams(n_samples=n_samples, batch=batch, cin=cin, cout=cout, P=P, x=_lib.ptr(x),
                                      w=_lib.ptr(w), mu=_lib.ptr(mu), rho=None, eps=_lib.ptr(eps), bias=_lib.ptr(bias),
                                      out=_lib.ptr(out), sigma=_lib.ptr(sigma), ln_gamma=_lib.ptr(g), ln_beta=_lib.ptr(b),
-                                     ln_eps=ln_eps, force_simt=int(bool(force_simt)))
+                                     ln_eps=ln_eps, force_simt=int(bool(force_simt)), x_img_stride=int(img_stride),
+                                     sample_interleave=int(bool(interleave)), workspace=_lib.ptr(ws), workspace_bytes=ws.numel())
     _lib.launch("bayes_pointwise", lib.bem_bayes_pointwise, p, x.device, key=(batch, cin, cout, P),
-                nbytes=4 * batch * P * (cin + cout))
+                nbytes=4 * batch * P * (cin + cout), kernels=1 if force_simt else 2)
     return out
 
 
@@ -119,6 +130,16 @@ class _PointwiseFn(torch.autograd.Function):
             if ctx.has_bias:
                 db = ds.sum(dim=(1, 3))
         return dx, dw, db, None
+
+
+def grouped_pointwise(x, w, bias=None):
+    """Grouped 1x1 convolution as the reference's `F.conv1d(x.view(B, K*Cin, L), w.view(K*Cout, Cin, 1), groups=K)`
+    (vmamba.py:659-661): x: (B, K, Cin, L) (any stride between (b, k) images), w: (K, Cout, Cin) -> (B, K, Cout, L).
+    The K groups are the kernel's weight sets. Inference only (no autograd)."""
+    B, K, Cin, L = x.shape
+    xv = x.reshape(B * K, Cin, L) if x.is_contiguous() else x.flatten(0, 1)
+    out = _pointwise_raw(xv, w=w, bias=bias, n_samples=K, interleave=True)
+    return out.view(B, K, -1, L)
 
 
 def pointwise_conv(x, w, bias=None, n_samples=1, ln=None, force_simt=False):

@@ -83,11 +83,11 @@ __global__ void __launch_bounds__(256) bayes_pointwise_kernel(const BemBayesPoin
     __shared__ __align__(16) float sX[PW_BK][PW_BN];
     const int img = blockIdx.z;
     const int imgs_per_sample = p.batch / p.n_samples;
-    const int s = p.n_samples > 1 ? img / imgs_per_sample : 0;
+    const int s = p.n_samples > 1 ? (p.sample_interleave ? img % p.n_samples : img / imgs_per_sample) : 0;
     const int co0 = blockIdx.y * PW_BM;
     const int64_t p0 = (int64_t)blockIdx.x * PW_BN;
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-    const float* x = p.x + (int64_t)img * p.cin * p.P;
+    const float* x = p.x + (int64_t)img * (p.x_img_stride ? p.x_img_stride : (int64_t)p.cin * p.P);
     const int64_t wofs = (int64_t)s * p.cout * p.cin;
     const bool vec_ok = (p.P % 4 == 0);
 
@@ -231,6 +231,11 @@ int bem_bayes_sample(const BemBayesSampleParams* p, void* stream) {
     if (blocks > cap) blocks = cap;
     bayes_sample_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(*p);
     return (int)cudaGetLastError();
+}
+
+int64_t bem_bayes_pointwise_workspace_bytes(int n_samples, int cin, int cout) {
+    if (n_samples <= 0 || cin <= 0 || cout <= 0) return 0;
+    return bayes_pointwise_tc_workspace(n_samples, cin, cout);
 }
 
 int bem_bayes_pointwise(const BemBayesPointwiseParams* p, void* stream) {

@@ -12,9 +12,10 @@
 //   * fp32 parity: every operand is split into a tf32 "hi" part and the fp32 remainder "lo"; three MMAs per K step
 //     (hi*hi + hi*lo + lo*hi) give ~2^-21 relative accuracy, i.e. the 1e-5 tier of the parity tests. The contraction is
 //     HBM-bound at these channel counts (arithmetic intensity 20-140 FLOP/B), so the 3x tensor work is free.
-//   * the operand staging pass is where the fusion happens: the 128 threads of a CTA read x coalesced along pixels,
-//     apply the (optional) LayerNorm with per-pixel statistics, split, and store K-major; the weight tile is formed as
-//     mu + log1p(exp(rho)) * eps while it is staged, so the sampled weights never exist in HBM.
+//   * the operand staging is where the fusion happens: the 128 threads of a CTA read x coalesced along pixels, apply
+//     the (optional) LayerNorm with per-pixel statistics, split, and store K-major. The weights are sampled
+//     (mu + sigma * eps), split and laid out once per launch by a tiny pack kernel, and reach shared memory with one
+//     TMA bulk copy per K chunk; a sampled fp32 weight tensor is never materialised.
 //   * epilogue: tcgen05.ld (32 lanes x 32 bit x 16 columns) -> + bias -> 128-byte coalesced stores along pixels.
 #include "bem_kernels.h"
 #include "scan_common.cuh"
@@ -73,35 +74,82 @@ constexpr uint32_t TC_LBO = 128;
 constexpr uint32_t TC_SBO = (TC_KC / 4) * 128;
 __device__ __forceinline__ uint32_t tile_off(int row, int k4) { return (uint32_t)((row >> 3) * TC_SBO + k4 * TC_LBO + (row & 7) * 16); }
 
-__global__ void __launch_bounds__(128, 2) bayes_pointwise_tc_kernel(const BemBayesPointwiseParams p, const int NT) {
+// ------------------------------------------------------------------------------------------------
+// weight pack: sample (w = mu + sigma * eps), split into tf32 hi / fp32 remainder lo, and lay the tiles out exactly as
+// the MMA wants them in shared memory, so the GEMM fetches its B operand with one TMA bulk copy per K chunk.
+// pack[((s * ntiles + tile) * nk + kc)] = [hi tile NT x KC | lo tile NT x KC], canonical K-major layout (tile_off)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bayes_weight_pack_kernel(const BemBayesPointwiseParams p, const int NT, const int ntiles,
+                                                              const int nk, float* __restrict__ pack) {
+    const int blk = blockIdx.x;             // (s, tile, kc)
+    const int kc = blk % nk;
+    const int tile = (blk / nk) % ntiles;
+    const int s = blk / (nk * ntiles);
+    const int n0 = tile * NT, k0 = kc * TC_KC;
+    const int64_t wofs = (int64_t)s * p.cout * p.cin;
+    unsigned char* hi_t = reinterpret_cast<unsigned char*>(pack + (int64_t)blk * 2 * NT * TC_KC);
+    unsigned char* lo_t = hi_t + (size_t)NT * TC_KC * 4;
+    for (int idx = threadIdx.x; idx < NT * (TC_KC / 4); idx += blockDim.x) {
+        const int n = idx / (TC_KC / 4), k4 = idx - n * (TC_KC / 4);
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int ci = k0 + k4 * 4 + e, co = n0 + n;
+            float w = 0.f;
+            if (co < p.cout && ci < p.cin) {
+                const int64_t wi = (int64_t)co * p.cin + ci;
+                if (p.w) w = p.w[wofs + wi];
+                else {
+                    w = p.mu[wi];
+                    if (p.sigma) w = fmaf(p.sigma[wi], p.eps[wofs + wi], w);
+                    else if (p.rho) w = fmaf(log1pf(expf(p.rho[wi])), p.eps[wofs + wi], w);
+                }
+            }
+            hi[e] = tf32_hi(w);
+            lo[e] = w - hi[e];
+        }
+        const uint32_t off = tile_off(n, k4);
+        *reinterpret_cast<float4*>(hi_t + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(lo_t + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+__global__ void __launch_bounds__(128, 4) bayes_pointwise_tc_kernel(const BemBayesPointwiseParams p, const int NT, const int ntiles,
+                                                                  const float* __restrict__ pack, const uint32_t tmem_cols) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    // stage s: [A hi | A lo | B hi | B lo]; A tiles 128 x KC, B tiles NT x KC
+    // stage s: [A hi | A lo | B hi | B lo]; A tiles 128 x KC (staged by the threads), B tiles NT x KC (TMA from `pack`)
     const uint32_t a_bytes = TC_M * TC_KC * 4;
     const uint32_t b_bytes = (uint32_t)NT * TC_KC * 4;
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
     unsigned char* tail = smem + 2 * stage_bytes;
-    uint64_t* mma_done = reinterpret_cast<uint64_t*>(tail);        // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 16);
-    float* s_gamma = reinterpret_cast<float*>(tail + 32);           // [cin] LayerNorm weight / bias (optional)
+    uint64_t* mma_done = reinterpret_cast<uint64_t*>(tail);        // [2] MMAs reading a stage have completed
+    uint64_t* b_full = mma_done + 2;                                // [2] B tiles of a stage have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 32);
+    float* s_gamma = reinterpret_cast<float*>(tail + 48);           // [cin] LayerNorm weight / bias (optional)
     float* s_beta = s_gamma + p.cin;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n0 = blockIdx.x * NT;                                 // first output channel of this tile
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int n0 = tile * NT;                                       // first output channel of this tile
     const int64_t p0 = (int64_t)blockIdx.y * TC_M;
     const int img = blockIdx.z;
-    const int s_idx = p.n_samples > 1 ? img / (p.batch / p.n_samples) : 0;
+    const int s_idx = p.n_samples > 1 ? (p.sample_interleave ? img % p.n_samples : img / (p.batch / p.n_samples)) : 0;
     const int nvalid = min(NT, p.cout - n0);
-    const float* x = p.x + (int64_t)img * p.cin * p.P;
-    const int64_t wofs = (int64_t)s_idx * p.cout * p.cin;
+    const float* x = p.x + (int64_t)img * (p.x_img_stride ? p.x_img_stride : (int64_t)p.cin * p.P);
     const int64_t pix = p0 + tid;
     const bool pvalid = pix < p.P;
+    const int nk = (p.cin + TC_KC - 1) / TC_KC;
+    const float* bsrc = pack + ((int64_t)(s_idx * ntiles + tile) * nk) * 2 * NT * TC_KC;
 
     if (tid == 0) {
         mbar_init(&mma_done[0], 1);
         mbar_init(&mma_done[1], 1);
+        mbar_init(&b_full[0], 1);
+        mbar_init(&b_full[1], 1);
         fence_barrier_init();
+        fence_proxy_async();
     }
-    if (warp == 0) tmem_alloc(tmem_slot, TC_NMAX);
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
     const bool ln = p.ln_gamma != nullptr;
     if (ln) {
         for (int i = tid; i < p.cin; i += 128) {
@@ -109,18 +157,22 @@ __global__ void __launch_bounds__(128, 2) bayes_pointwise_tc_kernel(const BemBay
             s_beta[i] = p.ln_beta ? p.ln_beta[i] : 0.f;
         }
     }
-    // LayerNorm statistics of this thread's pixel over the input channels (two passes: mean, centred second moment)
+    // LayerNorm statistics of this thread's pixel over the input channels: one pass over sums shifted by the first
+    // channel (well conditioned), all loads independent
     float mean = 0.f, rstd = 1.f;
     if (ln && pvalid) {
-        float sum = 0.f;
-        for (int ci = 0; ci < p.cin; ++ci) sum += x[(int64_t)ci * p.P + pix];
-        mean = sum / (float)p.cin;
-        float sq = 0.f;
-        for (int ci = 0; ci < p.cin; ++ci) {
-            const float dlt = x[(int64_t)ci * p.P + pix] - mean;
-            sq = fmaf(dlt, dlt, sq);
+        const float x0 = x[pix];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+        for (int ci = 1; ci < p.cin; ++ci) {
+            const float dlt = x[(int64_t)ci * p.P + pix] - x0;
+            s1 += dlt;
+            s2 = fmaf(dlt, dlt, s2);
         }
-        rstd = rsqrtf(sq / (float)p.cin + p.ln_eps);
+        const float inv = 1.f / (float)p.cin;
+        const float m1 = s1 * inv;
+        mean = x0 + m1;
+        rstd = rsqrtf(fmaxf(s2 * inv - m1 * m1, 0.f) + p.ln_eps);
     }
     tc_fence_before();
     __syncthreads();
@@ -129,28 +181,34 @@ __global__ void __launch_bounds__(128, 2) bayes_pointwise_tc_kernel(const BemBay
 
     // instruction descriptor: D fp32, A/B tf32, K-major both, N = NT, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-    const int nk = (p.cin + TC_KC - 1) / TC_KC;
 
     for (int kc = 0; kc < nk; ++kc) {
         const int st = kc & 1;
-        if (kc >= 2) mbar_wait(&mma_done[st], ((kc >> 1) - 1) & 1, nullptr);   // MMAs that read this stage are done
+        const uint32_t use = kc >> 1;
+        if (kc >= 2) mbar_wait(&mma_done[st], (use - 1) & 1, nullptr);   // MMAs that read this stage are done
         unsigned char* sA_hi = smem + (size_t)st * stage_bytes;
         unsigned char* sA_lo = sA_hi + a_bytes;
-        unsigned char* sB_hi = sA_lo + a_bytes;
-        unsigned char* sB_lo = sB_hi + b_bytes;
+        unsigned char* sB_hi = sA_lo + a_bytes;   // lo tile follows contiguously, as in `pack`
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&b_full[st], 2 * b_bytes);
+            bulk_g2s(sB_hi, bsrc + (int64_t)kc * 2 * NT * TC_KC, 2 * b_bytes, &b_full[st]);
+        }
         const int k0 = kc * TC_KC;
-        // ---- activation tile: row = this thread's pixel, 16 channels ----
+        // ---- activation tile: row = this thread's pixel, 16 channels (loads first, then the arithmetic) ----
+        float xv[TC_KC];
+#pragma unroll
+        for (int e = 0; e < TC_KC; ++e) {
+            const int ci = k0 + e;
+            xv[e] = (pvalid && ci < p.cin) ? x[(int64_t)ci * p.P + pix] : 0.f;
+        }
 #pragma unroll
         for (int k4 = 0; k4 < TC_KC / 4; ++k4) {
             float hi[4], lo[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int ci = k0 + k4 * 4 + e;
-                float v = 0.f;
-                if (pvalid && ci < p.cin) {
-                    v = x[(int64_t)ci * p.P + pix];
-                    if (ln) v = fmaf((v - mean) * rstd, s_gamma[ci], s_beta[ci]);
-                }
+                float v = xv[k4 * 4 + e];
+                if (ln && pvalid && ci < p.cin) v = fmaf((v - mean) * rstd, s_gamma[ci], s_beta[ci]);
                 hi[e] = tf32_hi(v);
                 lo[e] = v - hi[e];
             }
@@ -158,36 +216,13 @@ __global__ void __launch_bounds__(128, 2) bayes_pointwise_tc_kernel(const BemBay
             *reinterpret_cast<float4*>(sA_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<float4*>(sA_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
-        // ---- weight tile: NT rows x 16 channels, sampled on load ----
-        for (int idx = tid; idx < NT * (TC_KC / 4); idx += 128) {
-            const int n = idx / (TC_KC / 4), k4 = idx - n * (TC_KC / 4);
-            float hi[4], lo[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int ci = k0 + k4 * 4 + e;
-                float w = 0.f;
-                if (n < nvalid && ci < p.cin) {
-                    const int64_t wi = (int64_t)(n0 + n) * p.cin + ci;
-                    if (p.w) w = p.w[wofs + wi];
-                    else {
-                        w = p.mu[wi];
-                        if (p.sigma) w = fmaf(p.sigma[wi], p.eps[wofs + wi], w);
-                        else if (p.rho) w = fmaf(log1pf(expf(p.rho[wi])), p.eps[wofs + wi], w);
-                    }
-                }
-                hi[e] = tf32_hi(w);
-                lo[e] = w - hi[e];
-            }
-            const uint32_t off = tile_off(n, k4);
-            *reinterpret_cast<float4*>(sB_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4*>(sB_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        }
         fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
+            mbar_wait(&b_full[st], use & 1, nullptr);
             tc_fence_after();
-            const uint32_t aH = smem_u32(sA_hi), aL = smem_u32(sA_lo), bH = smem_u32(sB_hi), bL = smem_u32(sB_lo);
+            const uint32_t aH = smem_u32(sA_hi), aL = smem_u32(sA_lo), bH = smem_u32(sB_hi), bL = bH + b_bytes;
 #pragma unroll
             for (int ks = 0; ks < TC_KC / 8; ++ks) {
                 const uint32_t adv = ks * 2 * TC_LBO;   // 8 tf32 = two 16-byte K chunks per MMA
@@ -225,20 +260,36 @@ __global__ void __launch_bounds__(128, 2) bayes_pointwise_tc_kernel(const BemBay
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, TC_NMAX);
+    if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+static void tc_tiling(int cin, int cout, int& ntiles, int& NT, int& nk) {
+    // output-channel tiling: as few tiles as possible, each a multiple of 16 and at most 256 channels
+    ntiles = (cout + TC_NMAX - 1) / TC_NMAX;
+    NT = ((cout + ntiles - 1) / ntiles + 15) / 16 * 16;
+    if (NT < 16) NT = 16;
+    nk = (cin + TC_KC - 1) / TC_KC;
+}
+
+int64_t bayes_pointwise_tc_workspace(int n_samples, int cin, int cout) {
+    int ntiles, NT, nk;
+    tc_tiling(cin, cout, ntiles, NT, nk);
+    return (int64_t)n_samples * ntiles * nk * 2 * NT * TC_KC * (int64_t)sizeof(float);
 }
 
 int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t stream) {
-    // output-channel tiling: as few tiles as possible, each a multiple of 16 and at most 256 channels
-    const int ntiles = (p.cout + TC_NMAX - 1) / TC_NMAX;
-    int NT = ((p.cout + ntiles - 1) / ntiles + 15) / 16 * 16;
-    if (NT < 16) NT = 16;
-    const int smem_bytes = 2 * (2 * TC_M * TC_KC * 4 + 2 * NT * TC_KC * 4) + 32 + 2 * p.cin * 4 + 64;
+    int ntiles, NT, nk;
+    tc_tiling(p.cin, p.cout, ntiles, NT, nk);
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < NT) tmem_cols <<= 1;
+    const int smem_bytes = 2 * (2 * TC_M * TC_KC * 4 + 2 * NT * TC_KC * 4) + 48 + 2 * p.cin * 4 + 64;
     if (smem_bytes > 227 * 1024) return BEM_ERR_UNSUPPORTED;
-    static int attr_set[64] = {0};
+    const int64_t need = bayes_pointwise_tc_workspace(p.n_samples, p.cin, p.cout);
+    if (!p.workspace || p.workspace_bytes < need || (reinterpret_cast<uintptr_t>(p.workspace) & 15)) return BEM_ERR_WORKSPACE;
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
+    static int attr_set[64] = {0};
     if (attr_set[dev] < smem_bytes) {
         cudaError_t e = cudaFuncSetAttribute(bayes_pointwise_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return (int)e;
@@ -246,8 +297,10 @@ int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t str
     }
     const int64_t ptiles = (p.P + TC_M - 1) / TC_M;
     if (ptiles > 65535 || p.batch > 65535) return BEM_ERR_UNSUPPORTED;
-    dim3 grid((unsigned)((p.cout + NT - 1) / NT), (unsigned)ptiles, (unsigned)p.batch);
-    bayes_pointwise_tc_kernel<<<grid, 128, smem_bytes, stream>>>(p, NT);
+    float* pack = reinterpret_cast<float*>(p.workspace);
+    bayes_weight_pack_kernel<<<p.n_samples * ntiles * nk, 256, 0, stream>>>(p, NT, ntiles, nk, pack);
+    dim3 grid((unsigned)ntiles, (unsigned)ptiles, (unsigned)p.batch);
+    bayes_pointwise_tc_kernel<<<grid, 128, smem_bytes, stream>>>(p, NT, ntiles, pack, tmem_cols);
     return (int)cudaGetLastError();
 }
 

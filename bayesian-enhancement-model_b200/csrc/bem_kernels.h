@@ -86,6 +86,7 @@ int scan_fwd_dispatch(const ScanFwdArgs& a, int dtype, int out_dtype, int sm_cou
 int scan_bwd_dispatch(ScanBwdArgs& a, int dtype, int dout_dtype, int sm_count, cudaStream_t stream);
 
 int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t stream);
+int64_t bayes_pointwise_tc_workspace(int n_samples, int cin, int cout);
 
 int device_sm_count();
 

@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .bayesian import functional as BF
 from .csm import cross_merge_fn, cross_scan_fn
 from .selective_scan import selective_scan_fn
 
@@ -31,11 +32,19 @@ def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_pr
     K, _, R = dt_projs_weight.shape
     L = H * W
     xs = cross_scan_fn(x, in_channel_first=True, out_channel_first=True, scans=scans)            # (B, 4, D, L)
-    x_dbl = F.conv1d(xs.view(B, -1, L), x_proj_weight.view(-1, D, 1),
-                     bias=(x_proj_bias.view(-1) if x_proj_bias is not None else None), groups=K)  # vmamba.py:659
-    x_dbl = x_dbl.view(B, K, -1, L)
-    dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)                                             # vmamba.py:660
-    dts = F.conv1d(dts.contiguous().view(B, -1, L), dt_projs_weight.view(K * D, -1, 1), groups=K)  # vmamba.py:661
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or x_proj_weight.requires_grad or dt_projs_weight.requires_grad)
+    if needs_grad or xs.dtype != torch.float32:
+        x_dbl = F.conv1d(xs.view(B, -1, L), x_proj_weight.view(-1, D, 1),
+                         bias=(x_proj_bias.view(-1) if x_proj_bias is not None else None), groups=K)  # vmamba.py:659
+        x_dbl = x_dbl.view(B, K, -1, L)
+        dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)                                             # vmamba.py:660
+        dts = F.conv1d(dts.contiguous().view(B, -1, L), dt_projs_weight.view(K * D, -1, 1), groups=K)  # vmamba.py:661
+    else:
+        # the same two grouped 1x1 contractions on the tcgen05 pointwise kernel, the K directions as its weight sets;
+        # dts is read as a strided channel slice of x_dbl (no .contiguous() copy)
+        x_dbl = BF.grouped_pointwise(xs, x_proj_weight, None if x_proj_bias is None else x_proj_bias.view(K, -1))
+        dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
+        dts = BF.grouped_pointwise(dts, dt_projs_weight)
     xs = xs.view(B, -1, L)
     dts = dts.contiguous().view(B, -1, L)
     As = -A_logs.to(torch.float).exp()                  # (K * D, N)

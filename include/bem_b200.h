@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define BEM_ABI_VERSION 2
+#define BEM_ABI_VERSION 3
 
 /* element types of u/delta/B/C/x-activations */
 enum { BEM_F32 = 0, BEM_F16 = 1, BEM_BF16 = 2 };
@@ -228,7 +228,13 @@ typedef struct BemBayesPointwiseParams {
     const float* ln_beta;   /* (cin) or NULL */
     float ln_eps;
     int32_t force_simt;     /* 1: fp32 CUDA-core tiles instead of the tcgen05 path (A/B measurements, no LayerNorm) */
+    int64_t x_img_stride;   /* elements between consecutive images of x; 0 = cin * P (channel stride is always P) */
+    int32_t sample_interleave; /* 0: image i uses weight set i / (batch / S); 1: i % S (grouped 1x1: x_proj / dt_proj,
+                                  basicsr/vmamba/models/vmamba.py:659-661, with the K directions as weight sets) */
+    void* workspace;        /* bem_bayes_pointwise_workspace_bytes() bytes, 16-byte aligned: packed weight tiles */
+    int64_t workspace_bytes;
 } BemBayesPointwiseParams;
+int64_t bem_bayes_pointwise_workspace_bytes(int n_samples, int cin, int cout);
 int bem_bayes_pointwise(const BemBayesPointwiseParams* p, void* stream);
 
 typedef struct BemBayesDepthwiseParams {
