@@ -17,6 +17,9 @@
 //     (mu + sigma * eps), split and laid out once per launch by a tiny pack kernel, and reach shared memory with one
 //     TMA bulk copy per K chunk; a sampled fp32 weight tensor is never materialised.
 //   * epilogue: tcgen05.ld (32 lanes x 32 bit x 16 columns) -> + bias -> 128-byte coalesced stores along pixels.
+#include <algorithm>
+#include <cstdlib>
+
 #include "bem_kernels.h"
 #include "scan_common.cuh"
 
@@ -66,6 +69,30 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
+// non-blocking probe loop: lower wake-up latency than try_wait's hardware suspend, for the waits on the critical path
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (int tries = 0; tries < (1 << 26); ++tries) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
 // canonical K-major layout of one [rows x TC_KC] fp32 tile: core matrix = 8 rows x 16 bytes, K-adjacent core matrices
@@ -79,8 +106,48 @@ __device__ __forceinline__ uint32_t tile_off(int row, int k4) { return (uint32_t
 // the MMA wants them in shared memory, so the GEMM fetches its B operand with one TMA bulk copy per K chunk.
 // pack[((s * ntiles + tile) * nk + kc)] = [hi tile NT x KC | lo tile NT x KC], canonical K-major layout (tile_off)
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sampled_weight(const BemBayesPointwiseParams& p, int64_t wofs, int64_t wi) {
+    if (p.w) return p.w[wofs + wi];
+    float w = p.mu[wi];
+    if (p.sigma) w = fmaf(p.sigma[wi], p.eps[wofs + wi], w);
+    else if (p.rho) w = fmaf(log1pf(expf(p.rho[wi])), p.eps[wofs + wi], w);
+    return w;
+}
+
+// `fold_ln` (persistent kernel): the LayerNorm weight is folded into the packed tiles, W' = gamma * W, and the blocks
+// past the tile blocks write, per (sample, output channel n), vec = ( s_n = sum_ci W'[n][ci], t_n = sum_ci beta[ci] *
+// W[n][ci] + bias[n] ), so that LN(x) . W = rstd * (x . W' - mean * s) + t is finished in the GEMM epilogue.
 __global__ void __launch_bounds__(256) bayes_weight_pack_kernel(const BemBayesPointwiseParams p, const int NT, const int ntiles,
-                                                              const int nk, float* __restrict__ pack) {
+                                                              const int nk, float* __restrict__ pack, const int fold_ln,
+                                                              float* __restrict__ vec) {
+    const int tile_blocks = p.n_samples * ntiles * nk;
+    if ((int)blockIdx.x >= tile_blocks) {
+        const int cblocks = (p.cout + 7) / 8;
+        const int vb = blockIdx.x - tile_blocks;
+        const int s = vb / cblocks, co = (vb - s * cblocks) * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+        if (co >= p.cout) return;
+        const int64_t wofs = (int64_t)s * p.cout * p.cin;
+        float ss = 0.f, tt = 0.f;
+        if (p.ln_gamma) {
+            for (int ci = lane; ci < p.cin; ci += 32) {
+                const float w = sampled_weight(p, wofs, (int64_t)co * p.cin + ci);
+                ss = fmaf(w, p.ln_gamma[ci], ss);
+                if (p.ln_beta) tt = fmaf(w, p.ln_beta[ci], tt);
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                tt += __shfl_xor_sync(0xffffffffu, tt, o);
+            }
+        }
+        if (lane == 0) {
+            if (p.bias) tt += p.bias[(int64_t)s * p.cout + co];
+            float* v = vec + ((int64_t)s * ntiles + co / NT) * 2 * NT;
+            v[2 * (co % NT)] = ss;
+            v[2 * (co % NT) + 1] = tt;
+        }
+        return;
+    }
     const int blk = blockIdx.x;             // (s, tile, kc)
     const int kc = blk % nk;
     const int tile = (blk / nk) % ntiles;
@@ -97,13 +164,8 @@ __global__ void __launch_bounds__(256) bayes_weight_pack_kernel(const BemBayesPo
             const int ci = k0 + k4 * 4 + e, co = n0 + n;
             float w = 0.f;
             if (co < p.cout && ci < p.cin) {
-                const int64_t wi = (int64_t)co * p.cin + ci;
-                if (p.w) w = p.w[wofs + wi];
-                else {
-                    w = p.mu[wi];
-                    if (p.sigma) w = fmaf(p.sigma[wi], p.eps[wofs + wi], w);
-                    else if (p.rho) w = fmaf(log1pf(expf(p.rho[wi])), p.eps[wofs + wi], w);
-                }
+                w = sampled_weight(p, wofs, (int64_t)co * p.cin + ci);
+                if (fold_ln && p.ln_gamma) w *= p.ln_gamma[ci];
             }
             hi[e] = tf32_hi(w);
             lo[e] = w - hi[e];
@@ -263,6 +325,316 @@ __global__ void __launch_bounds__(128, 4) bayes_pointwise_tc_kernel(const BemBay
     if (warp == 0) tmem_dealloc(tmem, tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------------
+// persistent, warp-specialised form (the default): one CTA per SM walks (image, pixel tile, output-channel tile) items
+//   warps 0,19  producers: raw x rows (cp.async, one 512-byte row per warp instruction) into a deep shared-memory ring
+//   warp 18     TMA producer: packed weight tiles (ring) and the per-channel epilogue vectors
+//   warp 1      MMA issuer: 3 x tcgen05.mma per K step into one of two TMEM accumulators (2 x 256 columns)
+//   warps 2-9   transform: raw x tile -> (x - shift) split into tf32 hi / lo, K-major canonical layout; LayerNorm sums
+//   warps 10-17 epilogue: tcgen05.ld -> rstd * (acc - mean * s_n) + t_n -> 128-byte coalesced stores
+// so the loads of item i+1, the MMAs of item i and the stores of item i-1 overlap, with 48 KB of loads in flight per SM.
+// Rows of A past the end of the image carry whatever the stage held before: row m of D depends on row m of A only and
+// those rows are never stored. Input channels past `cin` (last K chunk) are zeroed, they feed every output.
+// ------------------------------------------------------------------------------------------------
+constexpr int P3_LAG = 6;     // cp.async groups (chunks) in flight per producer warp
+constexpr int P3_RS_MAX = 16;  // raw x stages  (TC_KC rows x 128 pixels x 4 B = 8 KB each), as many as fit
+constexpr int P3_AS_MAX = 6;   // A stages      (hi | lo, 16 KB each)
+constexpr int P3_BS_MAX = 8;   // B stages      (hi | lo, 2 * NT * TC_KC * 4 B each)
+constexpr int P3_XW = 8;       // transform warps
+constexpr int P3_EW = 8;       // epilogue warps (two per TMEM lane quarter, alternating 16-column groups)
+constexpr int P3_THREADS = (4 + P3_XW + P3_EW) * 32;
+
+struct Ring {   // position in a ring of `n` stages and the phase bit of its mbarriers
+    uint32_t s = 0, ph = 0;
+    __device__ __forceinline__ void next(uint32_t n) {
+        if (++s == n) {
+            s = 0;
+            ph ^= 1;
+        }
+    }
+};
+constexpr uint32_t P3_RAW_BYTES = TC_KC * TC_M * 4;
+constexpr uint32_t P3_A_BYTES = TC_M * TC_KC * 4;
+
+struct P3Item {
+    int tile, img, s_idx, npx;
+    int64_t p0;
+};
+__device__ __forceinline__ P3Item p3_item(const BemBayesPointwiseParams& p, int64_t it, int ntiles, int ptiles) {
+    P3Item r;
+    r.tile = (int)(it % ntiles);
+    const int64_t q = it / ntiles;
+    r.p0 = (q % ptiles) * TC_M;
+    r.img = (int)(q / ptiles);
+    r.s_idx = p.n_samples > 1 ? (p.sample_interleave ? r.img % p.n_samples : r.img / (p.batch / p.n_samples)) : 0;
+    r.npx = (int)min((int64_t)TC_M, p.P - r.p0);
+    return r;
+}
+
+template <bool LN>
+__global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(const BemBayesPointwiseParams p, const int NT, const int ntiles,
+                                                                          const int ptiles, const int64_t n_items,
+                                                                          const float* __restrict__ pack, const float* __restrict__ vec,
+                                                                          const uint32_t RS, const uint32_t BS, const uint32_t AS, const int spin) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t b_bytes = (uint32_t)NT * TC_KC * 4;
+    unsigned char* s_raw = smem;
+    unsigned char* s_a = s_raw + RS * P3_RAW_BYTES;
+    unsigned char* s_b = s_a + AS * 2 * P3_A_BYTES;
+    float2* s_vec = reinterpret_cast<float2*>(s_b + BS * 2 * b_bytes);         // [2 acc buffers][NT] (s_n, t_n)
+    float2* s_part = s_vec + 2 * NT;                                           // [2 acc buffers][2 K halves][128] (sum, sum sq)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 2 * 2 * TC_M);
+    uint64_t* raw_full = bars;
+    uint64_t* raw_empty = raw_full + P3_RS_MAX;
+    uint64_t* a_full = raw_empty + P3_RS_MAX;
+    uint64_t* a_empty = a_full + P3_AS_MAX;
+    uint64_t* b_full = a_empty + P3_AS_MAX;
+    uint64_t* b_empty = b_full + P3_BS_MAX;
+    uint64_t* acc_full = b_empty + P3_BS_MAX;
+    uint64_t* acc_empty = acc_full + 2;
+    uint64_t* stats_full = acc_empty + 2;
+    uint64_t* vec_full = stats_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(vec_full + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nk = (p.cin + TC_KC - 1) / TC_KC;
+
+    if (tid == 0) {
+        for (int i = 0; i < (int)RS; ++i) { mbar_init(&raw_full[i], 64); mbar_init(&raw_empty[i], P3_XW); }
+        for (int i = 0; i < (int)AS; ++i) { mbar_init(&a_full[i], P3_XW); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < (int)BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], P3_EW);
+            mbar_init(&stats_full[i], P3_XW);
+            mbar_init(&vec_full[i], 1);
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0 || warp == 3 + P3_XW + P3_EW) {
+        // ---------------- producers: activations (LDGSTS, 16 B per lane, one 512-byte row per instruction) ----------------
+        // 512-byte bulk copies are bound by their per-copy overhead, and a cp.async-tracked mbarrier arrive serialises a
+        // warp's copies behind it (one chunk in flight). So: plain cp.async groups, P3_LAG chunks in flight per warp, and an
+        // ordinary arrive once a group has landed. Rows past the last input channel and pixels past the image are
+        // zero-filled through the src-size operand. Two warps, each taking 8 of the 16 rows of every chunk.
+        const int row0 = warp == 0 ? 0 : TC_KC / 2;
+        Ring r, done;
+        uint32_t issued = 0;
+        for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+            const P3Item w = p3_item(p, it, ntiles, ptiles);
+            const int px = min(lane * 4, w.npx - 4);            // npx % 4 == 0; lanes past the end copy 0 bytes from a valid address
+            const uint32_t pbytes = lane * 4 < w.npx ? 16u : 0u;
+            const float* x = p.x + (int64_t)w.img * (p.x_img_stride ? p.x_img_stride : (int64_t)p.cin * p.P) + w.p0 + px;
+            for (int kc = 0; kc < nk; ++kc, r.next(RS)) {
+                if (lane == 0) mbar_wait(&raw_empty[r.s], r.ph ^ 1, nullptr);
+                __syncwarp();
+                const uint32_t dst = smem_u32(s_raw + r.s * P3_RAW_BYTES) + (row0 * TC_M + lane * 4) * 4;
+                const int c0 = kc * TC_KC + row0;
+                if (c0 + TC_KC / 2 <= p.cin) {
+                    const float* src = x + (int64_t)c0 * p.P;
+#pragma unroll
+                    for (int row = 0; row < TC_KC / 2; ++row, src += p.P)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + row * (TC_M * 4)), "l"(src), "r"(pbytes) : "memory");
+                } else {
+#pragma unroll
+                    for (int row = 0; row < TC_KC / 2; ++row) {
+                        const float* src = x + (int64_t)min(c0 + row, p.cin - 1) * p.P;
+                        const uint32_t sz = c0 + row < p.cin ? pbytes : 0u;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + row * (TC_M * 4)), "l"(src), "r"(sz) : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (++issued > P3_LAG) {
+                    asm volatile("cp.async.wait_group %0;" ::"n"(P3_LAG) : "memory");
+                    mbar_arrive(&raw_full[done.s]);
+                    done.next(RS);
+                }
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        for (uint32_t i = issued > P3_LAG ? issued - P3_LAG : 0; i < issued; ++i, done.next(RS)) mbar_arrive(&raw_full[done.s]);
+    } else if (warp == 2 + P3_XW + P3_EW) {
+        // ---------------- TMA producer: weights ----------------
+        if (lane == 0) {
+            Ring r;
+            uint32_t li = 0;
+            for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
+                const P3Item w = p3_item(p, it, ntiles, ptiles);
+                const float* bsrc = pack + ((int64_t)(w.s_idx * ntiles + w.tile) * nk) * 2 * NT * TC_KC;
+                const uint32_t buf = li & 1;
+                mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1, nullptr);   // the epilogue two items back has read its vectors
+                mbar_arrive_expect_tx(&vec_full[buf], (uint32_t)NT * 8);
+                bulk_g2s(s_vec + buf * NT, vec + ((int64_t)w.s_idx * ntiles + w.tile) * 2 * NT, (uint32_t)NT * 8, &vec_full[buf]);
+                for (int kc = 0; kc < nk; ++kc, r.next(BS)) {
+                    mbar_wait(&b_empty[r.s], r.ph ^ 1, nullptr);
+                    mbar_arrive_expect_tx(&b_full[r.s], 2 * b_bytes);
+                    bulk_g2s(s_b + r.s * 2 * b_bytes, bsrc + (int64_t)kc * 2 * NT * TC_KC, 2 * b_bytes, &b_full[r.s]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        // The whole warp walks the loop (uniform control flow keeps descriptors in uniform registers); one elected lane
+        // issues. Descriptors are one base per operand plus the stage / K-step offset in the 14-bit address field.
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+        const uint64_t descA0 = make_desc(smem_u32(s_a), TC_LBO, TC_SBO), descB0 = make_desc(smem_u32(s_b), TC_LBO, TC_SBO);
+        const uint32_t b_step = (2 * b_bytes) >> 4, b_lo = b_bytes >> 4;
+        Ring ra, rb;
+        uint32_t li = 0;
+        for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
+            const uint32_t buf = li & 1;
+            mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1, nullptr);   // the epilogue has drained this accumulator
+            const uint32_t d = tmem + buf * 256;
+            for (int kc = 0; kc < nk; ++kc, ra.next(AS), rb.next(BS)) {
+                if (spin) {
+                    mbar_spin(&a_full[ra.s], ra.ph);
+                    mbar_spin(&b_full[rb.s], rb.ph);
+                } else {
+                    mbar_wait(&a_full[ra.s], ra.ph, nullptr);
+                    mbar_wait(&b_full[rb.s], rb.ph, nullptr);
+                }
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t dAh = descA0 + (uint64_t)(ra.s * ((2 * P3_A_BYTES) >> 4)), dAl = dAh + (P3_A_BYTES >> 4);
+                    const uint64_t dBh = descB0 + (uint64_t)(rb.s * b_step), dBl = dBh + b_lo;
+#pragma unroll
+                    for (int ks = 0; ks < TC_KC / 8; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * ((2 * TC_LBO) >> 4));
+                        umma_tf32(d, dAh + adv, dBh + adv, idesc, ks ? 1u : (uint32_t)(kc != 0));
+                        umma_tf32(d, dAh + adv, dBl + adv, idesc, 1);
+                        umma_tf32(d, dAl + adv, dBh + adv, idesc, 1);
+                    }
+                    umma_commit(&a_empty[ra.s]);
+                    umma_commit(&b_empty[rb.s]);
+                    if (kc == nk - 1) umma_commit(&acc_full[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp < 2 + P3_XW) {
+        // ---------------- transform: raw rows -> shifted, split, K-major ----------------
+        const int t = tid - 64, m = t & (TC_M - 1), kh = t >> 7;   // pixel, K half (8 channels of the 16-channel chunk)
+        const uint32_t off0 = tile_off(m, kh * 2), off1 = tile_off(m, kh * 2 + 1);
+        Ring rr, ra;
+        uint32_t li = 0;
+        for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
+            float s1 = 0.f, s2 = 0.f, shift = 0.f;
+            for (int kc = 0; kc < nk; ++kc, rr.next(RS), ra.next(AS)) {
+                mbar_wait(&raw_full[rr.s], rr.ph, nullptr);
+                const float* raw = reinterpret_cast<const float*>(s_raw + rr.s * P3_RAW_BYTES) + m;
+                if (LN && kc == 0) shift = raw[0];                         // per-pixel shift: its first channel
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = raw[(kh * 8 + e) * TC_M];
+                const int left = p.cin - kc * TC_KC - kh * 8;               // channels of this half that exist
+                if (left < 8) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = e < left ? v[e] : shift;   // -> 0 after the shift
+                }
+                if (LN) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        v[e] -= shift;
+                        s1 += v[e];
+                        s2 = fmaf(v[e], v[e], s2);
+                    }
+                }
+                float hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    hi[e] = tf32_hi(v[e]);
+                    lo[e] = v[e] - hi[e];
+                }
+                if (spin) mbar_spin(&a_empty[ra.s], ra.ph ^ 1);
+                else mbar_wait(&a_empty[ra.s], ra.ph ^ 1, nullptr);
+                unsigned char* sA_hi = s_a + ra.s * 2 * P3_A_BYTES;
+                unsigned char* sA_lo = sA_hi + P3_A_BYTES;
+                *reinterpret_cast<float4*>(sA_hi + off0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(sA_hi + off1) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+                *reinterpret_cast<float4*>(sA_lo + off0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<float4*>(sA_lo + off1) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&a_full[ra.s]);
+                    mbar_arrive(&raw_empty[rr.s]);
+                }
+            }
+            if (LN) {
+                const uint32_t buf = li & 1;
+                mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1, nullptr);   // the epilogue two items back has read its sums
+                s_part[(buf * 2 + kh) * TC_M + m] = make_float2(s1, s2);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&stats_full[buf]);
+            }
+        }
+    } else {
+        // ---------------- epilogue ----------------
+        const int ew = warp - (2 + P3_XW), q = warp & 3, half = ew >> 2, m = q * 32 + lane;   // TMEM lane quarter = warp % 4
+        uint32_t li = 0;
+        for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
+            const P3Item w = p3_item(p, it, ntiles, ptiles);
+            const uint32_t buf = li & 1, par = (li >> 1) & 1;
+            const int n0 = w.tile * NT, nvalid = min(NT, p.cout - n0);
+            float rstd = 1.f, nmr = 0.f;
+            if (LN) {
+                mbar_wait(&stats_full[buf], par, nullptr);
+                const float2 a = s_part[(buf * 2) * TC_M + m], b = s_part[(buf * 2 + 1) * TC_M + m];
+                const float inv = 1.f / (float)p.cin;
+                const float mean = (a.x + b.x) * inv;
+                rstd = rsqrtf(fmaxf((a.y + b.y) * inv - mean * mean, 0.f) + p.ln_eps);
+                nmr = -mean * rstd;
+            }
+            mbar_wait(&vec_full[buf], par, nullptr);
+            mbar_wait(&acc_full[buf], par, nullptr);
+            tc_fence_after();
+            const bool valid = m < w.npx;
+            const int64_t P = p.P;
+            float* out = p.out + ((int64_t)w.img * p.cout + n0) * P + w.p0 + m;
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * 256;
+            const float2* sv = s_vec + buf * NT;
+            const int ngrp = (nvalid + 15) >> 4;
+            for (int gi = half; gi < ngrp; gi += 2) {
+                const int c0 = gi * 16;
+                float v[16];
+                tmem_ld16(taddr + (uint32_t)c0, v);
+                float* o = out + (int64_t)c0 * P;
+                if (c0 + 16 <= nvalid) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float2 st = sv[c0 + i];
+                        const float r = LN ? fmaf(rstd, v[i], fmaf(nmr, st.x, st.y)) : v[i] + st.y;
+                        if (valid) *o = r;
+                        o += P;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float2 st = sv[min(c0 + i, NT - 1)];
+                        const float r = LN ? fmaf(rstd, v[i], fmaf(nmr, st.x, st.y)) : v[i] + st.y;
+                        if (valid && c0 + i < nvalid) *o = r;
+                        o += P;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
 static void tc_tiling(int cin, int cout, int& ntiles, int& NT, int& nk) {
     // output-channel tiling: as few tiles as possible, each a multiple of 16 and at most 256 channels
     ntiles = (cout + TC_NMAX - 1) / TC_NMAX;
@@ -271,34 +643,81 @@ static void tc_tiling(int cin, int cout, int& ntiles, int& NT, int& nk) {
     nk = (cin + TC_KC - 1) / TC_KC;
 }
 
+// workspace = [packed tiles | per-(sample, tile) epilogue vectors]
+static int64_t tc_pack_floats(int n_samples, int cin, int cout) {
+    int ntiles, NT, nk;
+    tc_tiling(cin, cout, ntiles, NT, nk);
+    return (int64_t)n_samples * ntiles * nk * 2 * NT * TC_KC;
+}
 int64_t bayes_pointwise_tc_workspace(int n_samples, int cin, int cout) {
     int ntiles, NT, nk;
     tc_tiling(cin, cout, ntiles, NT, nk);
-    return (int64_t)n_samples * ntiles * nk * 2 * NT * TC_KC * (int64_t)sizeof(float);
+    return (tc_pack_floats(n_samples, cin, cout) + (int64_t)n_samples * ntiles * 2 * NT) * (int64_t)sizeof(float);
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
 }
 
 int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t stream) {
     int ntiles, NT, nk;
     tc_tiling(p.cin, p.cout, ntiles, NT, nk);
+    const int64_t need = bayes_pointwise_tc_workspace(p.n_samples, p.cin, p.cout);
+    if (!p.workspace || p.workspace_bytes < need || (reinterpret_cast<uintptr_t>(p.workspace) & 15)) return BEM_ERR_WORKSPACE;
+    const int64_t ptiles = (p.P + TC_M - 1) / TC_M;
+    if (ptiles > 65535 || p.batch > 65535) return BEM_ERR_UNSUPPORTED;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    float* pack = reinterpret_cast<float*>(p.workspace);
+    float* vec = pack + tc_pack_floats(p.n_samples, p.cin, p.cout);
+    const int pack_blocks = p.n_samples * ntiles * nk;
+    const int vec_blocks = p.n_samples * ((p.cout + 7) / 8);
+    // the persistent kernel moves x with bulk copies: rows must start and end on 16-byte boundaries
+    static const int force_v2 = env_int("BEM_PW_V2", 0);
+    static const int spin = env_int("BEM_PW_SPIN", 0);
+    static const int as_req = env_int("BEM_PW_AS", 3);
+    const bool aligned = (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && p.P % 4 == 0 && p.x_img_stride % 4 == 0;
+    if (aligned && !force_v2) {
+        // shared-memory plan: A ring fixed, B ring >= 3 stages (up to ~48 KB), the rest goes to raw x stages in flight
+        const int b_stage = 2 * NT * TC_KC * 4;
+        const int BS = std::max(3, std::min(P3_BS_MAX, (48 * 1024) / b_stage));
+        const int AS = std::max(2, std::min(P3_AS_MAX, as_req));
+        const int fixed = AS * 2 * (int)P3_A_BYTES + BS * b_stage + 2 * NT * 8 + 2 * 2 * TC_M * 8 +
+                          (2 * P3_RS_MAX + 2 * P3_AS_MAX + 2 * P3_BS_MAX + 8) * 8 + 16;
+        const int RS = std::max(P3_LAG + 2, std::min(P3_RS_MAX, (int)((220 * 1024 - fixed) / (int)P3_RAW_BYTES)));
+        const int smem_bytes = RS * (int)P3_RAW_BYTES + fixed;
+        if (smem_bytes > 227 * 1024) return BEM_ERR_UNSUPPORTED;
+        static int attr3[64] = {0}, sms[64] = {0};
+        if (attr3[dev] < smem_bytes) {
+            cudaError_t e = cudaFuncSetAttribute(bayes_pointwise_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(bayes_pointwise_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+            if (e != cudaSuccess) return (int)e;
+            attr3[dev] = smem_bytes;
+        }
+        if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+        bayes_weight_pack_kernel<<<pack_blocks + vec_blocks, 256, 0, stream>>>(p, NT, ntiles, nk, pack, 1, vec);
+        const int64_t n_items = (int64_t)p.batch * ptiles * ntiles;
+        const int grid = (int)std::min<int64_t>(n_items, sms[dev]);
+        if (p.ln_gamma)
+            bayes_pointwise_tc3_kernel<true><<<grid, P3_THREADS, smem_bytes, stream>>>(p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS, AS, spin);
+        else
+            bayes_pointwise_tc3_kernel<false><<<grid, P3_THREADS, smem_bytes, stream>>>(p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS, AS, spin);
+        return (int)cudaGetLastError();
+    }
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < NT) tmem_cols <<= 1;
     const int smem_bytes = 2 * (2 * TC_M * TC_KC * 4 + 2 * NT * TC_KC * 4) + 48 + 2 * p.cin * 4 + 64;
     if (smem_bytes > 227 * 1024) return BEM_ERR_UNSUPPORTED;
-    const int64_t need = bayes_pointwise_tc_workspace(p.n_samples, p.cin, p.cout);
-    if (!p.workspace || p.workspace_bytes < need || (reinterpret_cast<uintptr_t>(p.workspace) & 15)) return BEM_ERR_WORKSPACE;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    dev &= 63;
     static int attr_set[64] = {0};
     if (attr_set[dev] < smem_bytes) {
         cudaError_t e = cudaFuncSetAttribute(bayes_pointwise_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return (int)e;
         attr_set[dev] = smem_bytes;
     }
-    const int64_t ptiles = (p.P + TC_M - 1) / TC_M;
-    if (ptiles > 65535 || p.batch > 65535) return BEM_ERR_UNSUPPORTED;
-    float* pack = reinterpret_cast<float*>(p.workspace);
-    bayes_weight_pack_kernel<<<p.n_samples * ntiles * nk, 256, 0, stream>>>(p, NT, ntiles, nk, pack);
+    bayes_weight_pack_kernel<<<pack_blocks, 256, 0, stream>>>(p, NT, ntiles, nk, pack, 0, vec);
     dim3 grid((unsigned)ntiles, (unsigned)ptiles, (unsigned)p.batch);
     bayes_pointwise_tc_kernel<<<grid, 128, smem_bytes, stream>>>(p, NT, ntiles, pack, tmem_cols);
     return (int)cudaGetLastError();
