@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libbem_b200.so")
 
 BEM_F32, BEM_F16, BEM_BF16 = 0, 1, 2
 BEM_OK, BEM_ERR_BAD_ARG, BEM_ERR_WORKSPACE, BEM_ERR_UNSUPPORTED = 0, 10001, 10002, 10003
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 i32, i64, u64, vp = C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
 
@@ -22,7 +22,7 @@ class BemScanFwdParams(C.Structure):
                [(n, vp) for n in ("u", "delta", "A", "B", "C", "D", "delta_bias", "out", "x")] + \
                [(n, i64) for n in ("u_bs", "u_ds", "delta_bs", "delta_ds", "A_ds", "A_ns", "B_bs", "B_gs", "B_ns",
                                    "C_bs", "C_gs", "C_ns", "out_bs", "out_ds")] + \
-               [("workspace", vp), ("workspace_bytes", i64)]
+               [("workspace", vp), ("workspace_bytes", i64), ("residual", vp)]
 
 
 class BemScanBwdParams(C.Structure):
@@ -31,7 +31,7 @@ class BemScanBwdParams(C.Structure):
                                   "dC", "dD", "ddelta_bias")] + \
                [(n, i64) for n in ("u_bs", "u_ds", "delta_bs", "delta_ds", "A_ds", "A_ns", "B_bs", "B_gs", "B_ns",
                                    "C_bs", "C_gs", "C_ns", "dout_bs", "dout_ds", "du_bs", "du_ds", "ddelta_bs", "ddelta_ds")] + \
-               [("workspace", vp), ("workspace_bytes", i64)]
+               [("workspace", vp), ("workspace_bytes", i64), ("residual", vp)]
 
 
 class BemCsmParams(C.Structure):
@@ -54,11 +54,16 @@ class BemBayesPointwiseParams(C.Structure):
     _fields_ = [(n, i32) for n in ("n_samples", "batch", "cin", "cout")] + [("P", i64)] + \
                [(n, vp) for n in ("x", "w", "mu", "rho", "eps", "bias", "out", "sigma", "ln_gamma", "ln_beta")] + \
                [("ln_eps", C.c_float), ("force_simt", i32), ("x_img_stride", i64), ("sample_interleave", i32),
-                ("workspace", vp), ("workspace_bytes", i64)]
+                ("workspace", vp), ("workspace_bytes", i64), ("residual", vp)]
 
 
 class BemBayesDepthwiseParams(C.Structure):
-    _fields_ = [(n, i32) for n in ("n_samples", "batch", "C", "H", "W", "K")] + [(n, vp) for n in ("x", "w", "bias", "out")]
+    _fields_ = ([(n, i32) for n in ("n_samples", "batch", "C", "H", "W", "K")] + [(n, vp) for n in ("x", "w", "bias", "out")]
+                + [("act", i32)])
+
+
+class BemBayesSampleBatchedParams(C.Structure):
+    _fields_ = [("entries", vp), ("blocks", vp), ("n_blocks", i32), ("seed", C.c_uint64), ("sample0", i64), ("sample0_dev", vp)]
 
 
 # every symbol include/bem_b200.h declares: (restype, argtypes)
@@ -74,6 +79,7 @@ SYMBOLS = {
     "bem_ss2d_workspace_bytes": (i64, [C.c_int] * 6),
     "bem_ss2d_fwd": (C.c_int, [C.POINTER(BemSs2dFwdParams), vp]),
     "bem_bayes_sample": (C.c_int, [C.POINTER(BemBayesSampleParams), vp]),
+    "bem_bayes_sample_batched": (C.c_int, [C.POINTER(BemBayesSampleBatchedParams), vp]),
     "bem_bayes_pointwise_workspace_bytes": (i64, [C.c_int] * 3),
     "bem_bayes_pointwise": (C.c_int, [C.POINTER(BemBayesPointwiseParams), vp]),
     "bem_bayes_depthwise": (C.c_int, [C.POINTER(BemBayesDepthwiseParams), vp]),

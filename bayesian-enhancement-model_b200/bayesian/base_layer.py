@@ -22,29 +22,50 @@ class BaseLayer_(nn.Module):
     def __init__(self):
         super().__init__()
 
-    def forward(self, input, eps_weight=None, eps_bias=None, pre_norm=None):
+    def forward(self, input, eps_weight=None, eps_bias=None, pre_norm=None, post_act=None, residual=None):
         """eps_weight / eps_bias (extension): inject the noise instead of drawing it — used by the parity tests to replay
         the eps the reference layer left in its eps_* buffers.
         pre_norm (extension): a LayerNorm2d-like module (weight, bias, eps over the channel dim) that precedes this layer;
-        1x1 layers fuse it into the kernel when no gradient is needed, otherwise it is simply applied first."""
+        post_act (extension): "silu" | "gelu_gate", the activation that follows it; residual (extension): tensor added
+        to the result (the block's skip connection). Each is fused into the layer's kernel when the geometry allows and
+        no gradient is needed (1x1: norm + residual, depthwise 3x3: activation); otherwise it is simply applied here."""
         inj = getattr(self, "_injected_eps", None)   # tests: {"weight": t, "bias": t} replayed from the reference
         if inj:
             eps_weight = inj.get("weight", eps_weight)
             eps_bias = inj.get("bias", eps_bias)
-        self._ln = None
+        needs_grad = torch.is_grad_enabled() and (input.requires_grad or self.mu_weight.requires_grad)
+        self._ln = self._act = self._res = None
         if pre_norm is not None:
-            needs_grad = torch.is_grad_enabled() and (input.requires_grad or self.mu_weight.requires_grad)
             if self._fuses_norm() and not needs_grad:
                 self._ln = (pre_norm.weight, pre_norm.bias, pre_norm.eps)
             else:
                 input = pre_norm(input)
+        if not needs_grad:
+            if post_act is not None and self._fuses_act():
+                self._act = post_act
+            if residual is not None and self._fuses_residual():
+                self._res = residual
+        fused_act, fused_res = self._act is not None, self._res is not None
         try:
             if not self.deterministic:
-                return self._forward_uncertain(input, eps_weight, eps_bias)
+                out = self._forward_uncertain(input, eps_weight, eps_bias)
             else:
-                return self._forward_det(input)
+                out = self._forward_det(input)
         finally:
-            self._ln = None
+            self._ln = self._act = self._res = None
+        if post_act is not None and not fused_act:
+            out = BF.apply_act(out, post_act)
+        if residual is not None and not fused_res:
+            out = residual + out
+        return out
+
+    _ln = _act = _res = None
+
+    def _fuses_act(self):
+        return False
+
+    def _fuses_residual(self):
+        return False
 
     def _fuses_norm(self):
         return False
@@ -122,6 +143,10 @@ class BaseLayer_(nn.Module):
     def _sample(self, which, given):
         """-> (w, eps_used) with w: (S, *shape). stream ids: 2*layer_id for weights, 2*layer_id + 1 for biases."""
         mu, rho = getattr(self, "mu_" + which), getattr(self, "rho_" + which)
+        arena = getattr(self, "_arena", None)
+        if (arena is not None and given is None and self.eps_source == "philox" and self.mc_samples == 1
+                and not (torch.is_grad_enabled() and mu.requires_grad)):
+            return arena[which].unsqueeze(0), None   # drawn for the whole network by MCArena.draw (one launch)
         eps = self._draw_eps(which, given)
         sid = 2 * int(self.layer_id) + (1 if which == "bias" else 0)
         w, used = BF.sample_weights(mu, rho, eps, self.mc_samples, self.mc_seed, sid, self.mc_sample0)

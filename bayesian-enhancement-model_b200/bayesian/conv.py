@@ -91,9 +91,10 @@ class Conv2dReparameterization(BaseLayer_):
         """w: (S, Cout, Cin/g, kh, kw), b: (S, Cout) | None"""
         geo = self._geometry()
         if geo == "pointwise":
-            return BF.pointwise_conv(input, w.reshape(S, self.out_channels, self.in_channels), b, S, ln=self._ln)
+            return BF.pointwise_conv(input, w.reshape(S, self.out_channels, self.in_channels), b, S, ln=self._ln,
+                                     residual=self._res)
         if geo == "depthwise3":
-            return BF.depthwise_conv3x3(input, w.reshape(S, self.out_channels, 3, 3), b, S)
+            return BF.depthwise_conv3x3(input, w.reshape(S, self.out_channels, 3, 3), b, S, act=self._act)
         # geometry outside the BEM hot path: library convolution on the sampled weights (S samples as S x groups groups)
         if S == 1:
             return F.conv2d(input, w[0], None if b is None else b[0], self.stride, self.padding, self.dilation, self.groups)
@@ -114,13 +115,19 @@ class Conv2dReparameterization(BaseLayer_):
             b = self._sample("bias", eps_bias)[0] if self.bias else None
             oc, ic = self.out_channels, self.in_channels
             return BF.pointwise_conv_sampled(input, self.mu_weight.view(oc, ic), self._sigma_cached().view(oc, ic),
-                                             eps_w.reshape(S, oc, ic), b, S, ln=self._ln)
+                                             eps_w.reshape(S, oc, ic), b, S, ln=self._ln, residual=self._res)
         w, _ = self._sample("weight", eps_weight)
         b = self._sample("bias", eps_bias)[0] if self.bias else None
         return self._conv(input, w, b, S)
 
     def _fuses_norm(self):
         return self._geometry() == "pointwise"
+
+    def _fuses_residual(self):
+        return self._geometry() == "pointwise"
+
+    def _fuses_act(self):
+        return self._geometry() == "depthwise3"
 
     def _forward_det(self, input):
         w = self.mu_weight.unsqueeze(0)

@@ -67,10 +67,11 @@ def sample_weights(mu, rho, eps=None, n_samples=1, seed=0, stream_id=0, sample0=
 
 # ---------------------------------------------------------------------------------------------------
 def _pointwise_raw(x, w=None, bias=None, mu=None, sigma=None, eps=None, n_samples=1, ln=None, force_simt=False,
-                   interleave=False):
+                   interleave=False, residual=None):
     """x: (S*Bx, Cin, *spatial) fp32 — any image stride, channels P apart; w: (S|1, Cout, Cin) or mu/sigma/eps for the
     fused sample-on-load path; ln = (gamma, beta, eps): LayerNorm over the channels of every pixel fused into the
-    activation staging; interleave: image i uses weight set i % S instead of i // Bx."""
+    activation staging; interleave: image i uses weight set i % S instead of i // Bx; residual: (batch, Cout, *spatial)
+    contiguous tensor added to the result in the epilogue (the block's skip connection)."""
     _lib.require_cuda(x)
     if x.dtype != torch.float32:
         raise RuntimeError(f"bem_b200.bayesian: input must be float32 (got {x.dtype})")
@@ -93,14 +94,19 @@ def _pointwise_raw(x, w=None, bias=None, mu=None, sigma=None, eps=None, n_sample
         g, b, ln_eps = _f32c(ln[0], "ln weight"), _f32c(ln[1], "ln bias"), float(ln[2])
         if g.numel() != cin:
             raise RuntimeError(f"fused LayerNorm expects {cin} channels, got {g.numel()}")
+    if residual is not None:
+        residual = _f32c(residual, "residual")
+        if tuple(residual.shape) != tuple(out.shape):
+            raise RuntimeError(f"pointwise conv: residual {tuple(residual.shape)} does not match output {tuple(out.shape)}")
     ws = _lib.workspace(x.device, lib.bem_bayes_pointwise_workspace_bytes(n_samples, cin, cout), kind="pointwise")
     p = _lib.BemBayesPointwiseParams(n_samples=n_samples, batch=batch, cin=cin, cout=cout, P=P, x=_lib.ptr(x),
                                      w=_lib.ptr(w), mu=_lib.ptr(mu), rho=None, eps=_lib.ptr(eps), bias=_lib.ptr(bias),
                                      out=_lib.ptr(out), sigma=_lib.ptr(sigma), ln_gamma=_lib.ptr(g), ln_beta=_lib.ptr(b),
                                      ln_eps=ln_eps, force_simt=int(bool(force_simt)), x_img_stride=int(img_stride),
-                                     sample_interleave=int(bool(interleave)), workspace=_lib.ptr(ws), workspace_bytes=ws.numel())
+                                     sample_interleave=int(bool(interleave)), workspace=_lib.ptr(ws), workspace_bytes=ws.numel(),
+                                     residual=_lib.ptr(residual))
     _lib.launch("bayes_pointwise", lib.bem_bayes_pointwise, p, x.device, key=(batch, cin, cout, P),
-                nbytes=4 * batch * P * (cin + cout), kernels=1 if force_simt else 2)
+                nbytes=4 * batch * P * (cin + cout * (2 if residual is not None else 1)), kernels=1 if force_simt else 2)
     return out
 
 
@@ -142,34 +148,53 @@ def grouped_pointwise(x, w, bias=None):
     return out.view(B, K, -1, L)
 
 
-def pointwise_conv(x, w, bias=None, n_samples=1, ln=None, force_simt=False):
-    """out[img] = w[s(img)] @ LN(x[img]) + bias[s(img)]; w: (S, Cout, Cin), bias: (S, Cout) | None.
-    ln = (gamma, beta, eps) fuses the preceding LayerNorm2d (inference only)."""
+def pointwise_conv(x, w, bias=None, n_samples=1, ln=None, force_simt=False, residual=None):
+    """out[img] = w[s(img)] @ LN(x[img]) + bias[s(img)] (+ residual[img]); w: (S, Cout, Cin), bias: (S, Cout) | None.
+    ln = (gamma, beta, eps) fuses the preceding LayerNorm2d, residual the skip connection (both inference only)."""
     if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or (bias is not None and bias.requires_grad)):
         if ln is not None:
             raise RuntimeError("the fused LayerNorm path has no backward; apply the norm module separately when training")
-        return _PointwiseFn.apply(x, w, bias, n_samples)
-    return _pointwise_raw(x, w=w, bias=bias, n_samples=n_samples, ln=ln, force_simt=force_simt)
+        y = _PointwiseFn.apply(x, w, bias, n_samples)
+        return y if residual is None else residual + y
+    return _pointwise_raw(x, w=w, bias=bias, n_samples=n_samples, ln=ln, force_simt=force_simt, residual=residual)
 
 
-def pointwise_conv_sampled(x, mu, sigma, eps, bias=None, n_samples=1, ln=None, force_simt=False):
+def pointwise_conv_sampled(x, mu, sigma, eps, bias=None, n_samples=1, ln=None, force_simt=False, residual=None):
     """inference path: w = mu + sigma * eps (sigma = log1p(exp(rho)) precomputed once per layer) is formed while the
     weight tile is staged — the sampled weight never exists in HBM."""
-    return _pointwise_raw(x, mu=mu, sigma=sigma, eps=eps, bias=bias, n_samples=n_samples, ln=ln, force_simt=force_simt)
+    return _pointwise_raw(x, mu=mu, sigma=sigma, eps=eps, bias=bias, n_samples=n_samples, ln=ln, force_simt=force_simt,
+                          residual=residual)
 
 
 # ---------------------------------------------------------------------------------------------------
-def _depthwise_raw(x, w, bias, n_samples):
+ACTS = {None: 0, "none": 0, "silu": 1, "gelu_gate": 2}
+
+
+def _depthwise_raw(x, w, bias, n_samples, act=None):
     x = _f32c(x, "input")
     w = _f32c(w, "w")
     bias = _f32c(bias, "bias")
     batch, Cc, H, W = x.shape
     K = int(w.shape[-1])
-    out = torch.empty_like(x)
+    code = ACTS[act]
+    if code == 2 and Cc % 2:
+        raise RuntimeError("gated GELU needs an even channel count")
+    out = torch.empty((batch, Cc // 2 if code == 2 else Cc, H, W), dtype=torch.float32, device=x.device)
     p = _lib.BemBayesDepthwiseParams(n_samples=n_samples, batch=batch, C=Cc, H=H, W=W, K=K, x=_lib.ptr(x), w=_lib.ptr(w),
-                                     bias=_lib.ptr(bias), out=_lib.ptr(out))
-    _lib.launch("bayes_depthwise", lib.bem_bayes_depthwise, p, x.device, key=(batch, Cc, H, W), nbytes=8 * x.numel())
+                                     bias=_lib.ptr(bias), out=_lib.ptr(out), act=code)
+    _lib.launch("bayes_depthwise", lib.bem_bayes_depthwise, p, x.device, key=(batch, Cc, H, W, code),
+                nbytes=4 * (x.numel() + out.numel()))
     return out
+
+
+def apply_act(y, act):
+    """the unfused form of the depthwise kernel's `act` codes (training / non-depthwise geometries)"""
+    if ACTS[act] == 1:
+        return torch.nn.functional.silu(y)
+    if ACTS[act] == 2:
+        y1, y2 = y.chunk(2, dim=1)
+        return torch.nn.functional.gelu(y1) * y2
+    return y
 
 
 class _DepthwiseFn(torch.autograd.Function):
@@ -201,8 +226,17 @@ class _DepthwiseFn(torch.autograd.Function):
         return dx, dw, db, None
 
 
-def depthwise_conv3x3(x, w, bias=None, n_samples=1):
-    """x: (S*Bx, C, H, W); w: (S, C, 3, 3) (or (S, C, 1, 3, 3)); bias: (S, C) | None; stride 1, zero padding 1."""
+def depthwise_conv3x3(x, w, bias=None, n_samples=1, act=None):
+    """x: (S*Bx, C, H, W); w: (S, C, 3, 3) (or (S, C, 1, 3, 3)); bias: (S, C) | None; stride 1, zero padding 1.
+    act: None | "silu" | "gelu_gate" — the activation that follows the convolution, fused when no gradient is needed."""
     if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or (bias is not None and bias.requires_grad)):
-        return _DepthwiseFn.apply(x, w, bias, n_samples)
-    return _depthwise_raw(x, w, bias, n_samples)
+        return apply_act(_DepthwiseFn.apply(x, w, bias, n_samples), act)
+    return _depthwise_raw(x, w, bias, n_samples, act)
+
+
+def sample_batched(entries, blocks, n_blocks, seed, sample0=0, sample0_dev=None):
+    """one launch sampling every tensor listed in the device table `entries` (see MCArena)"""
+    p = _lib.BemBayesSampleBatchedParams(entries=_lib.ptr(entries), blocks=_lib.ptr(blocks), n_blocks=int(n_blocks),
+                                         seed=int(seed), sample0=int(sample0), sample0_dev=_lib.ptr(sample0_dev))
+    _lib.launch("bayes_sample", lib.bem_bayes_sample_batched, p, entries.device, key=("batched", int(n_blocks)),
+                nbytes=0)

@@ -59,17 +59,21 @@ class Linear2dReparameterization(_LinearBase):
         if (not needs_grad) and (self.eps_source == "torch" or eps_weight is not None):
             eps_w = self._draw_eps("weight", eps_weight)
             b = self._sample("bias", eps_bias)[0] if self.bias else None
-            return BF.pointwise_conv_sampled(input, self.mu_weight, self._sigma_cached(), eps_w, b, S, ln=self._ln)
+            return BF.pointwise_conv_sampled(input, self.mu_weight, self._sigma_cached(), eps_w, b, S, ln=self._ln,
+                                             residual=self._res)
         w, _ = self._sample("weight", eps_weight)
         b = self._sample("bias", eps_bias)[0] if self.bias else None
-        return BF.pointwise_conv(input, w, b, S, ln=self._ln)
+        return BF.pointwise_conv(input, w, b, S, ln=self._ln, residual=self._res)
 
     def _fuses_norm(self):
         return True
 
+    def _fuses_residual(self):
+        return True
+
     def _forward_det(self, input):
         return BF.pointwise_conv(input, self.mu_weight.unsqueeze(0), self.mu_bias.unsqueeze(0) if self.bias else None, 1,
-                                 ln=self._ln)
+                                 ln=self._ln, residual=self._res)
 
 
 class LinearReparameterization(_LinearBase):

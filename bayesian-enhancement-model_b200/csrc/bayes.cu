@@ -70,6 +70,22 @@ __global__ void __launch_bounds__(256) bayes_sample_kernel(const BemBayesSampleP
     }
 }
 
+// every Bayesian tensor of a network in one launch (one Monte-Carlo draw); same numbers as bayes_sample_kernel
+__global__ void __launch_bounds__(256) bayes_sample_batched_kernel(const BemBayesSampleBatchedParams p) {
+    const int e = p.blocks[2 * blockIdx.x];
+    const int64_t blk = (int64_t)p.blocks[2 * blockIdx.x + 1] + threadIdx.x;
+    const BemBayesSampleEntry en = p.entries[e];
+    if (blk * 4 >= en.numel) return;
+    const int64_t sample = p.sample0 + (p.sample0_dev ? *p.sample0_dev : 0);
+    float n[4];
+    philox_normal4(p.seed, (uint64_t)en.stream_id, (uint64_t)sample, (uint64_t)blk, n);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t i = blk * 4 + k;
+        if (i < en.numel) en.w[i] = fmaf(sigma_of_rho(en.rho[i]), n[k], en.mu[i]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // S-batched pointwise (1x1) convolution, fp32 CUDA-core tiles.
 //   out[img, co, p] = sum_ci W[s(img)][co][ci] * x[img][ci][p] + bias[s(img)][co]
@@ -162,8 +178,15 @@ __global__ void __launch_bounds__(256) bayes_pointwise_kernel(const BemBayesPoin
         for (int half = 0; half < 2; ++half) {
             const int64_t pp = p0 + half * 128 + tx * 4;
             float* dst = out + (int64_t)co * p.P + pp;
-            const float4 v = make_float4(acc[i][half * 4 + 0] + b, acc[i][half * 4 + 1] + b, acc[i][half * 4 + 2] + b,
-                                         acc[i][half * 4 + 3] + b);
+            float4 v = make_float4(acc[i][half * 4 + 0] + b, acc[i][half * 4 + 1] + b, acc[i][half * 4 + 2] + b,
+                                   acc[i][half * 4 + 3] + b);
+            if (p.residual) {
+                const float* rs = p.residual + ((int64_t)img * p.cout + co) * p.P + pp;
+                if (pp + 0 < p.P) v.x += rs[0];
+                if (pp + 1 < p.P) v.y += rs[1];
+                if (pp + 2 < p.P) v.z += rs[2];
+                if (pp + 3 < p.P) v.w += rs[3];
+            }
             if (vec_ok && pp + 3 < p.P) *reinterpret_cast<float4*>(dst) = v;
             else {
                 if (pp + 0 < p.P) dst[0] = v.x;
@@ -176,44 +199,107 @@ __global__ void __launch_bounds__(256) bayes_pointwise_kernel(const BemBayesPoin
 }
 
 // ------------------------------------------------------------------------------------------------
-// S-batched depthwise 3x3 (stride 1, zero padding 1). One thread: 4 consecutive output pixels of one row.
+// S-batched depthwise 3x3 (stride 1, zero padding 1) with the activation that follows it in the reference fused.
+// One thread: a strip of 4 output columns x DW_ROWS rows, input rows rolled through registers (one float4 + two halo
+// scalars loaded per output row instead of 18 scalars), float4 stores. ACT 2 (gated GELU) walks channel c and c + C/2
+// together and writes C/2 channels.
 // ------------------------------------------------------------------------------------------------
+constexpr int DW_ROWS = 8;
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.f + expf(-v)); }                        // torch SiLU, fp32
+__device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }   // nn.GELU() (erf form)
+
+struct DwRow { float v[6]; };   // columns w0-1 .. w0+4 of one input row (zero outside the image)
+
+__device__ __forceinline__ DwRow dw_load_row(const float* __restrict__ plane, int hh, int H, int W, int w0, bool vec_ok) {
+    DwRow r;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) r.v[j] = 0.f;
+    if (hh < 0 || hh >= H) return r;
+    const float* row = plane + (int64_t)hh * W;
+    if (vec_ok && w0 + 3 < W) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(row + w0));
+        r.v[1] = q.x; r.v[2] = q.y; r.v[3] = q.z; r.v[4] = q.w;
+    } else {
+#pragma unroll
+        for (int j = 1; j < 5; ++j)
+            if (w0 + j - 1 < W) r.v[j] = __ldg(row + w0 + j - 1);
+    }
+    if (w0 > 0) r.v[0] = __ldg(row + w0 - 1);
+    if (w0 + 4 < W) r.v[5] = __ldg(row + w0 + 4);
+    return r;
+}
+
+__device__ __forceinline__ void dw_fma_row(const DwRow& r, const float* __restrict__ w3, float (&acc)[4]) {
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[o] = fmaf(w3[j], r.v[o + j], acc[o]);
+}
+
+template <int ACT>
 __global__ void __launch_bounds__(256) bayes_depthwise3_kernel(const BemBayesDepthwiseParams p) {
-    const int W4 = (p.W + 3) / 4;
-    const int64_t per_plane = (int64_t)p.H * W4;
-    const int plane = blockIdx.x;   // img * C + c
-    const int img = plane / p.C, c = plane - img * p.C;
-    const int imgs_per_sample = p.batch / p.n_samples;
-    const int s = p.n_samples > 1 ? img / imgs_per_sample : 0;
-    const float* wp = p.w + ((int64_t)s * p.C + c) * 9;
-    float w[9];
+    constexpr int NP = ACT == 2 ? 2 : 1;                 // input planes per thread
+    const int Cout = ACT == 2 ? p.C / 2 : p.C;
+    const int W4 = (p.W + 3) / 4, HS = (p.H + DW_ROWS - 1) / DW_ROWS;
+    const int plane = blockIdx.x;                        // img * Cout + c
+    const int img = plane / Cout, c = plane - img * Cout;
+    const int s = p.n_samples > 1 ? img / (p.batch / p.n_samples) : 0;
+    float w[NP][9], b[NP];
+    const float* xin[NP];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) w[i] = wp[i];
-    const float b = p.bias ? p.bias[(int64_t)s * p.C + c] : 0.f;
-    const float* x = p.x + (int64_t)plane * p.H * p.W;
+    for (int q = 0; q < NP; ++q) {
+        const int cc = c + q * Cout;
+        const float* wp = p.w + ((int64_t)s * p.C + cc) * 9;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) w[q][i] = wp[i];
+        b[q] = p.bias ? p.bias[(int64_t)s * p.C + cc] : 0.f;
+        xin[q] = p.x + ((int64_t)img * p.C + cc) * p.H * p.W;
+    }
     float* out = p.out + (int64_t)plane * p.H * p.W;
-    for (int64_t t = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; t < per_plane; t += (int64_t)gridDim.y * blockDim.x) {
-        const int h = (int)(t / W4), w0 = (int)(t - (int64_t)h * W4) * 4;
-        float acc[4] = {b, b, b, b};
+    const bool vec_ok = (p.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.out)) & 15) == 0;
+    const int64_t strips = (int64_t)HS * W4;
+    for (int64_t t = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; t < strips; t += (int64_t)gridDim.y * blockDim.x) {
+        const int hs = (int)(t / W4), w0 = (int)(t - (int64_t)hs * W4) * 4;
+        const int h0 = hs * DW_ROWS;
+        DwRow r0[NP], r1[NP];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int hh = h + i - 1;
-            if (hh < 0 || hh >= p.H) continue;
-            const float* row = x + (int64_t)hh * p.W;
-            float v[6];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                const int ww = w0 + j - 1;
-                v[j] = (ww >= 0 && ww < p.W) ? __ldg(row + ww) : 0.f;
-            }
-#pragma unroll
-            for (int o = 0; o < 4; ++o)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) acc[o] = fmaf(w[i * 3 + j], v[o + j], acc[o]);
+        for (int q = 0; q < NP; ++q) {
+            r0[q] = dw_load_row(xin[q], h0 - 1, p.H, p.W, w0, vec_ok);
+            r1[q] = dw_load_row(xin[q], h0, p.H, p.W, w0, vec_ok);
         }
 #pragma unroll
-        for (int o = 0; o < 4; ++o)
-            if (w0 + o < p.W) out[(int64_t)h * p.W + w0 + o] = acc[o];
+        for (int i = 0; i < DW_ROWS; ++i) {
+            const int h = h0 + i;
+            if (h >= p.H) break;
+            float res[NP][4];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const DwRow r2 = dw_load_row(xin[q], h + 1, p.H, p.W, w0, vec_ok);
+                float acc[4] = {b[q], b[q], b[q], b[q]};
+                dw_fma_row(r0[q], &w[q][0], acc);
+                dw_fma_row(r1[q], &w[q][3], acc);
+                dw_fma_row(r2, &w[q][6], acc);
+#pragma unroll
+                for (int o = 0; o < 4; ++o) res[q][o] = acc[o];
+                r0[q] = r1[q];
+                r1[q] = r2;
+            }
+            float y[4];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                if (ACT == 1) y[o] = silu_f(res[0][o]);
+                else if (ACT == 2) y[o] = gelu_f(res[0][o]) * res[NP - 1][o];
+                else y[o] = res[0][o];
+            }
+            float* dst = out + (int64_t)h * p.W + w0;
+            if (vec_ok && w0 + 3 < p.W) *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
+            else {
+#pragma unroll
+                for (int o = 0; o < 4; ++o)
+                    if (w0 + o < p.W) dst[o] = y[o];
+            }
+        }
     }
 }
 
@@ -230,6 +316,12 @@ int bem_bayes_sample(const BemBayesSampleParams* p, void* stream) {
     const int64_t cap = (int64_t)device_sm_count() * 16;
     if (blocks > cap) blocks = cap;
     bayes_sample_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+    return (int)cudaGetLastError();
+}
+
+int bem_bayes_sample_batched(const BemBayesSampleBatchedParams* p, void* stream) {
+    if (!p || !p->entries || !p->blocks || p->n_blocks <= 0) return BEM_ERR_BAD_ARG;
+    bayes_sample_batched_kernel<<<p->n_blocks, 256, 0, (cudaStream_t)stream>>>(*p);
     return (int)cudaGetLastError();
 }
 
@@ -255,15 +347,17 @@ int bem_bayes_pointwise(const BemBayesPointwiseParams* p, void* stream) {
 int bem_bayes_depthwise(const BemBayesDepthwiseParams* p, void* stream) {
     if (!p || !p->x || !p->w || !p->out || p->n_samples <= 0 || p->batch <= 0 || p->C <= 0 || p->H <= 0 || p->W <= 0)
         return BEM_ERR_BAD_ARG;
-    if (p->batch % p->n_samples != 0) return BEM_ERR_BAD_ARG;
+    if (p->batch % p->n_samples != 0 || p->act < 0 || p->act > 2 || (p->act == 2 && p->C % 2 != 0)) return BEM_ERR_BAD_ARG;
     if (p->K != 3) return BEM_ERR_UNSUPPORTED;
-    const int64_t planes = (int64_t)p->batch * p->C;
+    const int64_t planes = (int64_t)p->batch * (p->act == 2 ? p->C / 2 : p->C);
     if (planes > 0x7fffffff) return BEM_ERR_UNSUPPORTED;
-    const int64_t per_plane = (int64_t)p->H * ((p->W + 3) / 4);
-    int64_t by = (per_plane + 255) / 256;
+    const int64_t strips = (int64_t)((p->H + DW_ROWS - 1) / DW_ROWS) * ((p->W + 3) / 4);
+    int64_t by = (strips + 255) / 256;
     if (by > 1024) by = 1024;
     dim3 grid((unsigned)planes, (unsigned)by);
-    bayes_depthwise3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+    if (p->act == 0) bayes_depthwise3_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+    else if (p->act == 1) bayes_depthwise3_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+    else bayes_depthwise3_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
     return (int)cudaGetLastError();
 }
 

@@ -51,6 +51,23 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 8 consecutive TMEM columns of this thread's lane <- registers
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+                 "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
     asm volatile(
@@ -68,21 +85,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-// non-blocking probe loop: lower wake-up latency than try_wait's hardware suspend, for the waits on the critical path
-__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    for (int tries = 0; tries < (1 << 26); ++tries) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (ok) return;
-    }
 }
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -315,7 +317,8 @@ __global__ void __launch_bounds__(128, 4) bayes_pointwise_tc_kernel(const BemBay
                 const int co = n0 + c0 + i;
                 if (c0 + i < nvalid) {
                     const float b = p.bias ? p.bias[(int64_t)s_idx * p.cout + co] : 0.f;
-                    out[(int64_t)co * p.P + pix] = v[i] + b;
+                    const int64_t oi = (int64_t)co * p.P + pix;
+                    out[oi] = v[i] + b + (p.residual ? p.residual[(int64_t)img * p.cout * p.P + oi] : 0.f);
                 }
             }
         }
@@ -329,16 +332,21 @@ __global__ void __launch_bounds__(128, 4) bayes_pointwise_tc_kernel(const BemBay
 // persistent, warp-specialised form (the default): one CTA per SM walks (image, pixel tile, output-channel tile) items
 //   warps 0,19  producers: raw x rows (cp.async, one 512-byte row per warp instruction) into a deep shared-memory ring
 //   warp 18     TMA producer: packed weight tiles (ring) and the per-channel epilogue vectors
-//   warp 1      MMA issuer: 3 x tcgen05.mma per K step into one of two TMEM accumulators (2 x 256 columns)
-//   warps 2-9   transform: raw x tile -> (x - shift) split into tf32 hi / lo, K-major canonical layout; LayerNorm sums
+//   warp 1      MMA issuer: 3 x tcgen05.mma per K step, A operand from TMEM, B from shared memory
+//   warps 2-9   transform: raw x tile -> (x - shift) split into tf32 hi / lo -> tcgen05.st into the A ring in TMEM
+//               (pixel = TMEM lane, channel = column); LayerNorm sums on the way
 //   warps 10-17 epilogue: tcgen05.ld -> rstd * (acc - mean * s_n) + t_n -> 128-byte coalesced stores
-// so the loads of item i+1, the MMAs of item i and the stores of item i-1 overlap, with 48 KB of loads in flight per SM.
-// Rows of A past the end of the image carry whatever the stage held before: row m of D depends on row m of A only and
+// so the loads of item i+1, the MMAs of item i and the stores of item i-1 overlap. Keeping A in TMEM takes its 16 KB of
+// stores and 24 KB of MMA operand reads per chunk off shared memory, which otherwise bounds the kernel.
+// TMEM columns: [0,192) and [192,384) accumulators, [384,512) A ring of 4 stages x (16 hi + 16 lo).
+// Rows of A past the end of the image carry zero-filled or stale values: row m of D depends on row m of A only and
 // those rows are never stored. Input channels past `cin` (last K chunk) are zeroed, they feed every output.
 // ------------------------------------------------------------------------------------------------
 constexpr int P3_LAG = 6;     // cp.async groups (chunks) in flight per producer warp
 constexpr int P3_RS_MAX = 16;  // raw x stages  (TC_KC rows x 128 pixels x 4 B = 8 KB each), as many as fit
-constexpr int P3_AS_MAX = 6;   // A stages      (hi | lo, 16 KB each)
+constexpr int P3_AS = 4;       // A stages in TMEM (16 hi + 16 lo columns each)
+constexpr int P3_NMAX = 192;   // output channels per tile: two accumulators + the A ring fit the 512 TMEM columns
+constexpr uint32_t P3_ACC_COLS = 192, P3_A_COL0 = 384;
 constexpr int P3_BS_MAX = 8;   // B stages      (hi | lo, 2 * NT * TC_KC * 4 B each)
 constexpr int P3_XW = 8;       // transform warps
 constexpr int P3_EW = 8;       // epilogue warps (two per TMEM lane quarter, alternating 16-column groups)
@@ -354,7 +362,6 @@ struct Ring {   // position in a ring of `n` stages and the phase bit of its mba
     }
 };
 constexpr uint32_t P3_RAW_BYTES = TC_KC * TC_M * 4;
-constexpr uint32_t P3_A_BYTES = TC_M * TC_KC * 4;
 
 struct P3Item {
     int tile, img, s_idx, npx;
@@ -375,20 +382,19 @@ template <bool LN>
 __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(const BemBayesPointwiseParams p, const int NT, const int ntiles,
                                                                           const int ptiles, const int64_t n_items,
                                                                           const float* __restrict__ pack, const float* __restrict__ vec,
-                                                                          const uint32_t RS, const uint32_t BS, const uint32_t AS, const int spin) {
+                                                                          const uint32_t RS, const uint32_t BS) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t b_bytes = (uint32_t)NT * TC_KC * 4;
     unsigned char* s_raw = smem;
-    unsigned char* s_a = s_raw + RS * P3_RAW_BYTES;
-    unsigned char* s_b = s_a + AS * 2 * P3_A_BYTES;
+    unsigned char* s_b = s_raw + RS * P3_RAW_BYTES;
     float2* s_vec = reinterpret_cast<float2*>(s_b + BS * 2 * b_bytes);         // [2 acc buffers][NT] (s_n, t_n)
     float2* s_part = s_vec + 2 * NT;                                           // [2 acc buffers][2 K halves][128] (sum, sum sq)
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 2 * 2 * TC_M);
     uint64_t* raw_full = bars;
     uint64_t* raw_empty = raw_full + P3_RS_MAX;
     uint64_t* a_full = raw_empty + P3_RS_MAX;
-    uint64_t* a_empty = a_full + P3_AS_MAX;
-    uint64_t* b_full = a_empty + P3_AS_MAX;
+    uint64_t* a_empty = a_full + P3_AS;
+    uint64_t* b_full = a_empty + P3_AS;
     uint64_t* b_empty = b_full + P3_BS_MAX;
     uint64_t* acc_full = b_empty + P3_BS_MAX;
     uint64_t* acc_empty = acc_full + 2;
@@ -401,7 +407,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
 
     if (tid == 0) {
         for (int i = 0; i < (int)RS; ++i) { mbar_init(&raw_full[i], 64); mbar_init(&raw_empty[i], P3_XW); }
-        for (int i = 0; i < (int)AS; ++i) { mbar_init(&a_full[i], P3_XW); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < P3_AS; ++i) { mbar_init(&a_full[i], P3_XW); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < (int)BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
@@ -483,34 +489,29 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
         // The whole warp walks the loop (uniform control flow keeps descriptors in uniform registers); one elected lane
-        // issues. Descriptors are one base per operand plus the stage / K-step offset in the 14-bit address field.
+        // issues. B descriptors are one base plus the stage / K-step offset in the 14-bit address field.
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-        const uint64_t descA0 = make_desc(smem_u32(s_a), TC_LBO, TC_SBO), descB0 = make_desc(smem_u32(s_b), TC_LBO, TC_SBO);
+        const uint64_t descB0 = make_desc(smem_u32(s_b), TC_LBO, TC_SBO);
         const uint32_t b_step = (2 * b_bytes) >> 4, b_lo = b_bytes >> 4;
         Ring ra, rb;
         uint32_t li = 0;
         for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
             const uint32_t buf = li & 1;
             mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1, nullptr);   // the epilogue has drained this accumulator
-            const uint32_t d = tmem + buf * 256;
-            for (int kc = 0; kc < nk; ++kc, ra.next(AS), rb.next(BS)) {
-                if (spin) {
-                    mbar_spin(&a_full[ra.s], ra.ph);
-                    mbar_spin(&b_full[rb.s], rb.ph);
-                } else {
-                    mbar_wait(&a_full[ra.s], ra.ph, nullptr);
-                    mbar_wait(&b_full[rb.s], rb.ph, nullptr);
-                }
+            const uint32_t d = tmem + buf * P3_ACC_COLS;
+            for (int kc = 0; kc < nk; ++kc, ra.next(P3_AS), rb.next(BS)) {
+                mbar_wait(&a_full[ra.s], ra.ph, nullptr);
+                mbar_wait(&b_full[rb.s], rb.ph, nullptr);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint64_t dAh = descA0 + (uint64_t)(ra.s * ((2 * P3_A_BYTES) >> 4)), dAl = dAh + (P3_A_BYTES >> 4);
+                    const uint32_t aH = tmem + P3_A_COL0 + ra.s * (2 * TC_KC), aL = aH + TC_KC;
                     const uint64_t dBh = descB0 + (uint64_t)(rb.s * b_step), dBl = dBh + b_lo;
 #pragma unroll
                     for (int ks = 0; ks < TC_KC / 8; ++ks) {
                         const uint64_t adv = (uint64_t)(ks * ((2 * TC_LBO) >> 4));
-                        umma_tf32(d, dAh + adv, dBh + adv, idesc, ks ? 1u : (uint32_t)(kc != 0));
-                        umma_tf32(d, dAh + adv, dBl + adv, idesc, 1);
-                        umma_tf32(d, dAl + adv, dBh + adv, idesc, 1);
+                        umma_tf32_ts(d, aH + ks * 8, dBh + adv, idesc, ks ? 1u : (uint32_t)(kc != 0));
+                        umma_tf32_ts(d, aH + ks * 8, dBl + adv, idesc, 1);
+                        umma_tf32_ts(d, aL + ks * 8, dBh + adv, idesc, 1);
                     }
                     umma_commit(&a_empty[ra.s]);
                     umma_commit(&b_empty[rb.s]);
@@ -520,14 +521,15 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
             }
         }
     } else if (warp < 2 + P3_XW) {
-        // ---------------- transform: raw rows -> shifted, split, K-major ----------------
-        const int t = tid - 64, m = t & (TC_M - 1), kh = t >> 7;   // pixel, K half (8 channels of the 16-channel chunk)
-        const uint32_t off0 = tile_off(m, kh * 2), off1 = tile_off(m, kh * 2 + 1);
+        // ---------------- transform: raw rows -> shifted, split -> A ring in TMEM ----------------
+        // pixel = TMEM lane (a warp reaches lanes 32 * (warp % 4) ..), K half = which of the two warps of that quarter
+        const int m = (warp & 3) * 32 + lane, kh = (warp - 2) >> 2;
+        const uint32_t a_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + P3_A_COL0 + kh * 8;
         Ring rr, ra;
         uint32_t li = 0;
         for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
             float s1 = 0.f, s2 = 0.f, shift = 0.f;
-            for (int kc = 0; kc < nk; ++kc, rr.next(RS), ra.next(AS)) {
+            for (int kc = 0; kc < nk; ++kc, rr.next(RS), ra.next(P3_AS)) {
                 mbar_wait(&raw_full[rr.s], rr.ph, nullptr);
                 const float* raw = reinterpret_cast<const float*>(s_raw + rr.s * P3_RAW_BYTES) + m;
                 if (LN && kc == 0) shift = raw[0];                         // per-pixel shift: its first channel
@@ -553,15 +555,12 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
                     hi[e] = tf32_hi(v[e]);
                     lo[e] = v[e] - hi[e];
                 }
-                if (spin) mbar_spin(&a_empty[ra.s], ra.ph ^ 1);
-                else mbar_wait(&a_empty[ra.s], ra.ph ^ 1, nullptr);
-                unsigned char* sA_hi = s_a + ra.s * 2 * P3_A_BYTES;
-                unsigned char* sA_lo = sA_hi + P3_A_BYTES;
-                *reinterpret_cast<float4*>(sA_hi + off0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(sA_hi + off1) = make_float4(hi[4], hi[5], hi[6], hi[7]);
-                *reinterpret_cast<float4*>(sA_lo + off0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                *reinterpret_cast<float4*>(sA_lo + off1) = make_float4(lo[4], lo[5], lo[6], lo[7]);
-                fence_proxy_async();
+                mbar_wait(&a_empty[ra.s], ra.ph ^ 1, nullptr);           // the MMAs that read this stage have completed
+                tc_fence_after();
+                tmem_st8(a_lane + ra.s * (2 * TC_KC), hi);
+                tmem_st8(a_lane + ra.s * (2 * TC_KC) + TC_KC, lo);
+                tmem_wait_st();
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(&a_full[ra.s]);
@@ -598,8 +597,10 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
             tc_fence_after();
             const bool valid = m < w.npx;
             const int64_t P = p.P;
-            float* out = p.out + ((int64_t)w.img * p.cout + n0) * P + w.p0 + m;
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * 256;
+            const int64_t obase = ((int64_t)w.img * p.cout + n0) * P + w.p0 + m;
+            float* out = p.out + obase;
+            const float* res = p.residual ? p.residual + obase : nullptr;
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * P3_ACC_COLS;
             const float2* sv = s_vec + buf * NT;
             const int ngrp = (nvalid + 15) >> 4;
             for (int gi = half; gi < ngrp; gi += 2) {
@@ -607,11 +608,20 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
                 float v[16];
                 tmem_ld16(taddr + (uint32_t)c0, v);
                 float* o = out + (int64_t)c0 * P;
+                float rv[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) rv[i] = 0.f;
+                if (res != nullptr && valid) {   // skip connection: the loads go out together, ahead of the stores
+                    const float* rp = res + (int64_t)c0 * P;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i, rp += P)
+                        if (c0 + i < nvalid) rv[i] = *rp;
+                }
                 if (c0 + 16 <= nvalid) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const float2 st = sv[c0 + i];
-                        const float r = LN ? fmaf(rstd, v[i], fmaf(nmr, st.x, st.y)) : v[i] + st.y;
+                        const float r = (LN ? fmaf(rstd, v[i], fmaf(nmr, st.x, st.y)) : v[i] + st.y) + rv[i];
                         if (valid) *o = r;
                         o += P;
                     }
@@ -619,7 +629,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const float2 st = sv[min(c0 + i, NT - 1)];
-                        const float r = LN ? fmaf(rstd, v[i], fmaf(nmr, st.x, st.y)) : v[i] + st.y;
+                        const float r = (LN ? fmaf(rstd, v[i], fmaf(nmr, st.x, st.y)) : v[i] + st.y) + rv[i];
                         if (valid && c0 + i < nvalid) *o = r;
                         o += P;
                     }
@@ -635,24 +645,29 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-static void tc_tiling(int cin, int cout, int& ntiles, int& NT, int& nk) {
-    // output-channel tiling: as few tiles as possible, each a multiple of 16 and at most 256 channels
-    ntiles = (cout + TC_NMAX - 1) / TC_NMAX;
+static void tc_tiling(int cin, int cout, int nmax, int& ntiles, int& NT, int& nk) {
+    // output-channel tiling: as few tiles as possible, each a multiple of 16 and at most `nmax` channels
+    ntiles = (cout + nmax - 1) / nmax;
     NT = ((cout + ntiles - 1) / ntiles + 15) / 16 * 16;
     if (NT < 16) NT = 16;
     nk = (cin + TC_KC - 1) / TC_KC;
 }
 
 // workspace = [packed tiles | per-(sample, tile) epilogue vectors]
-static int64_t tc_pack_floats(int n_samples, int cin, int cout) {
+static int64_t tc_pack_floats(int n_samples, int cin, int cout, int nmax) {
     int ntiles, NT, nk;
-    tc_tiling(cin, cout, ntiles, NT, nk);
+    tc_tiling(cin, cout, nmax, ntiles, NT, nk);
     return (int64_t)n_samples * ntiles * nk * 2 * NT * TC_KC;
 }
-int64_t bayes_pointwise_tc_workspace(int n_samples, int cin, int cout) {
+static int64_t tc_workspace_floats(int n_samples, int cin, int cout, int nmax) {
     int ntiles, NT, nk;
-    tc_tiling(cin, cout, ntiles, NT, nk);
-    return (tc_pack_floats(n_samples, cin, cout) + (int64_t)n_samples * ntiles * 2 * NT) * (int64_t)sizeof(float);
+    tc_tiling(cin, cout, nmax, ntiles, NT, nk);
+    return tc_pack_floats(n_samples, cin, cout, nmax) + (int64_t)n_samples * ntiles * 2 * NT;
+}
+int64_t bayes_pointwise_tc_workspace(int n_samples, int cin, int cout) {
+    // enough for either tiling (persistent kernel: tiles of <= 192 channels; unaligned-input kernel: <= 256)
+    return std::max(tc_workspace_floats(n_samples, cin, cout, P3_NMAX), tc_workspace_floats(n_samples, cin, cout, TC_NMAX)) *
+           (int64_t)sizeof(float);
 }
 
 static int env_int(const char* name, int dflt) {
@@ -661,8 +676,6 @@ static int env_int(const char* name, int dflt) {
 }
 
 int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t stream) {
-    int ntiles, NT, nk;
-    tc_tiling(p.cin, p.cout, ntiles, NT, nk);
     const int64_t need = bayes_pointwise_tc_workspace(p.n_samples, p.cin, p.cout);
     if (!p.workspace || p.workspace_bytes < need || (reinterpret_cast<uintptr_t>(p.workspace) & 15)) return BEM_ERR_WORKSPACE;
     const int64_t ptiles = (p.P + TC_M - 1) / TC_M;
@@ -671,21 +684,20 @@ int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t str
     cudaGetDevice(&dev);
     dev &= 63;
     float* pack = reinterpret_cast<float*>(p.workspace);
-    float* vec = pack + tc_pack_floats(p.n_samples, p.cin, p.cout);
+    // the persistent kernel moves x with 16-byte cp.async: rows must start and end on 16-byte boundaries
+    static const int force_v2 = env_int("BEM_PW_V2", 0);
+    const bool aligned = (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && p.P % 4 == 0 && p.x_img_stride % 4 == 0;
+    const bool persistent = aligned && !force_v2;
+    int ntiles, NT, nk;
+    tc_tiling(p.cin, p.cout, persistent ? P3_NMAX : TC_NMAX, ntiles, NT, nk);
+    float* vec = pack + tc_pack_floats(p.n_samples, p.cin, p.cout, persistent ? P3_NMAX : TC_NMAX);
     const int pack_blocks = p.n_samples * ntiles * nk;
     const int vec_blocks = p.n_samples * ((p.cout + 7) / 8);
-    // the persistent kernel moves x with bulk copies: rows must start and end on 16-byte boundaries
-    static const int force_v2 = env_int("BEM_PW_V2", 0);
-    static const int spin = env_int("BEM_PW_SPIN", 0);
-    static const int as_req = env_int("BEM_PW_AS", 3);
-    const bool aligned = (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && p.P % 4 == 0 && p.x_img_stride % 4 == 0;
-    if (aligned && !force_v2) {
-        // shared-memory plan: A ring fixed, B ring >= 3 stages (up to ~48 KB), the rest goes to raw x stages in flight
+    if (persistent) {
+        // shared-memory plan: B ring >= 3 stages (up to ~48 KB), the rest goes to raw x stages in flight
         const int b_stage = 2 * NT * TC_KC * 4;
         const int BS = std::max(3, std::min(P3_BS_MAX, (48 * 1024) / b_stage));
-        const int AS = std::max(2, std::min(P3_AS_MAX, as_req));
-        const int fixed = AS * 2 * (int)P3_A_BYTES + BS * b_stage + 2 * NT * 8 + 2 * 2 * TC_M * 8 +
-                          (2 * P3_RS_MAX + 2 * P3_AS_MAX + 2 * P3_BS_MAX + 8) * 8 + 16;
+        const int fixed = BS * b_stage + 2 * NT * 8 + 2 * 2 * TC_M * 8 + (2 * P3_RS_MAX + 2 * P3_AS + 2 * P3_BS_MAX + 8) * 8 + 16;
         const int RS = std::max(P3_LAG + 2, std::min(P3_RS_MAX, (int)((220 * 1024 - fixed) / (int)P3_RAW_BYTES)));
         const int smem_bytes = RS * (int)P3_RAW_BYTES + fixed;
         if (smem_bytes > 227 * 1024) return BEM_ERR_UNSUPPORTED;
@@ -702,9 +714,9 @@ int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t str
         const int64_t n_items = (int64_t)p.batch * ptiles * ntiles;
         const int grid = (int)std::min<int64_t>(n_items, sms[dev]);
         if (p.ln_gamma)
-            bayes_pointwise_tc3_kernel<true><<<grid, P3_THREADS, smem_bytes, stream>>>(p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS, AS, spin);
+            bayes_pointwise_tc3_kernel<true><<<grid, P3_THREADS, smem_bytes, stream>>>(p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS);
         else
-            bayes_pointwise_tc3_kernel<false><<<grid, P3_THREADS, smem_bytes, stream>>>(p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS, AS, spin);
+            bayes_pointwise_tc3_kernel<false><<<grid, P3_THREADS, smem_bytes, stream>>>(p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS);
         return (int)cudaGetLastError();
     }
     uint32_t tmem_cols = 32;

@@ -55,6 +55,66 @@ def default_score(pred: torch.Tensor) -> torch.Tensor:
     return lum.std(dim=(1, 2)) - 0.5 * clipped
 
 
+class MCArena:
+    """All sampled tensors of one Monte-Carlo draw in one buffer, filled by ONE kernel launch (bem_bayes_sample_batched)
+    instead of one launch per tensor per layer (conv.py:105-111 runs once per layer per forward in the reference).
+
+    Entry order = module order x (weight, bias); stream ids are the layers' own (2 * layer_id [+ 1]), so a draw gives
+    every layer exactly the numbers its per-layer Philox path would. The sample index can be read from a device word,
+    which is what lets a captured CUDA graph of the forward be replayed for any sample."""
+
+    def __init__(self, net, seed: int):
+        from .bayesian.base_layer import BaseLayer_
+        bayesian.set_mc_config(net)                       # assigns layer ids (= Philox stream ids) in module order
+        self.layers = [m for m in net.modules() if isinstance(m, BaseLayer_)]
+        if not self.layers:
+            raise RuntimeError("MCArena: the network has no bem_b200.bayesian layers")
+        self.seed = int(seed)
+        self.device = self.layers[0].mu_weight.device
+        _lib.require_cuda(self.layers[0].mu_weight)
+        tensors = []   # (layer, which, mu, rho, stream_id, offset)
+        total = 0
+        for L in self.layers:
+            for which in ("weight", "bias"):
+                if which == "bias" and not L.bias:
+                    continue
+                mu, rho = getattr(L, "mu_" + which), getattr(L, "rho_" + which)
+                if mu.dtype != torch.float32 or not mu.is_contiguous() or not rho.is_contiguous():
+                    raise RuntimeError("MCArena: parameters must be contiguous float32")
+                tensors.append((L, which, mu, rho, 2 * int(L.layer_id) + (1 if which == "bias" else 0), total))
+                total += (mu.numel() + 3) // 4 * 4          # keep every view 16-byte aligned
+        self.buffer = torch.empty(total, dtype=torch.float32, device=self.device)
+        base = self.buffer.data_ptr()
+        rows, blocks = [], []
+        self._ptrs = []
+        for e, (L, which, mu, rho, sid, off) in enumerate(tensors):
+            n = mu.numel()
+            rows.append([mu.data_ptr(), rho.data_ptr(), base + 4 * off, n, sid])
+            self._ptrs.append((mu, rho, mu.data_ptr(), rho.data_ptr()))
+            for b0 in range(0, (n + 3) // 4, 256):
+                blocks.append([e, b0])
+            L.__dict__.setdefault("_arena_views", {})[which] = self.buffer[off:off + n].view(mu.shape)
+        self.entries = torch.tensor(rows, dtype=torch.int64).to(self.device)
+        self.blocks = torch.tensor(blocks, dtype=torch.int32).to(self.device)
+        self.n_blocks = len(blocks)
+        self.sample0 = torch.zeros((), dtype=torch.int64, device=self.device)   # device-side sample index (graph replay)
+
+    def valid(self) -> bool:
+        return all(mu.data_ptr() == pm and rho.data_ptr() == pr for mu, rho, pm, pr in self._ptrs)
+
+    def attach(self, on: bool = True):
+        for L in self.layers:
+            L._arena = L.__dict__.get("_arena_views") if on else None
+
+    def draw(self, sample_id: Optional[int] = None):
+        """fill the arena for global sample `sample_id`; None = read the index from the device word `self.sample0`"""
+        from .bayesian import functional as BF
+        if sample_id is None:
+            BF.sample_batched(self.entries, self.blocks, self.n_blocks, self.seed, 0, self.sample0)
+        else:
+            BF.sample_batched(self.entries, self.blocks, self.n_blocks, self.seed, int(sample_id), None)
+
+
 class MCSampler:
     """Draws Monte-Carlo predictions of a Bayesian network for one input.
 
@@ -62,23 +122,82 @@ class MCSampler:
     seed       : Philox seed shared by all ranks
     batch      : samples evaluated per forward (S-batched grouped kernels); 1 reproduces the reference loop
     out_index  : which element of the network's output list is the prediction (eval.py:200 uses [-1])
+    arena      : draw all layers' weights with one launch per sample (philox source, batch 1); same numbers as without
+    graph      : capture the forward of one sample as a CUDA graph per input shape and replay it (needs `arena`); the
+                 reference's ~700 launches per sample are otherwise bound by the host
     """
 
     def __init__(self, net, seed: int = 287128, batch: int = 1, eps_source: str = "philox", out_index: int = -1,
-                 post: Optional[Callable] = None):
+                 post: Optional[Callable] = None, arena: bool = True, graph: bool = False):
         self.net = net
         self.seed = seed
         self.batch = max(1, int(batch))
         self.eps_source = eps_source
         self.out_index = out_index
         self.post = post or (lambda y: torch.clamp(y, 0, 1))   # eval.py:201
+        self.use_arena = bool(arena) and eps_source == "philox" and self.batch == 1
+        self.use_graph = bool(graph) and self.use_arena
+        self._arena = None
+        self._graphs = {}
         bayesian.set_prediction_type(net, deterministic=False)
+
+    # ------------------------------------------------------------------------------------------------
+    def _get_arena(self):
+        if self._arena is None or not self._arena.valid():
+            self._arena = MCArena(self.net, self.seed)
+            self._graphs = {}
+        return self._arena
+
+    def _forward_one(self, x):
+        y = self.net(x)
+        y = y[self.out_index] if isinstance(y, (list, tuple)) else y
+        return self.post(y)
+
+    def _graph_for(self, x):
+        key = (tuple(x.shape), x.dtype, x.device)
+        rec = self._graphs.get(key)
+        if rec is None:
+            arena = self._get_arena()
+            static_x = x.clone()
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream(x.device))
+            with torch.cuda.stream(side):            # warm-up off the capture: lazy initialisation, workspace growth
+                for _ in range(2):
+                    arena.draw(None)
+                    self._forward_one(static_x)
+            torch.cuda.current_stream(x.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                arena.draw(None)
+                static_y = self._forward_one(static_x)
+            rec = (g, static_x, static_y)
+            self._graphs[key] = rec
+        return rec
 
     @torch.no_grad()
     def sample(self, x: torch.Tensor, sample_ids: Sequence[int]) -> torch.Tensor:
         """x: (1, C, H, W) -> (len(sample_ids), C_out, H, W), one prediction per global sample index."""
         outs = []
         ids = list(sample_ids)
+        if self.use_arena and ids and x.is_cuda and x.shape[0] == 1:
+            arena = self._get_arena()
+            bayesian.set_mc_config(self.net, mc_samples=1, eps_source="philox", seed=self.seed, sample0=0)
+            arena.attach(True)
+            try:
+                if self.use_graph:
+                    g, static_x, static_y = self._graph_for(x)
+                    static_x.copy_(x)
+                    for sid in ids:
+                        arena.sample0.fill_(int(sid))
+                        g.replay()
+                        outs.append(static_y.clone())
+                else:
+                    for sid in ids:
+                        arena.draw(int(sid))
+                        outs.append(self._forward_one(x))
+            finally:
+                arena.attach(False)
+            return torch.cat(outs, dim=0)
         i = 0
         while i < len(ids):
             # batch runs of consecutive-by-stride ids cannot share a Philox `sample0` unless contiguous; batch only

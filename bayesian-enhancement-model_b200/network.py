@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import bayesian
-from .ss2d import SS2D, LayerNorm2d, apply_1x1
+from .ss2d import SS2D, LayerNorm2d, apply_1x1, apply_residual, fuses_act
 
 
 class gdMlp(nn.Module):
@@ -33,11 +33,15 @@ class gdMlp(nn.Module):
         self.project_out = nn.Conv2d(hidden_features, out_features, kernel_size=1)
         self.act = act_layer()
 
-    def forward(self, x, pre_norm=None):
+    def forward(self, x, pre_norm=None, residual=None):
+        """vmamba.py:127-133; `residual`: the block's skip connection, added by project_out when it can fuse it."""
         x = apply_1x1(self.project_in, x, pre_norm)
-        x1, x2 = self.dwconv(x).chunk(2, dim=1)
-        x = self.act(x1) * x2
-        return self.project_out(x)
+        if fuses_act(self.dwconv) and isinstance(self.act, nn.GELU) and self.act.approximate == "none":
+            x = self.dwconv(x, post_act="gelu_gate")         # chunk -> gelu(x1) * x2 inside the depthwise kernel
+        else:
+            x1, x2 = self.dwconv(x).chunk(2, dim=1)
+            x = self.act(x1) * x2
+        return apply_residual(self.project_out, x, residual)
 
 
 class VSSBlock(nn.Module):
@@ -59,8 +63,8 @@ class VSSBlock(nn.Module):
                          drop=mlp_drop_rate, channels_first=channel_first)
 
     def forward(self, x):
-        x = x + self.op(x, pre_norm=self.norm)
-        return x + self.mlp(x, pre_norm=self.norm2)
+        x = self.op(x, pre_norm=self.norm, residual=x)
+        return self.mlp(x, pre_norm=self.norm2, residual=x)
 
 
 class PatchMerging(nn.Module):

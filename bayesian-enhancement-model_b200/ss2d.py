@@ -142,22 +142,45 @@ class SS2D(nn.Module):
         return ss2d_core(x, self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias, self.A_logs, self.Ds,
                          x_proj_bias=getattr(self, "x_proj_bias", None), out_norm=self.out_norm if apply_out_norm else None)
 
-    def forward(self, x: torch.Tensor, pre_norm=None, **kwargs):
+    def forward(self, x: torch.Tensor, pre_norm=None, residual=None, **kwargs):
         """forwardv2 (vmamba.py:700-716). `pre_norm`: the block's LayerNorm2d; when in_proj / out_proj are Bayesian 1x1
-        layers of this package both the block norm and `out_norm` are fused into their kernels."""
+        layers of this package both the block norm and `out_norm` are fused into their kernels, SiLU into the depthwise
+        kernel and `residual` (the block's skip connection, vmamba.py:1331) into out_proj's epilogue."""
         x = apply_1x1(self.in_proj, x, pre_norm)
-        if self.with_dconv:
-            x = self.conv2d(x)
-        x = self.act(x)
+        if self.with_dconv and fuses_act(self.conv2d) and isinstance(self.act, nn.SiLU):
+            x = self.conv2d(x, post_act="silu")
+        else:
+            if self.with_dconv:
+                x = self.conv2d(x)
+            x = self.act(x)
         fuse_out = fuses_norm(self.out_proj) and isinstance(self.out_act, nn.Identity) and not torch.is_grad_enabled()
         y = self.forward_core(x, apply_out_norm=not fuse_out)
         y = self.out_act(y)
-        return self.dropout(apply_1x1(self.out_proj, y, self.out_norm if fuse_out else None))
+        if isinstance(self.dropout, nn.Identity):
+            return apply_residual(self.out_proj, y, residual, self.out_norm if fuse_out else None)
+        y = self.dropout(apply_1x1(self.out_proj, y, self.out_norm if fuse_out else None))
+        return y if residual is None else residual + y
 
 
 def fuses_norm(layer) -> bool:
     f = getattr(layer, "_fuses_norm", None)
     return bool(f and f())
+
+
+def fuses_act(layer) -> bool:
+    f = getattr(layer, "_fuses_act", None)
+    return bool(f and f()) and not torch.is_grad_enabled()
+
+
+def apply_residual(layer, x, residual, norm=None):
+    """residual + layer(norm(x)), the additions / normalisation handed to the layer when it can fuse them"""
+    f = getattr(layer, "_fuses_residual", None)
+    if residual is not None and f and f() and not torch.is_grad_enabled():
+        if norm is not None and fuses_norm(layer):
+            return layer(x, pre_norm=norm, residual=residual)
+        return layer(x if norm is None else norm(x), residual=residual)
+    y = apply_1x1(layer, x, norm)
+    return y if residual is None else residual + y
 
 
 def apply_1x1(layer, x, norm):

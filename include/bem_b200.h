@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define BEM_ABI_VERSION 3
+#define BEM_ABI_VERSION 4
 
 /* element types of u/delta/B/C/x-activations */
 enum { BEM_F32 = 0, BEM_F16 = 1, BEM_BF16 = 2 };
@@ -211,6 +211,30 @@ typedef struct BemBayesSampleParams {
 } BemBayesSampleParams;
 int bem_bayes_sample(const BemBayesSampleParams* p, void* stream);
 
+/* One launch that samples every Bayesian tensor of a network for one Monte-Carlo draw: the per-layer
+ * `eps.normal_(); w = mu + sigma * eps` pairs of one forward (conv.py:105-111 x ~60 layers) collapsed into a single
+ * kernel. Entry i yields exactly what bem_bayes_sample gives for (seed, stream_id_i, sample) with the Philox source.
+ * `entries` and `blocks` are DEVICE arrays. blocks[2b] = entry index, blocks[2b+1] = first 4-element Philox block of
+ * CUDA block b, which covers 256 such blocks (1024 elements) of that entry.
+ * sample = sample0 + (sample0_dev ? *sample0_dev : 0): the device word lets a captured CUDA graph be replayed for
+ * another sample index. */
+typedef struct BemBayesSampleEntry {
+    const float* mu;
+    const float* rho;
+    float* w;
+    int64_t numel;
+    int64_t stream_id;
+} BemBayesSampleEntry;
+typedef struct BemBayesSampleBatchedParams {
+    const BemBayesSampleEntry* entries;
+    const int32_t* blocks;
+    int32_t n_blocks;
+    uint64_t seed;
+    int64_t sample0;
+    const int64_t* sample0_dev;
+} BemBayesSampleBatchedParams;
+int bem_bayes_sample_batched(const BemBayesSampleBatchedParams* p, void* stream);
+
 typedef struct BemBayesPointwiseParams {
     int32_t n_samples;   /* S: weight sets; 1 = shared weights */
     int32_t batch;       /* total images = S * Bx */
@@ -233,6 +257,8 @@ typedef struct BemBayesPointwiseParams {
                                   basicsr/vmamba/models/vmamba.py:659-661, with the K directions as weight sets) */
     void* workspace;        /* bem_bayes_pointwise_workspace_bytes() bytes, 16-byte aligned: packed weight tiles */
     int64_t workspace_bytes;
+    const float* residual;  /* (batch, cout, P) or NULL: out = residual + conv(x) — the block's skip connection
+                               (vmamba.py:1331-1333) folded into the epilogue; may alias `out` */
 } BemBayesPointwiseParams;
 int64_t bem_bayes_pointwise_workspace_bytes(int n_samples, int cin, int cout);
 int bem_bayes_pointwise(const BemBayesPointwiseParams* p, void* stream);
@@ -245,6 +271,9 @@ typedef struct BemBayesDepthwiseParams {
     const float* w;      /* (S, C, K, K) */
     const float* bias;   /* (S, C) or NULL */
     float* out;
+    int32_t act;         /* what follows the convolution in the reference, fused:
+                            0 none; 1 SiLU (SS2D.act, vmamba.py:708-710); 2 gated GELU: out has C/2 channels,
+                            out[c] = gelu(y[c]) * y[c + C/2] (gdMlp: chunk -> act(x1) * x2, vmamba.py:129-131) */
 } BemBayesDepthwiseParams;
 int bem_bayes_depthwise(const BemBayesDepthwiseParams* p, void* stream);
 

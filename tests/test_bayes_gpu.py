@@ -266,3 +266,75 @@ def test_fused_layernorm_pointwise(cin, cout, H, W):
         a = lin(x, pre_norm=norm)
         bref = lin(norm(x))
     assert nmax_err(a.cpu().numpy(), bref.cpu().numpy()) < TOL
+
+
+@pytest.mark.parametrize("C,H,W,S,Bx", [(8, 17, 23, 1, 1), (40, 33, 48, 1, 2), (6, 9, 600, 2, 1), (320, 20, 28, 1, 1)])
+@pytest.mark.parametrize("act", [None, "silu", "gelu_gate"])
+def test_depthwise_fused_activation(C, H, W, S, Bx, act):
+    """depthwise 3x3 + the activation that follows it in the reference (SiLU of SS2D, vmamba.py:708-710; gated GELU of
+    gdMlp, vmamba.py:129-131) in one kernel == conv2d then the torch activation, incl. ragged widths and row tails"""
+    import torch.nn.functional as F
+    from bem_b200.bayesian import functional as BF
+    g = torch.Generator(device="cpu").manual_seed(C * 100 + W)
+    x = torch.randn(S * Bx, C, H, W, generator=g).cuda()
+    w = torch.randn(S, C, 3, 3, generator=g).cuda() / 3
+    b = torch.randn(S, C, generator=g).cuda()
+    out = BF.depthwise_conv3x3(x, w, b, S, act=act)
+    refs = []
+    for s in range(S):
+        y = F.conv2d(x[s * Bx:(s + 1) * Bx].double(), w[s].unsqueeze(1).double(), b[s].double(), padding=1, groups=C)
+        if act == "silu":
+            y = F.silu(y)
+        elif act == "gelu_gate":
+            y1, y2 = y.chunk(2, dim=1)
+            y = F.gelu(y1) * y2
+        refs.append(y)
+    ref = torch.cat(refs, 0)
+    assert out.shape == ref.shape
+    assert nmax_err(out.cpu().numpy(), ref.cpu().numpy()) < TOL
+
+
+@pytest.mark.parametrize("cin,cout,H,W,ln", [(40, 40, 20, 30, True), (160, 40, 9, 13, False), (40, 200, 8, 9, True), (24, 7, 5, 4, False)])
+def test_pointwise_fused_residual(cin, cout, H, W, ln):
+    """skip connection folded into the 1x1 layer's epilogue (vmamba.py:1331-1333): layer(x, residual=r) == r + layer(x),
+    on the tensor-core kernel (aligned and unaligned pixel counts) and on the CUDA-core kernel"""
+    from bem_b200 import bayesian
+    from bem_b200.bayesian import functional as BF
+    from bem_b200.ss2d import LayerNorm2d
+    torch.manual_seed(cin * 7 + cout)
+    layer = bayesian.Conv2dReparameterization(cin, cout, 1, bias=True).cuda().eval()
+    norm = LayerNorm2d(cin).cuda() if ln else None
+    x = torch.randn(2, cin, H, W, device="cuda")
+    r = torch.randn(2, cout, H, W, device="cuda")
+    eps_w, eps_b = torch.randn_like(layer.eps_weight), torch.randn_like(layer.eps_bias)
+    with torch.no_grad():
+        fused = layer(x, eps_weight=eps_w, eps_bias=eps_b, pre_norm=norm, residual=r)
+        plain = layer(x, eps_weight=eps_w, eps_bias=eps_b, pre_norm=norm)
+    assert nmax_err(fused.cpu().numpy(), (r + plain).cpu().numpy()) < 1e-6
+    w = torch.randn(1, cout, cin, device="cuda")
+    simt = BF.pointwise_conv(x, w, None, 1, force_simt=True, residual=r)
+    assert nmax_err(simt.cpu().numpy(), (r + BF.pointwise_conv(x, w, None, 1, force_simt=True)).cpu().numpy()) < 1e-6
+
+
+def test_batched_sampling_matches_per_layer_sampling():
+    """MCArena (one launch for the whole network) gives every layer bit-identical weights to its own Philox draw"""
+    from bem_b200 import bayesian, mc
+    from bem_b200.bayesian import functional as BF
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(bayesian.Conv2dReparameterization(5, 7, 3, padding=1), bayesian.Linear2dReparameterization(7, 300),
+                              bayesian.Conv2dReparameterization(300, 300, 3, padding=1, groups=300, bias=False)).cuda().eval()
+    bayesian.set_mc_config(net, mc_samples=1, eps_source="philox", seed=99, sample0=0)
+    arena = mc.MCArena(net, seed=99)
+    for sample in (0, 5, 2 ** 33 + 1):
+        arena.draw(sample)
+        for L in arena.layers:
+            for which in ("weight", "bias"):
+                if which == "bias" and not L.bias:
+                    continue
+                sid = 2 * int(L.layer_id) + (which == "bias")
+                w, _ = BF.sample_weights(getattr(L, "mu_" + which), getattr(L, "rho_" + which), None, 1, 99, sid, sample)
+                assert torch.equal(w[0], L._arena_views[which]), (L.layer_id, which, sample)
+    arena.sample0.fill_(5)
+    arena.draw(None)                                   # sample index from the device word (CUDA-graph replay path)
+    ref, _ = BF.sample_weights(arena.layers[1].mu_weight, arena.layers[1].rho_weight, None, 1, 99, 2 * int(arena.layers[1].layer_id), 5)
+    assert torch.equal(ref[0], arena.layers[1]._arena_views["weight"])

@@ -128,3 +128,25 @@ def test_select_best_large_ties():
     assert int(mc.select_best(s)[0].item()) == 1234
     assert int(mc.select_best(-s, take_min=True)[0].item()) == 1234
     assert int(mc.select_best(torch.zeros(777, device="cuda"))[0].item()) == 0
+
+
+def test_mc_sampler_arena_and_cuda_graph_match_per_layer_path():
+    """one-launch weight arena and CUDA-graph replay are execution strategies only: same predictions as the per-layer
+    sampling path, sample by sample"""
+    from bem_b200 import mc, network
+    torch.manual_seed(0)
+    net = network.build_bayesian_model().cuda().eval()
+    x = torch.rand(1, 3, 32, 48, device="cuda")
+    ids = [0, 3, 4, 11]
+    with torch.backends.cudnn.flags(allow_tf32=False):
+        base = mc.MCSampler(net, seed=7, arena=False).sample(x, ids)
+        arena = mc.MCSampler(net, seed=7, arena=True).sample(x, ids)
+        graph_sampler = mc.MCSampler(net, seed=7, arena=True, graph=True)
+        graph = graph_sampler.sample(x, ids)
+        x2 = torch.rand(1, 3, 32, 48, device="cuda")
+        graph2 = graph_sampler.sample(x2, [4])           # replay with another input and sample index
+        ref2 = mc.MCSampler(net, seed=7, arena=False).sample(x2, [4])
+    assert nmax_err(arena.cpu().numpy(), base.cpu().numpy()) < 5e-5    # library convs are not bitwise run-to-run
+    assert nmax_err(graph.cpu().numpy(), base.cpu().numpy()) < 5e-5
+    assert nmax_err(graph2.cpu().numpy(), ref2.cpu().numpy()) < 5e-5
+    assert float((graph[0] - graph[1]).abs().max()) > 0
