@@ -204,29 +204,36 @@ __global__ void __launch_bounds__(256) bayes_pointwise_kernel(const BemBayesPoin
 // scalars loaded per output row instead of 18 scalars), float4 stores. ACT 2 (gated GELU) walks channel c and c + C/2
 // together and writes C/2 channels.
 // ------------------------------------------------------------------------------------------------
-constexpr int DW_ROWS = 8;
+constexpr int DW_ROWS = 16;
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.f + expf(-v)); }                        // torch SiLU, fp32
 __device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }   // nn.GELU() (erf form)
 
 struct DwRow { float v[6]; };   // columns w0-1 .. w0+4 of one input row (zero outside the image)
 
-__device__ __forceinline__ DwRow dw_load_row(const float* __restrict__ plane, int hh, int H, int W, int w0, bool vec_ok) {
+// VEC: W % 4 == 0 and 16-byte aligned planes -> one float4 + two halo scalars per row, the halo addresses clamped into
+// the row and their values masked (no divergence at the image's left / right edge). Rows outside the image are zero
+// (a branch that is uniform except in warps straddling two strips).
+template <bool VEC>
+__device__ __forceinline__ DwRow dw_load_row(const float* __restrict__ plane, int hh, int H, int W, int w0, int loff, int roff) {
     DwRow r;
 #pragma unroll
     for (int j = 0; j < 6; ++j) r.v[j] = 0.f;
-    if (hh < 0 || hh >= H) return r;
-    const float* row = plane + (int64_t)hh * W;
-    if (vec_ok && w0 + 3 < W) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(row + w0));
+    if ((unsigned)hh >= (unsigned)H) return r;
+    const float* row = plane + (int64_t)hh * W + w0;
+    if (VEC) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(row));
+        const float l = __ldg(row + loff), rr = __ldg(row + roff);
+        r.v[0] = loff < 0 ? l : 0.f;
         r.v[1] = q.x; r.v[2] = q.y; r.v[3] = q.z; r.v[4] = q.w;
+        r.v[5] = roff > 3 ? rr : 0.f;
     } else {
 #pragma unroll
-        for (int j = 1; j < 5; ++j)
-            if (w0 + j - 1 < W) r.v[j] = __ldg(row + w0 + j - 1);
+        for (int j = 0; j < 6; ++j) {
+            const int ww = w0 + j - 1;
+            if (ww >= 0 && ww < W) r.v[j] = __ldg(row + j - 1);
+        }
     }
-    if (w0 > 0) r.v[0] = __ldg(row + w0 - 1);
-    if (w0 + 4 < W) r.v[5] = __ldg(row + w0 + 4);
     return r;
 }
 
@@ -237,8 +244,8 @@ __device__ __forceinline__ void dw_fma_row(const DwRow& r, const float* __restri
         for (int j = 0; j < 3; ++j) acc[o] = fmaf(w3[j], r.v[o + j], acc[o]);
 }
 
-template <int ACT>
-__global__ void __launch_bounds__(256) bayes_depthwise3_kernel(const BemBayesDepthwiseParams p) {
+template <int ACT, bool VEC>
+__global__ void __launch_bounds__(256, 3) bayes_depthwise3_kernel(const BemBayesDepthwiseParams p) {
     constexpr int NP = ACT == 2 ? 2 : 1;                 // input planes per thread
     const int Cout = ACT == 2 ? p.C / 2 : p.C;
     const int W4 = (p.W + 3) / 4, HS = (p.H + DW_ROWS - 1) / DW_ROWS;
@@ -257,25 +264,26 @@ __global__ void __launch_bounds__(256) bayes_depthwise3_kernel(const BemBayesDep
         xin[q] = p.x + ((int64_t)img * p.C + cc) * p.H * p.W;
     }
     float* out = p.out + (int64_t)plane * p.H * p.W;
-    const bool vec_ok = (p.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.out)) & 15) == 0;
     const int64_t strips = (int64_t)HS * W4;
     for (int64_t t = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; t < strips; t += (int64_t)gridDim.y * blockDim.x) {
         const int hs = (int)(t / W4), w0 = (int)(t - (int64_t)hs * W4) * 4;
         const int h0 = hs * DW_ROWS;
+        const int loff = w0 > 0 ? -1 : 0, roff = w0 + 4 < p.W ? 4 : 3;   // halo columns, clamped into the row
         DwRow r0[NP], r1[NP];
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
-            r0[q] = dw_load_row(xin[q], h0 - 1, p.H, p.W, w0, vec_ok);
-            r1[q] = dw_load_row(xin[q], h0, p.H, p.W, w0, vec_ok);
+            r0[q] = dw_load_row<VEC>(xin[q], h0 - 1, p.H, p.W, w0, loff, roff);
+            r1[q] = dw_load_row<VEC>(xin[q], h0, p.H, p.W, w0, loff, roff);
         }
+        float* dst = out + (int64_t)h0 * p.W + w0;
 #pragma unroll
-        for (int i = 0; i < DW_ROWS; ++i) {
+        for (int i = 0; i < DW_ROWS; ++i, dst += p.W) {
             const int h = h0 + i;
             if (h >= p.H) break;
             float res[NP][4];
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
-                const DwRow r2 = dw_load_row(xin[q], h + 1, p.H, p.W, w0, vec_ok);
+                const DwRow r2 = dw_load_row<VEC>(xin[q], h + 1, p.H, p.W, w0, loff, roff);
                 float acc[4] = {b[q], b[q], b[q], b[q]};
                 dw_fma_row(r0[q], &w[q][0], acc);
                 dw_fma_row(r1[q], &w[q][3], acc);
@@ -292,8 +300,7 @@ __global__ void __launch_bounds__(256) bayes_depthwise3_kernel(const BemBayesDep
                 else if (ACT == 2) y[o] = gelu_f(res[0][o]) * res[NP - 1][o];
                 else y[o] = res[0][o];
             }
-            float* dst = out + (int64_t)h * p.W + w0;
-            if (vec_ok && w0 + 3 < p.W) *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
+            if (VEC) *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
             else {
 #pragma unroll
                 for (int o = 0; o < 4; ++o)
@@ -301,6 +308,13 @@ __global__ void __launch_bounds__(256) bayes_depthwise3_kernel(const BemBayesDep
             }
         }
     }
+}
+
+template <int ACT>
+static void depthwise_launch(const BemBayesDepthwiseParams& p, dim3 grid, cudaStream_t stream) {
+    const bool vec = (p.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.out)) & 15) == 0;
+    if (vec) bayes_depthwise3_kernel<ACT, true><<<grid, 256, 0, stream>>>(p);
+    else bayes_depthwise3_kernel<ACT, false><<<grid, 256, 0, stream>>>(p);
 }
 
 }  // namespace bem
@@ -355,9 +369,9 @@ int bem_bayes_depthwise(const BemBayesDepthwiseParams* p, void* stream) {
     int64_t by = (strips + 255) / 256;
     if (by > 1024) by = 1024;
     dim3 grid((unsigned)planes, (unsigned)by);
-    if (p->act == 0) bayes_depthwise3_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
-    else if (p->act == 1) bayes_depthwise3_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
-    else bayes_depthwise3_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+    if (p->act == 0) depthwise_launch<0>(*p, grid, (cudaStream_t)stream);
+    else if (p->act == 1) depthwise_launch<1>(*p, grid, (cudaStream_t)stream);
+    else depthwise_launch<2>(*p, grid, (cudaStream_t)stream);
     return (int)cudaGetLastError();
 }
 

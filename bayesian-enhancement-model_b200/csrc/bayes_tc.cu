@@ -67,6 +67,14 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
                  "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
                  : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                 "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                 "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
@@ -330,19 +338,29 @@ __global__ void __launch_bounds__(128, 4) bayes_pointwise_tc_kernel(const BemBay
 
 // ------------------------------------------------------------------------------------------------
 // persistent, warp-specialised form (the default): one CTA per SM walks (image, pixel tile, output-channel tile) items
-//   warps 0,19  producers: raw x rows (cp.async, one 512-byte row per warp instruction) into a deep shared-memory ring
-//   warp 18     TMA producer: packed weight tiles (ring) and the per-channel epilogue vectors
-//   warp 1      MMA issuer: 3 x tcgen05.mma per K step, A operand from TMEM, B from shared memory
-//   warps 2-9   transform: raw x tile -> (x - shift) split into tf32 hi / lo -> tcgen05.st into the A ring in TMEM
-//               (pixel = TMEM lane, channel = column); LayerNorm sums on the way
-//   warps 10-17 epilogue: tcgen05.ld -> rstd * (acc - mean * s_n) + t_n -> 128-byte coalesced stores
+//   warps 0-3   producers: raw x rows (cp.async, one 512-byte row per warp instruction) into a deep shared-memory ring
+//   warp 4      MMA issuer: 3 x tcgen05.mma per K step, A operand from TMEM, B from shared memory
+//   warp 5      TMA producer: packed weight tiles (ring) and the per-channel epilogue vectors
+//   warps 6-13  transform: raw x tile -> (x - shift) split into tf32 hi / lo -> tcgen05.st into the A ring in TMEM
+//               (pixel = TMEM lane, channel = column), two groups of four warps on alternate chunks; LayerNorm sums
+//   warps 14-21 epilogue: tcgen05.ld -> rstd * (acc - mean * s_n) + t_n -> 128-byte coalesced stores
 // so the loads of item i+1, the MMAs of item i and the stores of item i-1 overlap. Keeping A in TMEM takes its 16 KB of
 // stores and 24 KB of MMA operand reads per chunk off shared memory, which otherwise bounds the kernel.
 // TMEM columns: [0,192) and [192,384) accumulators, [384,512) A ring of 4 stages x (16 hi + 16 lo).
 // Rows of A past the end of the image carry zero-filled or stale values: row m of D depends on row m of A only and
 // those rows are never stored. Input channels past `cin` (last K chunk) are zeroed, they feed every output.
 // ------------------------------------------------------------------------------------------------
-constexpr int P3_LAG = 6;     // cp.async groups (chunks) in flight per producer warp
+// debug timeline (tools/trace_pointwise.py, BEM_PW_DBG bit 3): (tag, arg, SM clock) records of CTA 0, one region of
+// TRACE_PER records per traced warp, plain stores (nothing on the critical path waits for them)
+constexpr int TRACE_ROLES = 8, TRACE_PER = 2048;
+__device__ uint4 g_trace[TRACE_ROLES * TRACE_PER];
+struct Tracer {
+    uint32_t n = 0;
+    __device__ __forceinline__ void operator()(int dbg, int role, uint32_t tag, uint32_t arg) {
+        if ((dbg & 8) && blockIdx.x == 0 && n < TRACE_PER) g_trace[role * TRACE_PER + n++] = make_uint4(tag, arg, (uint32_t)clock64(), 1u);
+    }
+};
+
 constexpr int P3_RS_MAX = 16;  // raw x stages  (TC_KC rows x 128 pixels x 4 B = 8 KB each), as many as fit
 constexpr int P3_AS = 4;       // A stages in TMEM (16 hi + 16 lo columns each)
 constexpr int P3_NMAX = 192;   // output channels per tile: two accumulators + the A ring fit the 512 TMEM columns
@@ -350,7 +368,9 @@ constexpr uint32_t P3_ACC_COLS = 192, P3_A_COL0 = 384;
 constexpr int P3_BS_MAX = 8;   // B stages      (hi | lo, 2 * NT * TC_KC * 4 B each)
 constexpr int P3_XW = 8;       // transform warps
 constexpr int P3_EW = 8;       // epilogue warps (two per TMEM lane quarter, alternating 16-column groups)
-constexpr int P3_THREADS = (4 + P3_XW + P3_EW) * 32;
+constexpr int P3_PW = 4;       // activation producer warps (TC_KC / P3_PW rows of every chunk each)
+constexpr int P3_W_MMA = P3_PW, P3_W_WGT = P3_PW + 1, P3_W_X0 = P3_PW + 2, P3_W_E0 = P3_W_X0 + P3_XW;   // first warp of each role
+constexpr int P3_THREADS = (P3_W_E0 + P3_EW) * 32;
 
 struct Ring {   // position in a ring of `n` stages and the phase bit of its mbarriers
     uint32_t s = 0, ph = 0;
@@ -367,12 +387,20 @@ struct P3Item {
     int tile, img, s_idx, npx;
     int64_t p0;
 };
-__device__ __forceinline__ P3Item p3_item(const BemBayesPointwiseParams& p, int64_t it, int ntiles, int ptiles) {
+// item index -> (tile, pixel tile, image); 32-bit arithmetic (the host checks n_items < 2^31): 64-bit divisions cost
+// ~1400 clk per item on the MMA warp's critical path
+__device__ __forceinline__ P3Item p3_item(const BemBayesPointwiseParams& p, int64_t it64, int ntiles, int ptiles) {
     P3Item r;
-    r.tile = (int)(it % ntiles);
-    const int64_t q = it / ntiles;
-    r.p0 = (q % ptiles) * TC_M;
-    r.img = (int)(q / ptiles);
+    const uint32_t it = (uint32_t)it64;
+    uint32_t q = it;
+    r.tile = 0;
+    if (ntiles > 1) {
+        q = it / (uint32_t)ntiles;
+        r.tile = (int)(it - q * (uint32_t)ntiles);
+    }
+    const uint32_t im = q / (uint32_t)ptiles;
+    r.p0 = (int64_t)(q - im * (uint32_t)ptiles) * TC_M;
+    r.img = (int)im;
     r.s_idx = p.n_samples > 1 ? (p.sample_interleave ? r.img % p.n_samples : r.img / (p.batch / p.n_samples)) : 0;
     r.npx = (int)min((int64_t)TC_M, p.P - r.p0);
     return r;
@@ -382,13 +410,14 @@ template <bool LN>
 __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(const BemBayesPointwiseParams p, const int NT, const int ntiles,
                                                                           const int ptiles, const int64_t n_items,
                                                                           const float* __restrict__ pack, const float* __restrict__ vec,
-                                                                          const uint32_t RS, const uint32_t BS) {
+                                                                          const uint32_t RS, const uint32_t BS, const int b_resident, const int dbg) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t b_bytes = (uint32_t)NT * TC_KC * 4;
     unsigned char* s_raw = smem;
     unsigned char* s_b = s_raw + RS * P3_RAW_BYTES;
-    float2* s_vec = reinterpret_cast<float2*>(s_b + BS * 2 * b_bytes);         // [2 acc buffers][NT] (s_n, t_n)
-    float2* s_part = s_vec + 2 * NT;                                           // [2 acc buffers][2 K halves][128] (sum, sum sq)
+    // B: a ring of BS stages, or (b_resident) every packed tile of the layer, BS = n_samples * ntiles * nk, loaded once
+    float2* s_vec = reinterpret_cast<float2*>(s_b + BS * 2 * b_bytes);         // [n_samples * ntiles][NT] (s_n, t_n), resident
+    float2* s_part = s_vec + p.n_samples * ntiles * NT;                        // [2 acc buffers][2 groups][128] (sum, sum sq)
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 2 * 2 * TC_M);
     uint64_t* raw_full = bars;
     uint64_t* raw_empty = raw_full + P3_RS_MAX;
@@ -404,89 +433,110 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nk = (p.cin + TC_KC - 1) / TC_KC;
+    Tracer tr;
 
     if (tid == 0) {
-        for (int i = 0; i < (int)RS; ++i) { mbar_init(&raw_full[i], 64); mbar_init(&raw_empty[i], P3_XW); }
-        for (int i = 0; i < P3_AS; ++i) { mbar_init(&a_full[i], P3_XW); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < (int)BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < (int)RS; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], P3_XW / 2); }
+        for (int i = 0; i < P3_AS; ++i) { mbar_init(&a_full[i], P3_XW / 2); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < (b_resident ? 1 : (int)BS); ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        mbar_init(&vec_full[0], 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], P3_EW);
             mbar_init(&stats_full[i], P3_XW);
-            mbar_init(&vec_full[i], 1);
         }
         fence_barrier_init();
         fence_proxy_async();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == P3_W_MMA) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 0 || warp == 3 + P3_XW + P3_EW) {
+    if (warp < P3_PW) {
         // ---------------- producers: activations (LDGSTS, 16 B per lane, one 512-byte row per instruction) ----------------
         // 512-byte bulk copies are bound by their per-copy overhead, and a cp.async-tracked mbarrier arrive serialises a
-        // warp's copies behind it (one chunk in flight). So: plain cp.async groups, P3_LAG chunks in flight per warp, and an
-        // ordinary arrive once a group has landed. Rows past the last input channel and pixels past the image are
-        // zero-filled through the src-size operand. Two warps, each taking 8 of the 16 rows of every chunk.
-        const int row0 = warp == 0 ? 0 : TC_KC / 2;
-        Ring r, done;
-        uint32_t issued = 0;
+        // warp's copies behind it. So: plain cp.async groups and an ordinary arrive once a group has landed. Warp w owns
+        // chunks g = w (mod P3_PW) — the loop is latency-bound (~600 clk per iteration), four of them interleave — and
+        // keeps RS / P3_PW of them in flight. Rows past the last input channel and pixels past the image are zero-filled
+        // through the src-size operand.
+        const uint32_t lag = RS / P3_PW - 1;               // groups in flight per warp after which the oldest must land
+        uint32_t g = 0, issued = 0;
+        Ring r, done;                                       // ring positions of chunk g / of this warp's oldest pending chunk
+        for (uint32_t i = 0; i < (uint32_t)warp; ++i) done.next(RS);
         for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
             const P3Item w = p3_item(p, it, ntiles, ptiles);
             const int px = min(lane * 4, w.npx - 4);            // npx % 4 == 0; lanes past the end copy 0 bytes from a valid address
             const uint32_t pbytes = lane * 4 < w.npx ? 16u : 0u;
             const float* x = p.x + (int64_t)w.img * (p.x_img_stride ? p.x_img_stride : (int64_t)p.cin * p.P) + w.p0 + px;
-            for (int kc = 0; kc < nk; ++kc, r.next(RS)) {
+            for (int kc = 0; kc < nk; ++kc, ++g, r.next(RS)) {
+                if (g % P3_PW != (uint32_t)warp) continue;
                 if (lane == 0) mbar_wait(&raw_empty[r.s], r.ph ^ 1, nullptr);
                 __syncwarp();
-                const uint32_t dst = smem_u32(s_raw + r.s * P3_RAW_BYTES) + (row0 * TC_M + lane * 4) * 4;
-                const int c0 = kc * TC_KC + row0;
-                if (c0 + TC_KC / 2 <= p.cin) {
-                    const float* src = x + (int64_t)c0 * p.P;
+                if (warp == 0 && lane == 0) tr(dbg, 0, 2, g);
+                const uint32_t dst = smem_u32(s_raw + r.s * P3_RAW_BYTES) + lane * 16;
+                const int c0 = kc * TC_KC;
+                if ((dbg & 1) == 0) {
+                    if (c0 + TC_KC <= p.cin) {
+                        const float* src = x + (int64_t)c0 * p.P;
 #pragma unroll
-                    for (int row = 0; row < TC_KC / 2; ++row, src += p.P)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + row * (TC_M * 4)), "l"(src), "r"(pbytes) : "memory");
-                } else {
+                        for (int row = 0; row < TC_KC; ++row, src += p.P)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + row * (TC_M * 4)), "l"(src), "r"(pbytes) : "memory");
+                    } else {
 #pragma unroll
-                    for (int row = 0; row < TC_KC / 2; ++row) {
-                        const float* src = x + (int64_t)min(c0 + row, p.cin - 1) * p.P;
-                        const uint32_t sz = c0 + row < p.cin ? pbytes : 0u;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + row * (TC_M * 4)), "l"(src), "r"(sz) : "memory");
+                        for (int row = 0; row < TC_KC; ++row) {
+                            const float* src = x + (int64_t)min(c0 + row, p.cin - 1) * p.P;
+                            const uint32_t sz = c0 + row < p.cin ? pbytes : 0u;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + row * (TC_M * 4)), "l"(src), "r"(sz) : "memory");
+                        }
                     }
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
-                if (++issued > P3_LAG) {
-                    asm volatile("cp.async.wait_group %0;" ::"n"(P3_LAG) : "memory");
-                    mbar_arrive(&raw_full[done.s]);
-                    done.next(RS);
+                if (warp == 0 && lane == 0) tr(dbg, 0, 1, g);
+                if (++issued > lag) {
+                    if (lag == 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
+                    else if (lag == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+                    else asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&raw_full[done.s]);
+                    if (warp == 0 && lane == 0) tr(dbg, 0, 3, g);
+                    for (int i = 0; i < P3_PW; ++i) done.next(RS);
                 }
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        for (uint32_t i = issued > P3_LAG ? issued - P3_LAG : 0; i < issued; ++i, done.next(RS)) mbar_arrive(&raw_full[done.s]);
-    } else if (warp == 2 + P3_XW + P3_EW) {
+        __syncwarp();
+        for (uint32_t i = issued > lag ? issued - lag : 0; i < issued; ++i) {
+            if (lane == 0) mbar_arrive(&raw_full[done.s]);
+            for (int k = 0; k < P3_PW; ++k) done.next(RS);
+        }
+    } else if (warp == P3_W_WGT) {
         // ---------------- TMA producer: weights ----------------
+        // The per-channel epilogue vectors are loaded once. So are the packed tiles when the whole layer fits
+        // (b_resident: every level-0 layer) — consecutive items use the same weights; otherwise they stream through a ring.
         if (lane == 0) {
-            Ring r;
-            uint32_t li = 0;
-            for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
-                const P3Item w = p3_item(p, it, ntiles, ptiles);
-                const float* bsrc = pack + ((int64_t)(w.s_idx * ntiles + w.tile) * nk) * 2 * NT * TC_KC;
-                const uint32_t buf = li & 1;
-                mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1, nullptr);   // the epilogue two items back has read its vectors
-                mbar_arrive_expect_tx(&vec_full[buf], (uint32_t)NT * 8);
-                bulk_g2s(s_vec + buf * NT, vec + ((int64_t)w.s_idx * ntiles + w.tile) * 2 * NT, (uint32_t)NT * 8, &vec_full[buf]);
-                for (int kc = 0; kc < nk; ++kc, r.next(BS)) {
-                    mbar_wait(&b_empty[r.s], r.ph ^ 1, nullptr);
-                    mbar_arrive_expect_tx(&b_full[r.s], 2 * b_bytes);
-                    bulk_g2s(s_b + r.s * 2 * b_bytes, bsrc + (int64_t)kc * 2 * NT * TC_KC, 2 * b_bytes, &b_full[r.s]);
+            const uint32_t vec_bytes = (uint32_t)(p.n_samples * ntiles * NT) * 8;
+            mbar_arrive_expect_tx(&vec_full[0], vec_bytes);
+            bulk_g2s(s_vec, vec, vec_bytes, &vec_full[0]);
+            if (b_resident) {
+                mbar_arrive_expect_tx(&b_full[0], BS * 2 * b_bytes);
+                for (uint32_t i = 0; i < BS; ++i) bulk_g2s(s_b + i * 2 * b_bytes, pack + (int64_t)i * 2 * NT * TC_KC, 2 * b_bytes, &b_full[0]);
+            } else {
+                Ring r;
+                for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+                    const P3Item w = p3_item(p, it, ntiles, ptiles);
+                    const float* bsrc = pack + ((int64_t)(w.s_idx * ntiles + w.tile) * nk) * 2 * NT * TC_KC;
+                    for (int kc = 0; kc < nk; ++kc, r.next(BS)) {
+                        mbar_wait(&b_empty[r.s], r.ph ^ 1, nullptr);
+                        mbar_arrive_expect_tx(&b_full[r.s], 2 * b_bytes);
+                        bulk_g2s(s_b + r.s * 2 * b_bytes, bsrc + (int64_t)kc * 2 * NT * TC_KC, 2 * b_bytes, &b_full[r.s]);
+                    }
                 }
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
+    } else if (warp == P3_W_MMA) {
         // ---------------- MMA issuer ----------------
         // The whole warp walks the loop (uniform control flow keeps descriptors in uniform registers); one elected lane
         // issues. B descriptors are one base plus the stage / K-step offset in the 14-bit address field.
@@ -495,15 +545,22 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
         const uint32_t b_step = (2 * b_bytes) >> 4, b_lo = b_bytes >> 4;
         Ring ra, rb;
         uint32_t li = 0;
+        if (b_resident) mbar_wait(&b_full[0], 0, nullptr);
         for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
             const uint32_t buf = li & 1;
+            if (b_resident) {   // stage index of this item's first tile within the resident set
+                const P3Item w = p3_item(p, it, ntiles, ptiles);
+                rb.s = (uint32_t)((w.s_idx * ntiles + w.tile) * nk);
+            }
             mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1, nullptr);   // the epilogue has drained this accumulator
+            if (lane == 0) tr(dbg, 3, 20, li);
             const uint32_t d = tmem + buf * P3_ACC_COLS;
-            for (int kc = 0; kc < nk; ++kc, ra.next(P3_AS), rb.next(BS)) {
+            for (int kc = 0; kc < nk; ++kc, ra.next(P3_AS), rb.next(b_resident ? 0xffffffffu : BS)) {
                 mbar_wait(&a_full[ra.s], ra.ph, nullptr);
-                mbar_wait(&b_full[rb.s], rb.ph, nullptr);
+                if (!b_resident) mbar_wait(&b_full[rb.s], rb.ph, nullptr);
+                if (lane == 0) tr(dbg, 3, 21, kc);
                 tc_fence_after();
-                if (elect_one()) {
+                if (elect_one() && !(dbg & 4)) {
                     const uint32_t aH = tmem + P3_A_COL0 + ra.s * (2 * TC_KC), aL = aH + TC_KC;
                     const uint64_t dBh = descB0 + (uint64_t)(rb.s * b_step), dBl = dBh + b_lo;
 #pragma unroll
@@ -514,71 +571,86 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
                         umma_tf32_ts(d, aL + ks * 8, dBh + adv, idesc, 1);
                     }
                     umma_commit(&a_empty[ra.s]);
-                    umma_commit(&b_empty[rb.s]);
+                    if (!b_resident) umma_commit(&b_empty[rb.s]);
                     if (kc == nk - 1) umma_commit(&acc_full[buf]);
+                } else if (dbg & 4) {
+                    if (elect_one()) {
+                        mbar_arrive(&a_empty[ra.s]);
+                        if (!b_resident) mbar_arrive(&b_empty[rb.s]);
+                        if (kc == nk - 1) mbar_arrive(&acc_full[buf]);
+                    }
                 }
                 __syncwarp();
             }
         }
-    } else if (warp < 2 + P3_XW) {
+    } else if (warp < P3_W_E0) {
         // ---------------- transform: raw rows -> shifted, split -> A ring in TMEM ----------------
-        // pixel = TMEM lane (a warp reaches lanes 32 * (warp % 4) ..), K half = which of the two warps of that quarter
-        const int m = (warp & 3) * 32 + lane, kh = (warp - 2) >> 2;
-        const uint32_t a_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + P3_A_COL0 + kh * 8;
+        // pixel = TMEM lane (a warp reaches lanes 32 * (warp % 4) ..). The two warps of a lane quarter take alternate
+        // chunks (all 16 channels of a pixel each): the per-chunk handshakes of one group overlap the other group's.
+        const int m = (warp & 3) * 32 + lane, grp = (warp - P3_W_X0) >> 2;
+        const uint32_t a_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + P3_A_COL0;
         Ring rr, ra;
-        uint32_t li = 0;
+        uint32_t li = 0, g = 0;
         for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
             float s1 = 0.f, s2 = 0.f, shift = 0.f;
-            for (int kc = 0; kc < nk; ++kc, rr.next(RS), ra.next(P3_AS)) {
+            if (LN) {   // per-pixel shift of the LayerNorm sums and of A: the pixel's first channel
+                const P3Item w = p3_item(p, it, ntiles, ptiles);
+                if (m < w.npx) shift = __ldg(p.x + (int64_t)w.img * (p.x_img_stride ? p.x_img_stride : (int64_t)p.cin * p.P) + w.p0 + m);
+            }
+            for (int kc = 0; kc < nk; ++kc, ++g, rr.next(RS), ra.next(P3_AS)) {
+                if ((g & 1) != (uint32_t)grp) continue;
                 mbar_wait(&raw_full[rr.s], rr.ph, nullptr);
+                if ((warp & 3) == 0 && lane == 0) tr(dbg, 1 + grp, 10 + grp, g);
                 const float* raw = reinterpret_cast<const float*>(s_raw + rr.s * P3_RAW_BYTES) + m;
-                if (LN && kc == 0) shift = raw[0];                         // per-pixel shift: its first channel
-                float v[8];
+                float v[TC_KC];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = raw[(kh * 8 + e) * TC_M];
-                const int left = p.cin - kc * TC_KC - kh * 8;               // channels of this half that exist
-                if (left < 8) {
+                for (int e = 0; e < TC_KC; ++e) v[e] = (dbg & 2) ? 1.f : raw[e * TC_M];
+                const int left = p.cin - kc * TC_KC;                          // channels of this chunk that exist
+                if (left < TC_KC) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = e < left ? v[e] : shift;   // -> 0 after the shift
+                    for (int e = 0; e < TC_KC; ++e) v[e] = e < left ? v[e] : shift;   // -> 0 after the shift
                 }
                 if (LN) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
+                    for (int e = 0; e < TC_KC; ++e) {
                         v[e] -= shift;
                         s1 += v[e];
                         s2 = fmaf(v[e], v[e], s2);
                     }
                 }
-                float hi[8], lo[8];
+                float hi[TC_KC], lo[TC_KC];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
+                for (int e = 0; e < TC_KC; ++e) {
                     hi[e] = tf32_hi(v[e]);
                     lo[e] = v[e] - hi[e];
                 }
                 mbar_wait(&a_empty[ra.s], ra.ph ^ 1, nullptr);           // the MMAs that read this stage have completed
+                if ((warp & 3) == 0 && lane == 0) tr(dbg, 1 + grp, 12 + grp, g);
                 tc_fence_after();
-                tmem_st8(a_lane + ra.s * (2 * TC_KC), hi);
-                tmem_st8(a_lane + ra.s * (2 * TC_KC) + TC_KC, lo);
+                tmem_st16(a_lane + ra.s * (2 * TC_KC), hi);
+                tmem_st16(a_lane + ra.s * (2 * TC_KC) + TC_KC, lo);
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(&a_full[ra.s]);
                     mbar_arrive(&raw_empty[rr.s]);
+                    if ((warp & 3) == 0) tr(dbg, 1 + grp, 14 + grp, g);
                 }
             }
             if (LN) {
                 const uint32_t buf = li & 1;
                 mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1, nullptr);   // the epilogue two items back has read its sums
-                s_part[(buf * 2 + kh) * TC_M + m] = make_float2(s1, s2);
+                s_part[(buf * 2 + grp) * TC_M + m] = make_float2(s1, s2);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&stats_full[buf]);
             }
         }
     } else {
         // ---------------- epilogue ----------------
-        const int ew = warp - (2 + P3_XW), q = warp & 3, half = ew >> 2, m = q * 32 + lane;   // TMEM lane quarter = warp % 4
+        const int ew = warp - P3_W_E0, q = warp & 3, half = ew >> 2, m = q * 32 + lane;   // TMEM lane quarter = warp % 4
         uint32_t li = 0;
+        mbar_wait(&vec_full[0], 0, nullptr);
         for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
             const P3Item w = p3_item(p, it, ntiles, ptiles);
             const uint32_t buf = li & 1, par = (li >> 1) & 1;
@@ -592,8 +664,8 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
                 rstd = rsqrtf(fmaxf((a.y + b.y) * inv - mean * mean, 0.f) + p.ln_eps);
                 nmr = -mean * rstd;
             }
-            mbar_wait(&vec_full[buf], par, nullptr);
             mbar_wait(&acc_full[buf], par, nullptr);
+            if (ew == 0 && lane == 0) tr(dbg, 4, 30, li);
             tc_fence_after();
             const bool valid = m < w.npx;
             const int64_t P = p.P;
@@ -601,7 +673,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
             float* out = p.out + obase;
             const float* res = p.residual ? p.residual + obase : nullptr;
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * P3_ACC_COLS;
-            const float2* sv = s_vec + buf * NT;
+            const float2* sv = s_vec + (w.s_idx * ntiles + w.tile) * NT;
             const int ngrp = (nvalid + 15) >> 4;
             for (int gi = half; gi < ngrp; gi += 2) {
                 const int c0 = gi * 16;
@@ -638,11 +710,12 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (ew == 0 && lane == 0) tr(dbg, 4, 31, li);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, 512);
+    if (warp == P3_W_MMA) tmem_dealloc(tmem, 512);
 }
 
 static void tc_tiling(int cin, int cout, int nmax, int& ntiles, int& NT, int& nk) {
@@ -686,19 +759,26 @@ int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t str
     float* pack = reinterpret_cast<float*>(p.workspace);
     // the persistent kernel moves x with 16-byte cp.async: rows must start and end on 16-byte boundaries
     static const int force_v2 = env_int("BEM_PW_V2", 0);
+    static const int dbg = env_int("BEM_PW_DBG", 0);   // timing experiments only (results are wrong when set)
     const bool aligned = (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && p.P % 4 == 0 && p.x_img_stride % 4 == 0;
-    const bool persistent = aligned && !force_v2;
     int ntiles, NT, nk;
-    tc_tiling(p.cin, p.cout, persistent ? P3_NMAX : TC_NMAX, ntiles, NT, nk);
+    tc_tiling(p.cin, p.cout, P3_NMAX, ntiles, NT, nk);
+    // the persistent kernel keeps the epilogue vectors of every (sample, tile) in shared memory
+    const bool persistent = aligned && !force_v2 && (int64_t)p.n_samples * ntiles * NT * 8 <= 16 * 1024;
+    if (!persistent) tc_tiling(p.cin, p.cout, TC_NMAX, ntiles, NT, nk);
     float* vec = pack + tc_pack_floats(p.n_samples, p.cin, p.cout, persistent ? P3_NMAX : TC_NMAX);
     const int pack_blocks = p.n_samples * ntiles * nk;
     const int vec_blocks = p.n_samples * ((p.cout + 7) / 8);
     if (persistent) {
-        // shared-memory plan: B ring >= 3 stages (up to ~48 KB), the rest goes to raw x stages in flight
+        // shared-memory plan: the layer's packed tiles resident when they fit in 120 KB, else a B ring of >= 3 stages
+        // (up to ~48 KB); the epilogue vectors resident; the rest goes to raw x stages in flight
         const int b_stage = 2 * NT * TC_KC * 4;
-        const int BS = std::max(3, std::min(P3_BS_MAX, (48 * 1024) / b_stage));
-        const int fixed = BS * b_stage + 2 * NT * 8 + 2 * 2 * TC_M * 8 + (2 * P3_RS_MAX + 2 * P3_AS + 2 * P3_BS_MAX + 8) * 8 + 16;
-        const int RS = std::max(P3_LAG + 2, std::min(P3_RS_MAX, (int)((220 * 1024 - fixed) / (int)P3_RAW_BYTES)));
+        const int all_stages = p.n_samples * ntiles * nk;
+        const int vec_bytes = p.n_samples * ntiles * NT * 8;
+        const int b_resident = (int64_t)all_stages * b_stage <= 120 * 1024;
+        const int BS = b_resident ? all_stages : std::max(3, std::min(P3_BS_MAX, (48 * 1024) / b_stage));
+        const int fixed = BS * b_stage + vec_bytes + 2 * 2 * TC_M * 8 + (2 * P3_RS_MAX + 2 * P3_AS + 2 * P3_BS_MAX + 8) * 8 + 16;
+        const int RS = std::max(2 * P3_PW, std::min(P3_RS_MAX, (int)((220 * 1024 - fixed) / (int)P3_RAW_BYTES)) / P3_PW * P3_PW);
         const int smem_bytes = RS * (int)P3_RAW_BYTES + fixed;
         if (smem_bytes > 227 * 1024) return BEM_ERR_UNSUPPORTED;
         static int attr3[64] = {0}, sms[64] = {0};
@@ -712,11 +792,12 @@ int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t str
         if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
         bayes_weight_pack_kernel<<<pack_blocks + vec_blocks, 256, 0, stream>>>(p, NT, ntiles, nk, pack, 1, vec);
         const int64_t n_items = (int64_t)p.batch * ptiles * ntiles;
+        if (n_items >= (1ll << 31)) return BEM_ERR_UNSUPPORTED;
         const int grid = (int)std::min<int64_t>(n_items, sms[dev]);
         if (p.ln_gamma)
-            bayes_pointwise_tc3_kernel<true><<<grid, P3_THREADS, smem_bytes, stream>>>(p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS);
+            bayes_pointwise_tc3_kernel<true><<<grid, P3_THREADS, smem_bytes, stream>>>(p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS, b_resident, dbg);
         else
-            bayes_pointwise_tc3_kernel<false><<<grid, P3_THREADS, smem_bytes, stream>>>(p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS);
+            bayes_pointwise_tc3_kernel<false><<<grid, P3_THREADS, smem_bytes, stream>>>(p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS, b_resident, dbg);
         return (int)cudaGetLastError();
     }
     uint32_t tmem_cols = 32;
@@ -736,3 +817,15 @@ int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t str
 }
 
 }  // namespace bem
+
+// not part of the ABI: reads (and clears) the debug timeline of the persistent pointwise kernel (tools/trace_pointwise.py)
+extern "C" int bem_dbg_pointwise_trace(unsigned int* out, int max_records) {
+    const int total = bem::TRACE_ROLES * bem::TRACE_PER;
+    if (max_records < total) return -1;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, bem::g_trace, (size_t)total * sizeof(uint4));
+    void* sym = nullptr;
+    cudaGetSymbolAddress(&sym, bem::g_trace);
+    cudaMemset(sym, 0, (size_t)total * sizeof(uint4));
+    return total;
+}

@@ -17,7 +17,23 @@ import torch
 import torch.nn as nn
 
 from . import bayesian
+from .bayesian import functional as BF
 from .ss2d import SS2D, LayerNorm2d, apply_1x1, apply_residual, fuses_act
+
+
+class Conv2d(nn.Conv2d):
+    """nn.Conv2d (same name, parameters and state_dict) whose deterministic 1x1 case — PatchMerging.reduction, the
+    DualUpSample projections, the decoder fusion convs (UNet_arch.py:88-135, 161-163) — runs on the same tcgen05 pointwise
+    kernel as the Bayesian 1x1 layers (one weight set, no sampling) when no gradient is needed; everything else is the
+    library convolution."""
+
+    def forward(self, x):
+        if (self.kernel_size == (1, 1) and self.stride == (1, 1) and self.padding == (0, 0) and self.groups == 1
+                and x.is_cuda and x.dtype == torch.float32 and self.weight.dtype == torch.float32
+                and not (torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad))):
+            w = self.weight.view(1, self.out_channels, self.in_channels)
+            return BF.pointwise_conv(x, w, None if self.bias is None else self.bias.view(1, -1), 1)
+        return super().forward(x)
 
 
 class gdMlp(nn.Module):
@@ -27,10 +43,10 @@ class gdMlp(nn.Module):
         super().__init__()
         out_features = out_features or in_features
         hidden_features = hidden_features or in_features
-        self.project_in = nn.Conv2d(in_features, hidden_features * 2, kernel_size=1)
-        self.dwconv = nn.Conv2d(hidden_features * 2, hidden_features * 2, kernel_size=3, stride=1, padding=1,
+        self.project_in = Conv2d(in_features, hidden_features * 2, kernel_size=1)
+        self.dwconv = Conv2d(hidden_features * 2, hidden_features * 2, kernel_size=3, stride=1, padding=1,
                                 groups=hidden_features * 2)
-        self.project_out = nn.Conv2d(hidden_features, out_features, kernel_size=1)
+        self.project_out = Conv2d(hidden_features, out_features, kernel_size=1)
         self.act = act_layer()
 
     def forward(self, x, pre_norm=None, residual=None):
@@ -74,7 +90,7 @@ class PatchMerging(nn.Module):
         super().__init__()
         self.dim = dim
         self.norm = LayerNorm2d(4 * dim)
-        self.reduction = nn.Conv2d(4 * dim, 2 * dim, 1, 1, 0, bias=False)
+        self.reduction = Conv2d(4 * dim, 2 * dim, 1, 1, 0, bias=False)
 
     def forward(self, x):
         x = torch.cat([x[:, :, 0::2, 0::2], x[:, :, 1::2, 0::2], x[:, :, 0::2, 1::2], x[:, :, 1::2, 1::2]], 1)
@@ -89,19 +105,19 @@ class DualUpSample(nn.Module):
         self.factor = scale_factor
         c = in_channels
         if scale_factor == 2:
-            self.conv = nn.Conv2d(c, c // 2, 1, 1, 0, bias=False)
-            self.up_p = nn.Sequential(nn.Conv2d(c, 2 * c, 1, 1, 0, bias=False), nn.PReLU(), nn.PixelShuffle(2),
-                                      nn.Conv2d(c // 2, c // 2, 1, stride=1, padding=0, bias=False))
-            self.up_b = nn.Sequential(nn.Conv2d(c, c, 1, 1, 0), nn.PReLU(),
+            self.conv = Conv2d(c, c // 2, 1, 1, 0, bias=False)
+            self.up_p = nn.Sequential(Conv2d(c, 2 * c, 1, 1, 0, bias=False), nn.PReLU(), nn.PixelShuffle(2),
+                                      Conv2d(c // 2, c // 2, 1, stride=1, padding=0, bias=False))
+            self.up_b = nn.Sequential(Conv2d(c, c, 1, 1, 0), nn.PReLU(),
                                       nn.Upsample(scale_factor=2, mode="bilinear", align_corners=False),
-                                      nn.Conv2d(c, c // 2, 1, stride=1, padding=0, bias=False))
+                                      Conv2d(c, c // 2, 1, stride=1, padding=0, bias=False))
         elif scale_factor == 4:
-            self.conv = nn.Conv2d(2 * c, c, 1, 1, 0, bias=False)
-            self.up_p = nn.Sequential(nn.Conv2d(c, 16 * c, 1, 1, 0, bias=False), nn.PReLU(), nn.PixelShuffle(4),
-                                      nn.Conv2d(c, c, 1, stride=1, padding=0, bias=False))
-            self.up_b = nn.Sequential(nn.Conv2d(c, c, 1, 1, 0), nn.PReLU(),
+            self.conv = Conv2d(2 * c, c, 1, 1, 0, bias=False)
+            self.up_p = nn.Sequential(Conv2d(c, 16 * c, 1, 1, 0, bias=False), nn.PReLU(), nn.PixelShuffle(4),
+                                      Conv2d(c, c, 1, stride=1, padding=0, bias=False))
+            self.up_b = nn.Sequential(Conv2d(c, c, 1, 1, 0), nn.PReLU(),
                                       nn.Upsample(scale_factor=4, mode="bilinear", align_corners=False),
-                                      nn.Conv2d(c, c, 1, stride=1, padding=0, bias=False))
+                                      Conv2d(c, c, 1, stride=1, padding=0, bias=False))
         else:
             raise NotImplementedError(scale_factor)
 
@@ -159,7 +175,7 @@ class SubNetwork(nn.Module):
         for i in range(level):
             self.decoder_layers.append(nn.ModuleList([
                 DualUpSample(curr, scale_factor=2),
-                nn.Conv2d(curr, curr // 2, 1, 1, bias=False),
+                Conv2d(curr, curr // 2, 1, 1, bias=False),
                 BasicBlock(dim=curr // 2, num_blocks=num_blocks[level - 1 - i], d_state=d_state[level - 1 - i],
                            ssm_ratio=ssm_ratio, mlp_ratio=mlp_ratio, bayesian=True)]))
             curr //= 2
@@ -201,11 +217,11 @@ class Network(nn.Module):
         self.stage = stage
         self.mask_token = nn.Parameter(torch.zeros(1, n_feat, 1, 1))
         nn.init.trunc_normal_(self.mask_token, mean=0.0, std=0.02)
-        self.first_conv = nn.Conv2d(in_channels, n_feat, 3, 1, 1, bias=True)
+        self.first_conv = Conv2d(in_channels, n_feat, 3, 1, 1, bias=True)
         nn.init.kaiming_normal_(self.first_conv.weight, mode="fan_out", nonlinearity="linear")
         nn.init.zeros_(self.first_conv.bias)
         self.subnets = nn.ModuleList([])
-        self.proj = nn.Conv2d(n_feat, out_channels, 3, 1, 1, bias=True)
+        self.proj = Conv2d(n_feat, out_channels, 3, 1, 1, bias=True)
         nn.init.zeros_(self.proj.bias)
         if last_act is None:
             self.last_act = nn.Identity()

@@ -14,6 +14,17 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
 def timed(fn, iters=10):
+    """device time of one call (its kernels captured in a CUDA graph: no host launch gaps), cold L2"""
+    fn()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    fn = g.replay
     ts = []
     for _ in range(iters):
         flush.zero_()
