@@ -11,6 +11,8 @@
 //   bem_bayes_depthwise  S-batched depthwise 3x3, per-sample weights
 // This file holds the fp32 CUDA-core kernels (bit-faithful fp32 accumulate: the 1e-5 parity tier);
 // the tcgen05 tensor-core kernel of the pointwise contraction (the default) lives in bayes_tc.cu.
+#include <cstdlib>
+
 #include "bem_kernels.h"
 
 namespace bem {
@@ -310,9 +312,138 @@ __global__ void __launch_bounds__(256, 3) bayes_depthwise3_kernel(const BemBayes
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Shared-memory form (W % 4 == 0): the register kernel above is bound by global-load latency (72 % long-scoreboard
+// stalls). Here a CTA owns R output rows of one plane (pair): the R + 2 input rows are one contiguous run of the plane,
+// fetched by ONE TMA bulk copy per plane while the other CTAs of the SM compute (4 CTAs x 48 KB in flight per SM);
+// threads then read rows with LDS.128, take the two halo columns from their warp neighbours by shuffle, and store
+// float4 rows. One thread = 4 columns x DWS_RPT rows.
+// ------------------------------------------------------------------------------------------------
+constexpr int DWS_RPT = 4;
+
+template <int ACT>
+__global__ void __launch_bounds__(512) bayes_depthwise3_smem_kernel(const BemBayesDepthwiseParams p, const int R) {
+    constexpr int NP = ACT == 2 ? 2 : 1;
+    extern __shared__ __align__(128) unsigned char dsm[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(dsm);
+    float* tile = reinterpret_cast<float*>(dsm + 128);            // [NP][R + 2][W]
+    const int Cout = ACT == 2 ? p.C / 2 : p.C;
+    const int W = p.W, W4 = W >> 2, H = p.H;
+    const int plane = blockIdx.x, img = plane / Cout, c = plane - img * Cout;
+    const int s = p.n_samples > 1 ? img / (p.batch / p.n_samples) : 0;
+    const int h0 = blockIdx.y * R;
+    const int rows_out = min(R, H - h0);
+    const int lo = max(h0 - 1, 0), hi = min(h0 + rows_out, H - 1);      // input rows [lo, hi] exist
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int plane_elems = (R + 2) * W;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t bytes = (uint32_t)(hi - lo + 1) * W * 4;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes * NP) : "memory");
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const float* src = p.x + (((int64_t)img * p.C + c + q * Cout) * H + lo) * W;
+            float* dstp = tile + q * plane_elems + (lo - (h0 - 1)) * W;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(dstp)), "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+        }
+    }
+    // rows above / below the image are zero (disjoint from what the copies write)
+    if (h0 == 0)
+        for (int i = tid; i < NP * W; i += blockDim.x) tile[(i / W) * plane_elems + (i % W)] = 0.f;
+    for (int r = hi + 1; r <= h0 + R; ++r)
+        for (int i = tid; i < NP * W; i += blockDim.x) tile[(i / W) * plane_elems + (r - (h0 - 1)) * W + (i % W)] = 0.f;
+    float w[NP][9], b[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const int cc = c + q * Cout;
+        const float* wp = p.w + ((int64_t)s * p.C + cc) * 9;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) w[q][i] = wp[i];
+        b[q] = p.bias ? p.bias[(int64_t)s * p.C + cc] : 0.f;
+    }
+    __syncthreads();
+    {
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0,1,0,p;\n}"
+                         : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+    }
+    const int rs = tid / W4, cg = tid - rs * W4;                 // row split, column group
+    const bool active = rs * DWS_RPT < rows_out;
+    const int w0 = cg * 4;
+    const int r0 = min(rs * DWS_RPT, R - DWS_RPT);               // first local output row (inactive threads: any valid row)
+    float acc[NP][DWS_RPT][4];
+#pragma unroll
+    for (int q = 0; q < NP; ++q)
+#pragma unroll
+        for (int i = 0; i < DWS_RPT; ++i)
+#pragma unroll
+            for (int o = 0; o < 4; ++o) acc[q][i][o] = b[q];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const float* tp = tile + q * plane_elems + r0 * W + w0;  // local input row r0 = image row h0 + r0 - 1
+#pragma unroll
+        for (int j = 0; j < DWS_RPT + 2; ++j) {
+            const float4 v = *reinterpret_cast<const float4*>(tp + j * W);
+            float l = __shfl_up_sync(0xffffffffu, v.w, 1), rr = __shfl_down_sync(0xffffffffu, v.x, 1);
+            if (lane == 0 || cg == 0) l = cg > 0 ? tp[j * W - 1] : 0.f;
+            if (lane == 31 || cg == W4 - 1) rr = cg < W4 - 1 ? tp[j * W + 4] : 0.f;
+            const float x6[6] = {l, v.x, v.y, v.z, v.w, rr};
+#pragma unroll
+            for (int i = 0; i < DWS_RPT; ++i) {
+                const int k = j - i;                              // tap row of output row i fed by input row j
+                if (k >= 0 && k < 3) {
+#pragma unroll
+                    for (int o = 0; o < 4; ++o)
+#pragma unroll
+                        for (int t = 0; t < 3; ++t) acc[q][i][o] = fmaf(w[q][k * 3 + t], x6[o + t], acc[q][i][o]);
+                }
+            }
+        }
+    }
+    if (!active) return;
+    float* out = p.out + ((int64_t)plane * H + h0 + r0) * W + w0;
+#pragma unroll
+    for (int i = 0; i < DWS_RPT; ++i) {
+        if (r0 + i >= rows_out) break;
+        float y[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            if (ACT == 1) y[o] = silu_f(acc[0][i][o]);
+            else if (ACT == 2) y[o] = gelu_f(acc[0][i][o]) * acc[NP - 1][i][o];
+            else y[o] = acc[0][i][o];
+        }
+        *reinterpret_cast<float4*>(out + (int64_t)i * W) = make_float4(y[0], y[1], y[2], y[3]);
+    }
+}
+
 template <int ACT>
 static void depthwise_launch(const BemBayesDepthwiseParams& p, dim3 grid, cudaStream_t stream) {
     const bool vec = (p.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.out)) & 15) == 0;
+    static const int no_smem = getenv("BEM_DW_REG") ? atoi(getenv("BEM_DW_REG")) : 0;
+    if (vec && !no_smem) {
+        // rows per CTA: 16 if the tile stays within ~48 KB, else 8; threads = column groups x row splits
+        constexpr int NP = ACT == 2 ? 2 : 1;
+        const int W4 = p.W / 4;
+        int R = 16;
+        if (NP * (R + 2) * p.W * 4 > 56 * 1024 || W4 * (R / DWS_RPT) > 512) R = 8;
+        const int threads = (W4 * (R / DWS_RPT) + 31) / 32 * 32;
+        const int smem = 128 + NP * (R + 2) * p.W * 4;
+        if (threads <= 512 && smem <= 100 * 1024 && p.H >= 1) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            static int attr[64] = {0};
+            if (attr[dev & 63] < smem) {
+                cudaFuncSetAttribute(bayes_depthwise3_smem_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+                attr[dev & 63] = 100 * 1024;
+            }
+            dim3 g2(grid.x, (unsigned)((p.H + R - 1) / R));
+            bayes_depthwise3_smem_kernel<ACT><<<g2, threads, smem, stream>>>(p, R);
+            return;
+        }
+    }
     if (vec) bayes_depthwise3_kernel<ACT, true><<<grid, 256, 0, stream>>>(p);
     else bayes_depthwise3_kernel<ACT, false><<<grid, 256, 0, stream>>>(p);
 }
