@@ -27,13 +27,20 @@ class Conv2d(nn.Conv2d):
     kernel as the Bayesian 1x1 layers (one weight set, no sampling) when no gradient is needed; everything else is the
     library convolution."""
 
-    def forward(self, x):
-        if (self.kernel_size == (1, 1) and self.stride == (1, 1) and self.padding == (0, 0) and self.groups == 1
-                and x.is_cuda and x.dtype == torch.float32 and self.weight.dtype == torch.float32
+    def _is_1x1(self):
+        return self.kernel_size == (1, 1) and self.stride == (1, 1) and self.padding == (0, 0) and self.groups == 1
+
+    def _fuses_norm(self):
+        return self._is_1x1()
+
+    def forward(self, x, pre_norm=None):
+        """pre_norm: a LayerNorm2d that precedes the conv (PatchMerging, UNet_arch.py:80-82), fused when the kernel runs"""
+        if (self._is_1x1() and x.is_cuda and x.dtype == torch.float32 and self.weight.dtype == torch.float32
                 and not (torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad))):
             w = self.weight.view(1, self.out_channels, self.in_channels)
-            return BF.pointwise_conv(x, w, None if self.bias is None else self.bias.view(1, -1), 1)
-        return super().forward(x)
+            ln = None if pre_norm is None else (pre_norm.weight, pre_norm.bias, pre_norm.eps)
+            return BF.pointwise_conv(x, w, None if self.bias is None else self.bias.view(1, -1), 1, ln=ln)
+        return super().forward(x if pre_norm is None else pre_norm(x))
 
 
 class gdMlp(nn.Module):
@@ -94,7 +101,7 @@ class PatchMerging(nn.Module):
 
     def forward(self, x):
         x = torch.cat([x[:, :, 0::2, 0::2], x[:, :, 1::2, 0::2], x[:, :, 0::2, 1::2], x[:, :, 1::2, 1::2]], 1)
-        return self.reduction(self.norm(x))
+        return apply_1x1(self.reduction, x, self.norm)
 
 
 class DualUpSample(nn.Module):

@@ -145,6 +145,56 @@ def main_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def scan_rooflines(dev, peak, reps=20):
+    """Level-0 selective scan of the workload (B1, K*D = 160, N = 1, L = 240000, fp32), forward and backward, each C-ABI
+    call (descriptor memset + kernel) captured as a CUDA graph and replayed back to back (the working set of one launch is
+    4-6x the L2, so every replay starts with none of its inputs cached); CUDA events on the replaying stream. Algorithmic bytes: SURVEY 8(d) / DESIGN 3.1-3.2."""
+    import torch
+    from bem_b200 import selective_scan as ss
+    Bn, KD, G, N, L = 1, 160, 4, 1, H_IMG * W_IMG
+    g = torch.Generator(device="cpu").manual_seed(1)
+    u = torch.randn(Bn, KD, L, generator=g).to(dev)
+    delta = (0.5 * torch.randn(Bn, KD, L, generator=g)).to(dev)
+    A = -torch.rand(KD, N, generator=g).to(dev) - 0.5
+    Bm = torch.randn(Bn, G, N, L, generator=g).to(dev)
+    Cm = torch.randn(Bn, G, N, L, generator=g).to(dev)
+    D = torch.randn(KD, generator=g).to(dev)
+    bias = torch.randn(KD, generator=g).to(dev)
+    dout = torch.randn(Bn, KD, L, generator=g).to(dev)
+    out, x = ss.fwd(u, delta, A, Bm, Cm, D, bias, True, 1, True)
+
+    def timed(fn):
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            fn()
+        ts = []
+        for _ in range(reps):   # no explicit flush: one launch streams 468 / 783 MB, 4-6x the 126 MB L2
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gr.replay()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1))
+        return sum(ts) / len(ts)
+
+    res = {}
+    s_in, s_o = 4, 4
+    fwd_bytes = Bn * KD * L * (2 * s_in + s_o) + 2 * Bn * G * N * L * s_in
+    bwd_bytes = Bn * KD * L * (4 * s_in + s_o) + 4 * Bn * G * N * L * s_in
+    for name, fn, nbytes in (("fwd", lambda: ss.fwd(u, delta, A, Bm, Cm, D, bias, True, 1, True), fwd_bytes),
+                             ("bwd", lambda: ss.bwd(u, delta, A, Bm, Cm, D, bias, dout, x, True, 1), bwd_bytes)):
+        ms = timed(fn)
+        ach = nbytes / (ms * 1e-3) / 1e9
+        res[name] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "bytes_per_launch": float(nbytes), "ms_per_launch": ms, "launches_timed": reps}
+    return res
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
@@ -245,17 +295,15 @@ def main_ours(args):
         return
 
     peak, peak_src = measured_peaks()
-    # dominant hot-path kernel: the level-0 scan forward (largest traffic per launch)
-    roof = None
-    scan = prof.get("scan_fwd")
-    if scan:
-        key, rec = max(scan["by_key"].items(), key=lambda kv: kv[1]["bytes"] / max(kv[1]["calls"], 1))
-        per_launch_bytes = rec["bytes"] / rec["calls"]
-        per_launch_ms = rec["ms"] / rec["calls"]
-        ach = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "scan_fwd_kernel<float,float,24,8,N1> " + key, "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                "bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms, "launches_timed": rec["calls"]}
+    # dominant kernel of the hot path: the level-0 scan forward (largest traffic per launch of the section-8 rows)
+    sr = scan_rooflines(dev, peak)
+    roof = dict(sr["fwd"], kernel="scan_fwd_kernel<float,float,24,8,N1> (B1, KD160, N1, L240000, fp32)", peak_source=peak_src,
+                timing="one C-ABI call (descriptor memset + kernel) per CUDA-graph replay, CUDA events; working set 468 MB >> 126 MB L2")
+    eager_fwd = prof.get("scan_fwd")
+    if eager_fwd:   # the same launches as they ran inside the eager per-kernel pass (adds host launch gaps)
+        key, rec = max(eager_fwd["by_key"].items(), key=lambda kv: kv[1]["bytes"] / max(kv[1]["calls"], 1))
+        roof["eager_ms_per_launch"] = rec["ms"] / rec["calls"]
+    roof_bwd = dict(sr["bwd"], kernel="scan_bwd_kernel<float,float,12,8,N1> (same shape)", peak_source=peak_src)
     shares = {k: {"calls": v["calls"], "ms_per_step": v["ms"] / prof_steps,
                   "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None} for k, v in prof.items()}
     line = {"metric": METRIC, "value": world * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -267,7 +315,7 @@ def main_ours(args):
                        "execution": "eager launches" if args.no_graph else "CUDA graph replay of one sample's forward"},
             "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": img_host.numel() * 4,
                     "d2h_bytes_per_step": out_host.numel() * 4},
-            "gpu_launches": launches, "clocks": clk, "roofline": roof, "kernels": shares, "job": job}
+            "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_scan_bwd": roof_bwd, "kernels": shares, "job": job}
     if not args.no_cpu_baseline and world == 1:
         try:
             r = cpu_reference_run(2, 0, budget_s=25.0)
