@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libbem_b200.so")
 
 BEM_F32, BEM_F16, BEM_BF16 = 0, 1, 2
 BEM_OK, BEM_ERR_BAD_ARG, BEM_ERR_WORKSPACE, BEM_ERR_UNSUPPORTED = 0, 10001, 10002, 10003
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 i32, i64, u64, vp = C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
 
@@ -136,7 +136,7 @@ def workspace(device: torch.device, nbytes: int, kind: str = "scan") -> torch.Te
     key = (kind, device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)   # scan kernels need a zero-filled first use
         _workspaces[key] = ws
     return ws
 

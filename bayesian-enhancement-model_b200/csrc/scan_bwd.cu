@@ -58,6 +58,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
         const int ST = p.ST;
         const int GRS = p.G * p.RS;
         constexpr int kMaxSc = (NW * (2 * kMaxDstate + 2) + 31) / 32;
+        // launch epoch of the descriptors: read before this CTA's first draw (the last drawer of the launch bumps it)
+        const uint32_t epoch = *reinterpret_cast<volatile unsigned int*>(p.ticket + 2);
         unsigned int t = 0;
         if (lane == 0) t = atomicAdd(p.ticket, 1u);
         t = __shfl_sync(FULL, t, 0);
@@ -69,6 +71,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                 if (lane == 0) {
                     reinterpret_cast<TileCoord*>(smem + (size_t)s * stage_bytes)->nrows = -1;
                     mbar_arrive(&full[s]);
+                    // the last failing draw of the launch re-arms the workspace (see scan_fwd.cu)
+                    if (t == (unsigned)p.total_tiles + gridDim.x - 1) {
+                        p.ticket[2] = (epoch + 1) & 0x3fffffffu;
+                        p.ticket[0] = 0u;
+                    }
                 }
                 break;
             }
@@ -96,6 +103,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                 tc.len = len;
                 tc.aux0 = j;
                 tc.aux1 = (j == p.RBS - 1) ? 1 : 0;
+                tc.epoch = epoch;
                 // per-row scalars, requested before blocking on the slot
                 float scv[kMaxSc];
 #pragma unroll
@@ -206,6 +214,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
         mbar_wait(&full[s], phase, p.err);
         unsigned char* st = smem + (size_t)s * stage_bytes;
         const TileCoord tc = *reinterpret_cast<const TileCoord*>(st);
+        const uint32_t ep = tc.epoch;
         if (tc.nrows < 0) break;
         const int c = tc.c, b = tc.b, g = tc.g;
         const int j = tc.aux0;
@@ -315,14 +324,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                     Rs = 0.f;
                 }
                 const float Pa = __shfl_sync(FULL, Pr, 0), Ra = __shfl_sync(FULL, Rr, 0);
-                if (lane == 0 && plan.publish_agg) st_desc(aggrow + c, Pa, Ra, DESC_READY);
+                if (lane == 0 && plan.publish_agg) st_desc(aggrow + c, Pa, Ra, desc_tag(ep, DESC_READY));
                 float r_in = 0.f, Psuf = 1.f;
                 if (plan.nlanes) {
-                    const float2 suf = lookback_finish(lb_addr, lb_first, plan.nlanes, lane, p.err);
+                    const float2 suf = lookback_finish(lb_addr, lb_first, plan.nlanes, lane, p.err, ep);
                     Psuf = suf.x;
                     r_in = suf.y;
                 }
-                if (lane == 0 && plan.publish_incl) st_desc(inclrow + c, Pa * Psuf, fmaf(Pa, r_in, Ra), DESC_READY);
+                if (lane == 0 && plan.publish_incl) st_desc(inclrow + c, Pa * Psuf, fmaf(Pa, r_in, Ra), desc_tag(ep, DESC_READY));
                 const float rin_t = fmaf(Ps, r_in, Rs);   // adjoint entering this lane's last position
                 // outputs, one 128-bit vector of T at a time; dB / dC contributions go to this warp's rows of `red`
                 float* accB = red + warp * CL + e0;
@@ -450,7 +459,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                 }
                 uint4* aggrow = p.desc + (row * nt) * N;
                 uint4* inclrow = p.desc_incl + (row * nt) * N;
-                if (lane < N && plan.publish_agg) st_desc(aggrow + (int64_t)c * N + lane, aggP, aggR, DESC_READY);
+                if (lane < N && plan.publish_agg) st_desc(aggrow + (int64_t)c * N + lane, aggP, aggR, desc_tag(ep, DESC_READY));
                 float sufP = 1.f, sufR = 0.f;
                 if (plan.nlanes) {
                     for (int n0 = 0; n0 < N; n0 += 4) {   // four states' descriptors in flight at a time
@@ -464,7 +473,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             if (n0 + q < N) {
-                                const float2 suf = lookback_finish(addr[q], first[q], plan.nlanes, lane, p.err);
+                                const float2 suf = lookback_finish(addr[q], first[q], plan.nlanes, lane, p.err, ep);
                                 if (lane == n0 + q) {
                                     sufP = suf.x;
                                     sufR = suf.y;
@@ -473,7 +482,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                         }
                     }
                 }
-                if (lane < N && plan.publish_incl) st_desc(inclrow + (int64_t)c * N + lane, aggP * sufP, fmaf(aggP, sufR, aggR), DESC_READY);
+                if (lane < N && plan.publish_incl) st_desc(inclrow + (int64_t)c * N + lane, aggP * sufP, fmaf(aggP, sufR, aggR), desc_tag(ep, DESC_READY));
                 // pass 2: per state, forward states from the carry, reverse adjoints from the look-back
                 for (int n = 0; n < N; ++n) {
                     const float Av = sc[n];
@@ -671,8 +680,6 @@ static int launch_bwd(ScanBwdArgs& a, int sm_count, cudaStream_t stream) {
     }
     const int64_t ndesc = (int64_t)a.batch * a.dim * a.nchunks * a.N;
     a.desc_incl = a.desc + ndesc;
-    cudaError_t me = cudaMemsetAsync(a.ticket, 0, (size_t)(kWsHeader + 2 * ndesc * 16), stream);
-    if (me != cudaSuccess) return (int)me;
     const int grid = min(a.total_tiles, sm_count * ctas_per_sm);
     kernel<<<grid, (NW + 1) * 32, smem_bytes, stream>>>(a);
     return (int)cudaGetLastError();

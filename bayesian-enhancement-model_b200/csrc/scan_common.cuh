@@ -230,8 +230,12 @@ __device__ __forceinline__ void warp_scan_rev(float& P, float& V, int lane) {
     }
 }
 
-// Descriptor status
+// Descriptor status. The status word carries the launch epoch (workspace header word 2, incremented by the last ticket
+// drawer of every launch): a descriptor is valid only if it was written by THIS launch, so the workspace never has to
+// be cleared between launches (a ~1.6 MB memset node per scan otherwise) — it is zero-filled once by its owner.
 enum : uint32_t { DESC_EMPTY = 0, DESC_READY = 1 };
+__device__ __forceinline__ uint32_t desc_tag(uint32_t epoch, uint32_t kind) { return (epoch << 2) | kind; }
+__device__ __forceinline__ uint32_t desc_kind(uint32_t word, uint32_t epoch) { return (word >> 2) == (epoch & 0x3fffffffu) ? (word & 3u) : DESC_EMPTY; }
 constexpr int kAnchor = 16;   // every kAnchor-th tile of a row also publishes its INCLUSIVE composition
 
 // Deterministic decoupled look-back.
@@ -273,16 +277,16 @@ __device__ __forceinline__ uint4 lookback_prefetch(const uint4* addr) {
     return addr ? ld_desc(addr) : make_uint4(0u, 0u, DESC_READY, 0u);
 }
 // `first` is the result of an early lookback_prefetch of this lane's descriptor (issued before the tile's arithmetic).
-__device__ __forceinline__ float2 lookback_finish(const uint4* addr, uint4 first, int nlanes, int lane, unsigned int* err) {
+__device__ __forceinline__ float2 lookback_finish(const uint4* addr, uint4 first, int nlanes, int lane, unsigned int* err, uint32_t epoch) {
     uint4 v = first;
     // warp-convergent poll: one instruction stream for the whole warp, only the lanes still waiting reload
     // (per-lane spin loops would diverge into up to 31 independent loops that hog the scheduler's issue slots)
-    bool pending = addr != nullptr && v.z == DESC_EMPTY;
+    bool pending = addr != nullptr && desc_kind(v.z, epoch) == DESC_EMPTY;
     int spins = 0;
     while (__any_sync(FULL, pending)) {
         if (pending) {
             v = ld_desc(addr);
-            pending = v.z == DESC_EMPTY;
+            pending = desc_kind(v.z, epoch) == DESC_EMPTY;
         }
         if (++spins > 16) __nanosleep(64);
         if (spins > (1 << 22)) {   // watchdog, see mbar_wait
@@ -312,7 +316,7 @@ __device__ __forceinline__ float2 lookback_finish(const uint4* addr, uint4 first
 // Classic (timing-dependent) decoupled look-back, kept for A/B measurements: walks back over windows of 32 tiles and
 // stops at the first tile that has published an inclusive value. `agg0` holds status 1 = aggregate, 2 = inclusive.
 __device__ __forceinline__ float2 lookback_dynamic(const uint4* desc0, int64_t dstride, int c, int nchunks, int step, int lane,
-                                                   unsigned int* err) {
+                                                   unsigned int* err, uint32_t epoch) {
     float runP = 1.f, runV = 0.f;
     int j = c + step;
     while (true) {
@@ -326,7 +330,7 @@ __device__ __forceinline__ float2 lookback_dynamic(const uint4* desc0, int64_t d
         while (true) {
             if (inside && st == 0u) {
                 const uint4 v = ld_desc(desc0 + (int64_t)idx * dstride);
-                st = v.z;
+                st = desc_kind(v.z, epoch);
                 P = __uint_as_float(v.x);
                 V = __uint_as_float(v.y);
             }
@@ -372,6 +376,7 @@ struct TileCoord {
     int nrows;   // rows in this step (<= NW); < 0 marks the end of work
     int len;     // valid positions in this tile
     int aux0, aux1;
+    uint32_t epoch;   // launch epoch of the look-back descriptors (see desc_tag)
 };
 
 }  // namespace bem

@@ -60,6 +60,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
         const int RT = p.RT;
         const int GRB = p.G * p.RB;
         constexpr int kMaxSc = (NW * (kMaxDstate + 2) + 31) / 32;   // scalars per lane
+        // launch epoch of the descriptors: read before this CTA's first draw (the last drawer of the launch bumps it)
+        const uint32_t epoch = *reinterpret_cast<volatile unsigned int*>(p.ticket + 2);
         unsigned int t = 0;
         if (lane == 0) t = atomicAdd(p.ticket, 1u);
         t = __shfl_sync(FULL, t, 0);
@@ -73,6 +75,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
                 if (lane == 0) {
                     hdr->nrows = -1;
                     mbar_arrive(&full[s]);
+                    // every CTA ends with exactly one failing draw: the last of them re-arms the workspace for the next
+                    // launch (ticket back to zero, new descriptor epoch) — nobody draws after it
+                    if (t == (unsigned)p.total_tiles + gridDim.x - 1) {
+                        p.ticket[2] = (epoch + 1) & 0x3fffffffu;
+                        p.ticket[0] = 0u;
+                    }
                 }
                 break;
             }
@@ -87,6 +95,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
             const int l0 = tc.c * CL;
             tc.len = min(CL, p.L - l0);
             tc.aux0 = tc.aux1 = 0;
+            tc.epoch = epoch;
             const int len = tc.len;
             // per-row scalars A[0..N), D, bias: loads issued now, stored after the slot is free
             float scv[kMaxSc];
@@ -179,6 +188,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
         mbar_wait(&full[s], phase, p.err);
         unsigned char* st = smem + (size_t)s * stage_bytes;
         const TileCoord tc = *reinterpret_cast<const TileCoord*>(st);
+        const uint32_t ep = tc.epoch;
         if (tc.nrows < 0) break;
         const bool active = warp < tc.nrows;
         if (active) {
@@ -243,20 +253,20 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
                 if (p.lb_dynamic == 2) {   // timing experiment only: no cross-tile dependency at all (WRONG results)
                 } else if (p.lb_dynamic) {   // A/B: classic look-back (timing-dependent association)
                     if (c > 0) {
-                        if (lane == 0 && c + 1 < nt) st_desc(aggrow + c, Pa, Va, 1u);
-                            const float2 pre = lookback_dynamic(aggrow, 1, c, nt, -1, lane, p.err);
+                        if (lane == 0 && c + 1 < nt) st_desc(aggrow + c, Pa, Va, desc_tag(ep, 1u));
+                            const float2 pre = lookback_dynamic(aggrow, 1, c, nt, -1, lane, p.err, ep);
                         Pp = pre.x;
                         hp = pre.y;
                     }
-                    if (lane == 0 && c + 1 < nt) st_desc(aggrow + c, Pp * Pa, fmaf(Pa, hp, Va), 2u);
+                    if (lane == 0 && c + 1 < nt) st_desc(aggrow + c, Pp * Pa, fmaf(Pa, hp, Va), desc_tag(ep, 2u));
                 } else {
-                    if (lane == 0 && plan.publish_agg) st_desc(aggrow + c, Pa, Va, DESC_READY);
+                    if (lane == 0 && plan.publish_agg) st_desc(aggrow + c, Pa, Va, desc_tag(ep, DESC_READY));
                     if (plan.nlanes) {
-                        const float2 pre = lookback_finish(lb_addr, lb_first, plan.nlanes, lane, p.err);
+                        const float2 pre = lookback_finish(lb_addr, lb_first, plan.nlanes, lane, p.err, ep);
                         Pp = pre.x;
                         hp = pre.y;
                     }
-                    if (lane == 0 && plan.publish_incl) st_desc(inclrow + c, Pp * Pa, fmaf(Pa, hp, Va), DESC_READY);
+                    if (lane == 0 && plan.publish_incl) st_desc(inclrow + c, Pp * Pa, fmaf(Pa, hp, Va), desc_tag(ep, DESC_READY));
                 }
                 if (p.x) {
                     // carries: state and running decay at the end of every kCarry chunk of this tile
@@ -321,7 +331,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
                 }
                 uint4* aggrow = p.desc + (row * nt) * N;   // [tile][n]
                 uint4* inclrow = p.desc_incl + (row * nt) * N;
-                if (lane < N && plan.publish_agg) st_desc(aggrow + (int64_t)c * N + lane, aggP, aggV, DESC_READY);
+                if (lane < N && plan.publish_agg) st_desc(aggrow + (int64_t)c * N + lane, aggP, aggV, desc_tag(ep, DESC_READY));
                 float preP = 1.f, preV = 0.f;   // lane n: composition of tiles < c for state n
                 if (plan.nlanes) {
                     for (int n0 = 0; n0 < N; n0 += 4) {   // four states' descriptors in flight at a time
@@ -335,7 +345,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             if (n0 + q < N) {
-                                const float2 pre = lookback_finish(addr[q], first[q], plan.nlanes, lane, p.err);
+                                const float2 pre = lookback_finish(addr[q], first[q], plan.nlanes, lane, p.err, ep);
                                 if (lane == n0 + q) {
                                     preP = pre.x;
                                     preV = pre.y;
@@ -346,7 +356,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
                 }
                 if (lane < N) {
                     const float Pi = preP * aggP, hi = fmaf(aggP, preV, aggV);
-                    if (plan.publish_incl) st_desc(inclrow + (int64_t)c * N + lane, Pi, hi, DESC_READY);
+                    if (plan.publish_incl) st_desc(inclrow + (int64_t)c * N + lane, Pi, hi, desc_tag(ep, DESC_READY));
                     if (p.x) {
                         float2* xr = reinterpret_cast<float2*>(p.x) + (row * p.nxchunks + c) * N + lane;
                         *xr = make_float2(Pi, hi);
@@ -430,9 +440,6 @@ static int launch_fwd(ScanFwdArgs a, int sm_count, cudaStream_t stream) {
     a.total_tiles = (int)total;
     const int64_t ndesc = (int64_t)a.batch * a.dim * a.nchunks * a.N;
     a.desc_incl = a.desc + ndesc;
-    // zero the ticket / error word and exactly the descriptors this launch will use
-    cudaError_t me = cudaMemsetAsync(a.ticket, 0, (size_t)(kWsHeader + 2 * ndesc * 16), stream);
-    if (me != cudaSuccess) return (int)me;
     const int hdr_bytes = 128 + ((NW * (a.N + 2) * 4 + 127) / 128) * 128;
     const int stage_bytes = hdr_bytes + NW * 2 * CL * (int)sizeof(T) + 2 * a.N * CL * (int)sizeof(T);
     // two resident CTAs per SM when two stages fit in half of the shared memory, else one CTA with a deeper ring

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define BEM_ABI_VERSION 4
+#define BEM_ABI_VERSION 5
 
 /* element types of u/delta/B/C/x-activations */
 enum { BEM_F32 = 0, BEM_F16 = 1, BEM_BF16 = 2 };
@@ -55,7 +55,10 @@ const char* bem_error_string(int code);
  *              so `last_state = x[:, :, -1, 1::2]` holds exactly as in
  *              kernels/selective_scan/test_selective_scan.py:79. The reference fixes the chunk at 2048;
  *              here the chunk length depends on the element type (the tensor is opaque to callers).
- *   workspace: bem_scan_workspace_bytes() bytes, 16-byte aligned; contents are scratch (zeroed by the call)
+ *   workspace: bem_scan_workspace_bytes() bytes, 16-byte aligned, ZERO-FILLED BY THE CALLER BEFORE ITS FIRST USE and
+ *              from then on owned by the scan entry points of one stream (they re-arm it at the end of every launch:
+ *              ticket counter back to zero, descriptor epoch advanced — no per-launch clearing, which keeps a launch a
+ *              single kernel node under CUDA-graph capture). Word 1 is a sticky watchdog flag (0 = clean).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct BemScanFwdParams {
     int32_t batch, dim, seqlen, dstate, n_groups;

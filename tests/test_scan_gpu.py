@@ -255,3 +255,50 @@ def test_forward_is_bit_reproducible(cfg):
         out, x = bem.selective_scan_cuda_oflex.fwd(*args)
         assert torch.equal(out, out0) and torch.equal(x, x0)
     assert bem._lib.scan_error_word(inp["u"].device) == 0
+
+
+def test_scan_workspace_rearms_itself_across_launches_and_graph_replays():
+    """The look-back workspace is never cleared between launches (descriptor epoch + ticket re-armed by the kernel): back to
+    back launches of different shapes on one workspace, and replays of a captured CUDA graph (identical kernel arguments
+    every time), must all give the result of a fresh launch, bit for bit, forward and backward."""
+    import bem_b200
+    from bem_b200 import selective_scan as ss
+    torch.manual_seed(5)
+    dev = "cuda"
+
+    def mk(Bn, KD, L, N=1, G=2):
+        u = torch.randn(Bn, KD, L, device=dev)
+        dl = 0.5 * torch.randn(Bn, KD, L, device=dev)
+        A = -torch.rand(KD, N, device=dev) - 0.2
+        Bm = torch.randn(Bn, G, N, L, device=dev)
+        Cm = torch.randn(Bn, G, N, L, device=dev)
+        D = torch.randn(KD, device=dev)
+        bias = torch.randn(KD, device=dev)
+        return u, dl, A, Bm, Cm, D, bias
+
+    big, small = mk(1, 16, 20000), mk(2, 8, 3000)
+    ref_big = ss.fwd(*big, True, 1, True)
+    ref_small = ss.fwd(*small, True, 1, True)
+    for _ in range(3):   # alternate shapes: every launch sees the other shape's stale descriptors
+        a = ss.fwd(*small, True, 1, True)
+        b = ss.fwd(*big, True, 1, True)
+        assert torch.equal(a[0], ref_small[0]) and torch.equal(b[0], ref_big[0]) and torch.equal(b[1], ref_big[1])
+    dout = torch.randn_like(ref_big[0])
+    ref_bwd = ss.bwd(*big, dout, ref_big[1], True, 1)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ss.fwd(*big, True, 1, True)
+        ss.bwd(*big, dout, ref_big[1], True, 1)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out_g = ss.fwd(*big, True, 1, True)
+        bwd_g = ss.bwd(*big, dout, out_g[1], True, 1)
+    for _ in range(4):
+        out_g[0].zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out_g[0], ref_big[0])
+        assert torch.equal(bwd_g[0], ref_bwd[0]) and torch.equal(bwd_g[1], ref_bwd[1])
+    assert bem_b200._lib.scan_error_word(torch.device("cuda", torch.cuda.current_device())) == 0
