@@ -318,7 +318,14 @@ def main_ours(args):
         key, rec = max(eager_fwd["by_key"].items(), key=lambda kv: kv[1]["bytes"] / max(kv[1]["calls"], 1))
         roof["eager_ms_per_launch"] = rec["ms"] / rec["calls"]
     roof_bwd = dict(sr["bwd"], kernel="scan_bwd_kernel<float,float,12,8,N1> (same shape)", peak_source=peak_src)
-    roof_pw = dict(sr["pointwise"], kernel="bayes_weight_pack_kernel + bayes_pointwise_tc3_kernel<LN> (40 -> 320 ch, 240000 px, fp32 via 3xTF32)",
+    try:   # DRAM traffic per launch from the committed ncu capture of the same kernels and shapes
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as f:
+            tr = json.load(f)
+        roof["traffic"], roof_bwd["traffic"] = tr.get("scan_fwd_L0"), tr.get("scan_bwd_L0")
+        roof["traffic_source"] = roof_bwd["traffic_source"] = "profiles/r01_traffic.json (ncu --set full)"
+    except (OSError, ValueError):
+        tr = {}
+    roof_pw = dict(sr["pointwise"], traffic=tr.get("pointwise_40_320_ln_L0"), kernel="bayes_weight_pack_kernel + bayes_pointwise_tc3_kernel<LN> (40 -> 320 ch, 240000 px, fp32 via 3xTF32)",
                    peak_source=peak_src)
     shares = {k: {"calls": v["calls"], "ms_per_step": v["ms"] / prof_steps,
                   "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None} for k, v in prof.items()}

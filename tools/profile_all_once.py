@@ -1,0 +1,44 @@
+"""One pass over the hot-path kernels at their level-0 (600x400) shapes, each launched twice (the second launch is the one
+to read in an ncu capture): `ncu --set full -k regex:'scan_|pointwise_tc3|depthwise3|csm_' python tools/profile_all_once.py`."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bem_b200  # noqa: E402
+from bem_b200 import csm  # noqa: E402
+from bem_b200.bayesian import functional as BF  # noqa: E402
+
+dev = torch.device("cuda")
+torch.manual_seed(0)
+H, W = 400, 600
+L = H * W
+KD, N, G = 160, 1, 4
+u = torch.randn(1, KD, L, device=dev)
+delta = 0.5 * torch.rand(1, KD, L, device=dev)
+A = -0.5 * torch.rand(KD, N, device=dev)
+Bm = torch.randn(1, G, N, L, device=dev)
+Cm = torch.randn(1, G, N, L, device=dev)
+D = torch.randn(KD, device=dev)
+bias = 0.5 * torch.rand(KD, device=dev)
+dout = torch.randn(1, KD, L, device=dev)
+ext = bem_b200.selective_scan_cuda_oflex
+x40 = torch.randn(1, 40, H, W, device=dev)
+x160 = torch.randn(1, 160, H, W, device=dev)
+x320 = torch.randn(1, 320, H, W, device=dev)
+ln40 = (torch.ones(40, device=dev), torch.zeros(40, device=dev), 1e-5)
+w = lambda co, ci: torch.randn(1, co, ci, device=dev) / ci ** 0.5
+for rep in range(2):
+    out, xc = ext.fwd(u, delta, A, Bm, Cm, D, bias, True, 1, True)
+    ext.bwd(u, delta, A, Bm, Cm, D, bias, dout, xc, True, 1)
+    BF.pointwise_conv(x40, w(320, 40), torch.randn(1, 320, device=dev), 1, ln=ln40)          # gdMlp.project_in
+    BF.pointwise_conv(x160, w(40, 160), torch.randn(1, 40, device=dev), 1, residual=x40)     # gdMlp.project_out + skip
+    BF.pointwise_conv(x40, w(40, 40), None, 1, ln=ln40)                                        # SS2D.in_proj
+    BF.depthwise_conv3x3(x320, torch.randn(1, 320, 3, 3, device=dev), torch.randn(1, 320, device=dev), 1, act="gelu_gate")
+    BF.depthwise_conv3x3(x40, torch.randn(1, 40, 3, 3, device=dev), torch.randn(1, 40, device=dev), 1, act="silu")
+    xs = csm.cross_scan_fn(x40, True, True, 0)
+    csm.cross_merge_fn(xs.view(1, 4, 40, H, W), True, True, 0)
+torch.cuda.synchronize()
+print("done")
