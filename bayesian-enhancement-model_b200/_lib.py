@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libbem_b200.so")
 
 BEM_F32, BEM_F16, BEM_BF16 = 0, 1, 2
 BEM_OK, BEM_ERR_BAD_ARG, BEM_ERR_WORKSPACE, BEM_ERR_UNSUPPORTED = 0, 10001, 10002, 10003
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 i32, i64, u64, vp = C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
 
@@ -22,7 +22,7 @@ class BemScanFwdParams(C.Structure):
                [(n, vp) for n in ("u", "delta", "A", "B", "C", "D", "delta_bias", "out", "x")] + \
                [(n, i64) for n in ("u_bs", "u_ds", "delta_bs", "delta_ds", "A_ds", "A_ns", "B_bs", "B_gs", "B_ns",
                                    "C_bs", "C_gs", "C_ns", "out_bs", "out_ds")] + \
-               [("workspace", vp), ("workspace_bytes", i64), ("residual", vp)]
+               [("workspace", vp), ("workspace_bytes", i64), ("dt_rank", i32), ("dt_weight", vp), ("delta_gs", i64)]
 
 
 class BemScanBwdParams(C.Structure):
@@ -31,7 +31,7 @@ class BemScanBwdParams(C.Structure):
                                   "dC", "dD", "ddelta_bias")] + \
                [(n, i64) for n in ("u_bs", "u_ds", "delta_bs", "delta_ds", "A_ds", "A_ns", "B_bs", "B_gs", "B_ns",
                                    "C_bs", "C_gs", "C_ns", "dout_bs", "dout_ds", "du_bs", "du_ds", "ddelta_bs", "ddelta_ds")] + \
-               [("workspace", vp), ("workspace_bytes", i64), ("residual", vp)]
+               [("workspace", vp), ("workspace_bytes", i64)]
 
 
 class BemCsmParams(C.Structure):

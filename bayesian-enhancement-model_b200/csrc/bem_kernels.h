@@ -21,6 +21,8 @@ inline int scan_items(int dtype) { return dtype == BEM_F32 ? kItemsF32 : kItems1
 // workspace layout: [0,4) ticket, [4,8) error word, [128, ...) look-back descriptors (16 B each): aggregates, then inclusives
 constexpr int64_t kWsHeader = 128;
 
+constexpr int kMaxDtRank = 8;   // fused dt_proj: low-rank rows per group that fit the delta halves of a tile's row slots
+
 struct ScanFwdArgs {
     const void* u;
     const void* delta;
@@ -41,6 +43,9 @@ struct ScanFwdArgs {
     int softplus;
     int stages;
     int lb_dynamic;    // A/B knob: classic timing-dependent look-back instead of the deterministic one
+    int R;             // fused dt_proj rank (0: `delta` is given per channel row)
+    const float* dt_w; // (dim, R) dt_proj weight, row-major
+    int64_t dl_gs;     // group stride of the low-rank delta (B, G, R, L); dl_ds is then the stride between its R rows
     uint4* desc;
     uint4* desc_incl;
     unsigned int* ticket;

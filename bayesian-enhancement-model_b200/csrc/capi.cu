@@ -74,6 +74,8 @@ int bem_scan_fwd(const BemScanFwdParams* q, void* stream_) {
     a.batch = q->batch; a.dim = q->dim; a.L = q->seqlen; a.N = q->dstate; a.G = q->n_groups; a.Dg = q->dim / q->n_groups;
     a.nxchunks = (q->seqlen + CL - 1) / CL;   // carries of `x`; the tile count is set by the launcher
     a.softplus = q->delta_softplus ? 1 : 0;
+    if (q->dt_rank < 0 || (q->dt_rank > 0 && (!q->dt_weight || q->dtype != BEM_F32))) return BEM_ERR_BAD_ARG;
+    a.R = q->dt_rank; a.dt_w = q->dt_weight; a.dl_gs = q->delta_gs;
     unsigned char* ws = reinterpret_cast<unsigned char*>(q->workspace);
     a.ticket = reinterpret_cast<unsigned int*>(ws);
     a.err = reinterpret_cast<unsigned int*>(ws + 4);

@@ -21,8 +21,11 @@
 
 namespace bem {
 
-template <typename T, typename OutT, int ITEMS, int NW, bool N1>
+// RANK: fused dt_proj rank. 0 = `delta` given per channel row; > 0 = compile-time rank (the BEM ranks 3 and 5: unrolled, weights
+// in registers); -1 = rank read from the arguments (any rank <= kMaxDtRank, runtime loop).
+template <typename T, typename OutT, int ITEMS, int NW, bool N1, int RANK = 0>
 __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(const ScanFwdArgs p) {
+    constexpr bool FUSED = RANK != 0;
     constexpr int CL = 32 * ITEMS;
     constexpr bool kAcc = sizeof(T) == 4;   // fp32 inputs: full-precision decay rate (scan_common.cuh decay_m1)
     constexpr int XC = sizeof(T) == 4 ? kCarryF32 : kCarry16;   // positions per carry of `x`
@@ -35,7 +38,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
     const int N = N1 ? 1 : p.N;
     const int S = p.stages;
     const int bc_bytes = N * CL * (int)sizeof(T);
-    const int hdr_bytes = 128 + ((NW * (N + 2) * 4 + 127) / 128) * 128;   // TileCoord | per-row scalars [NW][N+2]
+    // fused dt_proj (p.R > 0): `delta` is the low-rank dt of the group, (B, G, R, L); the R rows of a tile take the delta
+    // halves of row slots 0..R-1 and every channel row forms delta = sum_r W[d][r] * dt[r] from its R weights (scalars)
+    const int R = RANK > 0 ? RANK : (RANK < 0 ? p.R : 0);
+    const int NSC = N + 2 + R;                                             // scalars per row: A[N], D, bias, W_dt[R]
+    const int hdr_bytes = 128 + ((NW * NSC * 4 + 127) / 128) * 128;       // TileCoord | per-row scalars [NW][NSC]
     const int stage_bytes = hdr_bytes + NW * ROW_SLOT + 2 * bc_bytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
     uint64_t* empty = full + S;
@@ -103,12 +110,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
             for (int q = 0; q < kMaxSc; ++q) {
                 const int i = lane + 32 * q;
                 float v = 0.f;
-                if (i < tc.nrows * (N + 2)) {
-                    const int rr = i / (N + 2), k = i - rr * (N + 2);
+                if (i < tc.nrows * NSC) {
+                    const int rr = i / NSC, k = i - rr * NSC;
                     const int64_t d = (int64_t)tc.g * p.Dg + tc.row0 + rr;
                     if (k < N) v = p.A[d * p.A_ds + k * p.A_ns];
                     else if (k == N) v = p.D ? p.D[d] : 0.f;
-                    else v = p.bias ? p.bias[d] : 0.f;
+                    else if (k == N + 1) v = p.bias ? p.bias[d] : 0.f;
+                    else v = p.dt_w[d * R + (k - N - 2)];
                 }
                 scv[q] = v;
             }
@@ -122,25 +130,27 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
 #pragma unroll
             for (int q = 0; q < kMaxSc; ++q) {
                 const int i = lane + 32 * q;
-                if (i < tc.nrows * (N + 2)) sc[i] = scv[q];
+                if (i < tc.nrows * NSC) sc[i] = scv[q];
             }
             unsigned char* rows = st + hdr_bytes;
-            // jobs: [0, nrows) u rows, [nrows, 2 nrows) delta rows, then N B rows, N C rows
-            const int njobs = 2 * tc.nrows + 2 * N;
+            // jobs: [0, nrows) u rows, then nd delta rows (one per channel row, or the group's R low-rank rows), N B rows, N C rows
+            const int nd = R > 0 ? R : tc.nrows;
+            const int njobs = tc.nrows + nd + 2 * N;
             uint32_t my_bytes = 0;
             for (int pass = 0; pass < 2; ++pass) {
                 for (int j = lane; j < njobs; j += 32) {
                     const T* src;
                     T* dst;
-                    if (j < 2 * tc.nrows) {
+                    if (j < tc.nrows + nd) {
                         const int isd = j >= tc.nrows;
                         const int rr = isd ? j - tc.nrows : j;
                         const int64_t d = (int64_t)tc.g * p.Dg + tc.row0 + rr;
-                        src = isd ? reinterpret_cast<const T*>(p.delta) + tc.b * p.dl_bs + d * p.dl_ds + l0
-                                  : reinterpret_cast<const T*>(p.u) + tc.b * p.u_bs + d * p.u_ds + l0;
+                        if (!isd) src = reinterpret_cast<const T*>(p.u) + tc.b * p.u_bs + d * p.u_ds + l0;
+                        else if (R > 0) src = reinterpret_cast<const T*>(p.delta) + tc.b * p.dl_bs + tc.g * p.dl_gs + rr * p.dl_ds + l0;
+                        else src = reinterpret_cast<const T*>(p.delta) + tc.b * p.dl_bs + d * p.dl_ds + l0;
                         dst = reinterpret_cast<T*>(rows + rr * ROW_SLOT) + (isd ? CL : 0);
                     } else {
-                        const int k = j - 2 * tc.nrows;
+                        const int k = j - tc.nrows - nd;
                         const int isc = k >= N;
                         const int n = isc ? k - N : k;
                         src = isc ? reinterpret_cast<const T*>(p.Cm) + tc.b * p.C_bs + tc.g * p.C_gs + n * p.C_ns + l0
@@ -197,7 +207,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
             const int len = tc.len;
             const int64_t d = (int64_t)tc.g * p.Dg + tc.row0 + warp;
             const int64_t row = (int64_t)tc.b * p.dim + d;
-            const float* sc = reinterpret_cast<const float*>(st + 128) + warp * (N + 2);
+            const float* sc = reinterpret_cast<const float*>(st + 128) + warp * NSC;
             unsigned char* rows = st + hdr_bytes;
             const T* su = reinterpret_cast<const T*>(rows + warp * ROW_SLOT);
             const T* sB = reinterpret_cast<const T*>(rows + NW * ROW_SLOT);
@@ -213,6 +223,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
                 const uint4* lb_addr = p.lb_dynamic ? nullptr : lookback_addr(aggrow, inclrow, 1, c, -1, plan, lane);
                 const uint4 lb_first = lookback_prefetch(lb_addr);   // in flight during the local scan
                 const float A1 = sc[0];
+                float wdt[RANK > 0 ? RANK : 1];
+                if constexpr (RANK > 0) {
+#pragma unroll
+                    for (int r = 0; r < RANK; ++r) wdt[r] = sc[N + 2 + r];
+                }
                 float cumA[ITEMS], hloc[ITEMS];
                 float P = 1.f, Vv = 0.f;
                 auto local_scan = [&](auto tag) {
@@ -221,7 +236,29 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
                     for (int v = 0; v < ITEMS / V; ++v) {
                         float uv[V], dl[V], Bv[V];
                         lds_items<T, V>(su + e0 + v * V, uv);
-                        lds_items<T, V>(su + CL + e0 + v * V, dl);
+                        if constexpr (!FUSED) {
+                            lds_items<T, V>(su + CL + e0 + v * V, dl);
+                        } else {   // dt_proj on the fly: delta = sum_r W[d][r] * dt_lowrank[r], r ascending (weights: smem broadcast)
+#pragma unroll
+                            for (int k = 0; k < V; ++k) dl[k] = 0.f;
+                            if constexpr (RANK > 0) {
+#pragma unroll
+                                for (int r = 0; r < RANK; ++r) {
+                                    float tr[V];
+                                    lds_items<T, V>(reinterpret_cast<const T*>(rows + r * ROW_SLOT) + CL + e0 + v * V, tr);
+#pragma unroll
+                                    for (int k = 0; k < V; ++k) dl[k] = r == 0 ? wdt[0] * tr[k] : fmaf(wdt[r], tr[k], dl[k]);
+                                }
+                            } else {
+                                for (int r = 0; r < R; ++r) {
+                                    float tr[V];
+                                    lds_items<T, V>(reinterpret_cast<const T*>(rows + r * ROW_SLOT) + CL + e0 + v * V, tr);
+                                    const float wr = sc[N + 2 + r];
+#pragma unroll
+                                    for (int k = 0; k < V; ++k) dl[k] = r == 0 ? wr * tr[k] : fmaf(wr, tr[k], dl[k]);
+                                }
+                            }
+                        }
                         lds_items<T, V>(sB + e0 + v * V, Bv);
 #pragma unroll
                         for (int k = 0; k < V; ++k) {
@@ -427,11 +464,17 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <typename T, typename OutT, int ITEMS, bool N1>
+template <typename T, typename OutT, int ITEMS, bool N1, int RANK = 0>
 static int launch_fwd(ScanFwdArgs a, int sm_count, cudaStream_t stream) {
     constexpr int NW = kScanWarps;
     constexpr int CL = 32 * ITEMS;
-    auto kernel = scan_fwd_kernel<T, OutT, ITEMS, NW, N1>;
+    if constexpr (N1 && RANK == 0 && sizeof(T) == 4) {   // fused dt_proj: own instantiations, the plain kernel keeps its registers
+        if (a.R == 3) return launch_fwd<T, OutT, ITEMS, N1, 3>(a, sm_count, stream);
+        if (a.R == 5) return launch_fwd<T, OutT, ITEMS, N1, 5>(a, sm_count, stream);
+        if (a.R > 0) return launch_fwd<T, OutT, ITEMS, N1, -1>(a, sm_count, stream);
+    }
+    if (a.R > 0 && (RANK == 0 || a.R > kMaxDtRank || a.R > NW || !a.dt_w)) return BEM_ERR_UNSUPPORTED;   // N = 1, fp32, rank <= 8
+    auto kernel = scan_fwd_kernel<T, OutT, ITEMS, NW, N1, RANK>;
     a.nchunks = (a.L + CL - 1) / CL;
     a.RB = (a.Dg + NW - 1) / NW;
     a.RT = a.batch * a.G * a.RB;
@@ -440,7 +483,7 @@ static int launch_fwd(ScanFwdArgs a, int sm_count, cudaStream_t stream) {
     a.total_tiles = (int)total;
     const int64_t ndesc = (int64_t)a.batch * a.dim * a.nchunks * a.N;
     a.desc_incl = a.desc + ndesc;
-    const int hdr_bytes = 128 + ((NW * (a.N + 2) * 4 + 127) / 128) * 128;
+    const int hdr_bytes = 128 + ((NW * (a.N + 2 + a.R) * 4 + 127) / 128) * 128;
     const int stage_bytes = hdr_bytes + NW * 2 * CL * (int)sizeof(T) + 2 * a.N * CL * (int)sizeof(T);
     // two resident CTAs per SM when two stages fit in half of the shared memory, else one CTA with a deeper ring
     const int budget2 = (227 * 1024) / 2 - 1024;

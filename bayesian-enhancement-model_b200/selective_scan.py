@@ -58,9 +58,13 @@ def _common_checks(u, delta, A, B, C, D_, delta_bias_):
     return batch, dim, seqlen, dstate, n_groups
 
 
-def fwd(u, delta, A, B, C, D_, delta_bias_, delta_softplus, nrows=1, out_float=True):
+def fwd(u, delta, A, B, C, D_, delta_bias_, delta_softplus, nrows=1, out_float=True, dt_weight=None):
     """``selective_scan_cuda_oflex.fwd`` (selective_scan_oflex.cpp:157-243) -> ``[out, x]``.
-    ``nrows`` is accepted and ignored exactly as in the reference (:236-238)."""
+    ``nrows`` is accepted and ignored exactly as in the reference (:236-238).
+    ``dt_weight`` (extension, inference): (dim, R) dt_proj weight; ``delta`` is then the low-rank dt (batch, n_groups, R, L)
+    and the projection ``F.conv1d(dts, dt_projs_weight, groups=K)`` (vmamba.py:661) happens inside the scan kernel."""
+    if dt_weight is not None:
+        return _fwd_lowrank(u, delta, A, B, C, D_, delta_bias_, delta_softplus, out_float, dt_weight)
     batch, dim, seqlen, dstate, n_groups = _common_checks(u, delta, A, B, C, D_, delta_bias_)
     dev = u.device
     dt = _lib.dtype_code(u.dtype)
@@ -82,6 +86,43 @@ def fwd(u, delta, A, B, C, D_, delta_bias_, delta_softplus, nrows=1, out_float=T
     es, eo = u.element_size(), out.element_size()
     nbytes = batch * dim * seqlen * (2 * es + eo) + 2 * batch * n_groups * dstate * seqlen * es   # SURVEY 8d, boundary form
     _lib.launch("scan_fwd", lib.bem_scan_fwd, p, dev, key=(batch, dim, dstate, seqlen, str(u.dtype)), nbytes=nbytes)
+    return [out, x]
+
+
+def fused_dt_rank_ok(dt_rank: int, dstate: int, dtype) -> bool:
+    """configurations the fused dt_proj path of the forward kernel is built for"""
+    return 0 < dt_rank <= 8 and dstate == 1 and dtype == torch.float32
+
+
+def _fwd_lowrank(u, dtl, A, B, C, D_, delta_bias_, delta_softplus, out_float, dt_weight):
+    batch, dim, seqlen = u.shape
+    _lib.require_cuda(u, dtl, A, B, C, dt_weight)
+    n_groups, R = dtl.shape[1], dtl.shape[2]
+    dstate = A.shape[1]
+    _check(u.dtype == torch.float32 and dtl.dtype == torch.float32, "fused dt_proj: float32 only")
+    _check(tuple(dtl.shape) == (batch, n_groups, R, seqlen) and dtl.stride(-1) == 1, "low-rank delta must be (batch, groups, rank, L)")
+    _check(tuple(dt_weight.shape) == (dim, R), "dt_weight must be (dim, rank)")
+    _check(fused_dt_rank_ok(R, dstate, u.dtype), "fused dt_proj: dstate 1, rank <= 8")
+    _check(u.stride(-1) == 1 and B.stride(-1) == 1 and C.stride(-1) == 1, "u, B, C must be contiguous in the last dim")
+    dev = u.device
+    dt = _lib.dtype_code(u.dtype)
+    CL = lib.bem_scan_chunk_len(dt)
+    n_chunks = (seqlen + CL - 1) // CL
+    out = torch.empty((batch, dim, seqlen), dtype=torch.float32, device=dev)
+    x = torch.empty((batch, dim, n_chunks, dstate * 2), dtype=torch.float32, device=dev)
+    ws = _lib.workspace(dev, lib.bem_scan_workspace_bytes(batch, dim, seqlen, dstate, dt))
+    w = dt_weight.to(torch.float32).contiguous()
+    A = A.to(torch.float32)
+    p = _lib.BemScanFwdParams(
+        batch=batch, dim=dim, seqlen=seqlen, dstate=dstate, n_groups=n_groups, dtype=dt, out_dtype=_lib.BEM_F32,
+        delta_softplus=int(bool(delta_softplus)), u=_lib.ptr(u), delta=_lib.ptr(dtl), A=_lib.ptr(A), B=_lib.ptr(B), C=_lib.ptr(C),
+        D=_lib.ptr(D_), delta_bias=_lib.ptr(delta_bias_), out=_lib.ptr(out), x=_lib.ptr(x),
+        u_bs=u.stride(0), u_ds=u.stride(1), delta_bs=dtl.stride(0), delta_ds=dtl.stride(2), A_ds=A.stride(0), A_ns=A.stride(1),
+        B_bs=B.stride(0), B_gs=B.stride(1), B_ns=B.stride(2), C_bs=C.stride(0), C_gs=C.stride(1), C_ns=C.stride(2),
+        out_bs=out.stride(0), out_ds=out.stride(1), workspace=_lib.ptr(ws), workspace_bytes=ws.numel(),
+        dt_rank=R, dt_weight=_lib.ptr(w), delta_gs=dtl.stride(1))
+    nbytes = 4 * (2 * batch * dim * seqlen + batch * n_groups * (R + 2 * dstate) * seqlen)
+    _lib.launch("scan_fwd", lib.bem_scan_fwd, p, dev, key=(batch, dim, dstate, seqlen, "fused_dt%d" % R), nbytes=nbytes)
     return [out, x]
 
 

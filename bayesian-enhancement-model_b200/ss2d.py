@@ -15,7 +15,8 @@ import torch.nn.functional as F
 
 from .bayesian import functional as BF
 from .csm import cross_merge_fn, cross_scan_fn
-from .selective_scan import selective_scan_fn
+from .selective_scan import fused_dt_rank_ok, selective_scan_fn
+from .selective_scan import fwd as scan_fwd
 
 _SCAN_MODES = dict(cross2d=0, unidi=1, bidi=2)
 
@@ -44,6 +45,15 @@ def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_pr
         # dts is read as a strided channel slice of x_dbl (no .contiguous() copy)
         x_dbl = BF.grouped_pointwise(xs, x_proj_weight, None if x_proj_bias is None else x_proj_bias.view(K, -1))
         dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
+        if fused_dt_rank_ok(R, N, xs.dtype) and not force_fp32:
+            # dt_proj inside the scan kernel: the (B, K*D, L) delta tensor is neither written nor read (vmamba.py:661)
+            As = -A_logs.to(torch.float).exp()
+            ys = scan_fwd(xs.view(B, -1, L), dts, As, Bs, Cs, Ds.to(torch.float), dt_projs_bias.view(-1).to(torch.float),
+                          delta_softplus, 1, True, dt_weight=dt_projs_weight.view(K * D, R))[0].view(B, K, -1, H, W)
+            y = cross_merge_fn(ys, in_channel_first=True, out_channel_first=True, scans=scans).view(B, -1, H, W)
+            if out_norm is not None:
+                y = out_norm(y)
+            return y.to(x.dtype)
         dts = BF.grouped_pointwise(dts, dt_projs_weight)
     xs = xs.view(B, -1, L)
     dts = dts.contiguous().view(B, -1, L)

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define BEM_ABI_VERSION 5
+#define BEM_ABI_VERSION 6
 
 /* element types of u/delta/B/C/x-activations */
 enum { BEM_F32 = 0, BEM_F16 = 1, BEM_BF16 = 2 };
@@ -82,6 +82,14 @@ typedef struct BemScanFwdParams {
     int64_t out_bs, out_ds;
     void* workspace;
     int64_t workspace_bytes;
+    /* Fused dt_proj (SS2Dv2.forward_corev2, basicsr/vmamba/models/vmamba.py:660-661: `dts = F.conv1d(dts, dt_projs_weight,
+     * groups=K)` feeding the scan). dt_rank > 0: `delta` is the LOW-RANK dt of shape (batch, n_groups, dt_rank, seqlen)
+     * with strides delta_bs (batch), delta_gs (group), delta_ds (rank row), and the kernel forms
+     * delta[b, d, l] = sum_r dt_weight[d][r] * delta_lowrank[b, g(d), r, l] itself — the (batch, dim, seqlen) delta tensor is
+     * never written or read. fp32, dstate = 1, dt_rank <= 8 (else BEM_ERR_UNSUPPORTED: run the projection separately). */
+    int32_t dt_rank;             /* 0: delta is given per channel row (the plain selective_scan_fn contract) */
+    const float* dt_weight;      /* (dim, dt_rank) row-major, or NULL */
+    int64_t delta_gs;
 } BemScanFwdParams;
 
 typedef struct BemScanBwdParams {

@@ -302,3 +302,27 @@ def test_scan_workspace_rearms_itself_across_launches_and_graph_replays():
         assert torch.equal(out_g[0], ref_big[0])
         assert torch.equal(bwd_g[0], ref_bwd[0]) and torch.equal(bwd_g[1], ref_bwd[1])
     assert bem_b200._lib.scan_error_word(torch.device("cuda", torch.cuda.current_device())) == 0
+
+
+@pytest.mark.parametrize("Bn,G,Dg,L,R", [(1, 4, 40, 2400, 3), (2, 2, 10, 777, 5), (1, 1, 3, 70, 1), (1, 4, 16, 5000, 8)])
+def test_scan_fused_dt_proj_matches_projection_then_scan(Bn, G, Dg, L, R):
+    """dt_rank > 0: the scan kernel forms delta = dt_projs_weight . dt_lowrank itself (SS2Dv2.forward_corev2,
+    vmamba.py:660-661 runs the grouped conv1d first). Same result as projecting in fp64 and scanning, on out and carries;
+    incl. unaligned / ragged rows, strided low-rank views and more than one batch."""
+    from bem_b200 import selective_scan as ss
+    g = torch.Generator(device="cpu").manual_seed(L + R)
+    KD, N = G * Dg, 1
+    u = torch.randn(Bn, KD, L, generator=g).cuda()
+    x_dbl = torch.randn(Bn, G, R + 2 * N, L, generator=g).cuda()           # as x_proj leaves it: dt | B | C per direction
+    dtl, Bm, Cm = torch.split(x_dbl, [R, N, N], dim=2)                      # strided views, no copy
+    Wdt = (torch.randn(KD, R, generator=g) * 0.5).cuda()
+    A = (-torch.rand(KD, N, generator=g) - 0.2).cuda()
+    D = torch.randn(KD, generator=g).cuda()
+    bias = torch.randn(KD, generator=g).cuda()
+    out, xc = ss.fwd(u, dtl, A, Bm, Cm, D, bias, True, 1, True, dt_weight=Wdt)
+    delta = torch.einsum("bgrl,gdr->bgdl", dtl.double(), Wdt.double().view(G, Dg, R)).reshape(Bn, KD, L)
+    ref, xref = ss.fwd(u, delta.float().contiguous(), A, Bm.contiguous(), Cm.contiguous(), D, bias, True, 1, True)
+    assert nmax_err(out.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+    assert nmax_err(xc.cpu().numpy(), xref.cpu().numpy()) < 1e-5
+    out2, _ = ss.fwd(u, dtl, A, Bm, Cm, D, bias, True, 1, True, dt_weight=Wdt)
+    assert torch.equal(out, out2)                                           # deterministic
