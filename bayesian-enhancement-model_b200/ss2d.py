@@ -43,7 +43,13 @@ def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_pr
     else:
         # the same two grouped 1x1 contractions on the tcgen05 pointwise kernel, the K directions as its weight sets;
         # dts is read as a strided channel slice of x_dbl (no .contiguous() copy)
-        x_dbl = BF.grouped_pointwise(xs, x_proj_weight, None if x_proj_bias is None else x_proj_bias.view(K, -1))
+        # x_proj: a 1x1 convolution commutes with the pixel permutation of a traversal, so the K projections are one
+        # 1x1 conv of the UN-scanned x (D -> K*(R+2N) channels, x read once instead of the four scanned copies), whose
+        # result each direction then traverses on its own channel block (cross_scan, one_by_one) — vmamba.py:659
+        Cx = x_proj_weight.shape[1]
+        z = BF.pointwise_conv(x.reshape(B, D, L), x_proj_weight.reshape(1, K * Cx, D),
+                              None if x_proj_bias is None else x_proj_bias.reshape(1, K * Cx), 1)
+        x_dbl = cross_scan_fn(z.view(B, K, Cx, H, W), in_channel_first=True, out_channel_first=True, one_by_one=True, scans=scans)
         dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
         if fused_dt_rank_ok(R, N, xs.dtype) and not force_fp32:
             # dt_proj inside the scan kernel: the (B, K*D, L) delta tensor is neither written nor read (vmamba.py:661)
