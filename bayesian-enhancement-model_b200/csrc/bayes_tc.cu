@@ -790,7 +790,7 @@ int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t str
             attr3[dev] = smem_bytes;
         }
         if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
-        bayes_weight_pack_kernel<<<pack_blocks + vec_blocks, 256, 0, stream>>>(p, NT, ntiles, nk, pack, 1, vec);
+        if (!p.prepacked) bayes_weight_pack_kernel<<<pack_blocks + vec_blocks, 256, 0, stream>>>(p, NT, ntiles, nk, pack, 1, vec);
         const int64_t n_items = (int64_t)p.batch * ptiles * ntiles;
         if (n_items >= (1ll << 31)) return BEM_ERR_UNSUPPORTED;
         const int grid = (int)std::min<int64_t>(n_items, sms[dev]);
@@ -810,7 +810,7 @@ int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t str
         if (e != cudaSuccess) return (int)e;
         attr_set[dev] = smem_bytes;
     }
-    bayes_weight_pack_kernel<<<pack_blocks, 256, 0, stream>>>(p, NT, ntiles, nk, pack, 0, vec);
+    if (!p.prepacked) bayes_weight_pack_kernel<<<pack_blocks, 256, 0, stream>>>(p, NT, ntiles, nk, pack, 0, vec);
     dim3 grid((unsigned)ntiles, (unsigned)ptiles, (unsigned)p.batch);
     bayes_pointwise_tc_kernel<<<grid, 128, smem_bytes, stream>>>(p, NT, ntiles, pack, tmem_cols);
     return (int)cudaGetLastError();

@@ -175,6 +175,35 @@ class MCSampler:
         return rec
 
     @torch.no_grad()
+    def sample_to_host(self, x_host: torch.Tensor, out_host: torch.Tensor, sample_id: int):
+        """One prediction from a (pinned) host image into a (pinned) host buffer, on the current stream and without
+        intermediate device copies when the graph path is active: H2D straight into the graph's input, replay, D2H straight
+        from the graph's output. Returns after the result has landed in `out_host`."""
+        if self.use_graph and x_host.shape[0] == 1:
+            arena = self._get_arena()
+            dev = arena.device
+            key = (tuple(x_host.shape), x_host.dtype, dev)
+            rec = self._graphs.get(key)
+            if rec is None:
+                bayesian.set_mc_config(self.net, mc_samples=1, eps_source="philox", seed=self.seed, sample0=0)
+                arena.attach(True)
+                try:
+                    rec = self._graph_for(x_host.to(dev))
+                finally:
+                    arena.attach(False)
+            g, static_x, static_y = rec
+            static_x.copy_(x_host, non_blocking=True)
+            arena.sample0.fill_(int(sample_id))
+            g.replay()
+            out_host.copy_(static_y[0] if out_host.dim() == static_y.dim() - 1 else static_y, non_blocking=True)
+        else:
+            dev = next(self.net.parameters()).device
+            y = self.sample(x_host.to(dev, non_blocking=True), [sample_id])
+            out_host.copy_(y[0] if out_host.dim() == y.dim() - 1 else y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_host
+
+    @torch.no_grad()
     def sample(self, x: torch.Tensor, sample_ids: Sequence[int]) -> torch.Tensor:
         """x: (1, C, H, W) -> (len(sample_ids), C_out, H, W), one prediction per global sample index."""
         outs = []

@@ -39,7 +39,8 @@ class Conv2d(nn.Conv2d):
                 and not (torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad))):
             w = self.weight.view(1, self.out_channels, self.in_channels)
             ln = None if pre_norm is None else (pre_norm.weight, pre_norm.bias, pre_norm.eps)
-            return BF.pointwise_conv(x, w, None if self.bias is None else self.bias.view(1, -1), 1, ln=ln)
+            cache = self.__dict__.setdefault("_pack_cache", {})   # constant weights: packed once, reused by every call
+            return BF.pointwise_conv(x, w, None if self.bias is None else self.bias.view(1, -1), 1, ln=ln, pack_cache=cache)
         return super().forward(x if pre_norm is None else pre_norm(x))
 
 

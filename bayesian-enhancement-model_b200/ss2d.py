@@ -22,7 +22,7 @@ _SCAN_MODES = dict(cross2d=0, unidi=1, bidi=2)
 
 
 def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias=None, out_norm=None,
-              scan_mode="cross2d", force_fp32=False, ssoflex=True, delta_softplus=True):
+              scan_mode="cross2d", force_fp32=False, ssoflex=True, delta_softplus=True, pack_cache=None):
     """x: (B, D, H, W) -> y: (B, D, H, W) (after `out_norm` when given), following vmamba.py:656-698 line by line:
     cross_scan -> x_proj (grouped 1x1) -> split dt/B/C -> dt_proj (grouped 1x1) -> selective scan -> cross_merge."""
     if scan_mode not in _SCAN_MODES:
@@ -48,7 +48,7 @@ def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_pr
         # result each direction then traverses on its own channel block (cross_scan, one_by_one) — vmamba.py:659
         Cx = x_proj_weight.shape[1]
         z = BF.pointwise_conv(x.reshape(B, D, L), x_proj_weight.reshape(1, K * Cx, D),
-                              None if x_proj_bias is None else x_proj_bias.reshape(1, K * Cx), 1)
+                              None if x_proj_bias is None else x_proj_bias.reshape(1, K * Cx), 1, pack_cache=pack_cache)
         x_dbl = cross_scan_fn(z.view(B, K, Cx, H, W), in_channel_first=True, out_channel_first=True, one_by_one=True, scans=scans)
         dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
         if fused_dt_rank_ok(R, N, xs.dtype) and not force_fp32:
@@ -156,7 +156,8 @@ class SS2D(nn.Module):
 
     def forward_core(self, x, apply_out_norm=True):
         return ss2d_core(x, self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias, self.A_logs, self.Ds,
-                         x_proj_bias=getattr(self, "x_proj_bias", None), out_norm=self.out_norm if apply_out_norm else None)
+                         x_proj_bias=getattr(self, "x_proj_bias", None), out_norm=self.out_norm if apply_out_norm else None,
+                         pack_cache=self.__dict__.setdefault("_pack_cache", {}))
 
     def forward(self, x: torch.Tensor, pre_norm=None, residual=None, **kwargs):
         """forwardv2 (vmamba.py:700-716). `pre_norm`: the block's LayerNorm2d; when in_proj / out_proj are Bayesian 1x1

@@ -244,11 +244,8 @@ def main_ours(args):
     def step(i):
         return sampler.sample(img, [rank + i * world])
 
-    def step_e2e(i):
-        x = img_host.to(dev, non_blocking=True)
-        y = sampler.sample(x, [rank + i * world])
-        out_host.copy_(y, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    def step_e2e(i):   # the public host-buffer call: H2D of the image, one MC sample, D2H of the prediction, synchronised
+        sampler.sample_to_host(img_host, out_host, rank + i * world)
 
     for i in range(args.warmup):
         step(i)

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define BEM_ABI_VERSION 6
+#define BEM_ABI_VERSION 7
 
 /* element types of u/delta/B/C/x-activations */
 enum { BEM_F32 = 0, BEM_F16 = 1, BEM_BF16 = 2 };
@@ -270,6 +270,9 @@ typedef struct BemBayesPointwiseParams {
     int64_t workspace_bytes;
     const float* residual;  /* (batch, cout, P) or NULL: out = residual + conv(x) — the block's skip connection
                                (vmamba.py:1331-1333) folded into the epilogue; may alias `out` */
+    int32_t prepacked;      /* 1: `workspace` still holds the packed tiles written by an earlier call with the same weights,
+                               bias, LayerNorm parameters, n_samples / cin / cout and the same alignment class of x
+                               (deterministic layers: pack once, reuse) — the pack kernel is skipped */
 } BemBayesPointwiseParams;
 int64_t bem_bayes_pointwise_workspace_bytes(int n_samples, int cin, int cout);
 int bem_bayes_pointwise(const BemBayesPointwiseParams* p, void* stream);

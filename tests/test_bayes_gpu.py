@@ -338,3 +338,28 @@ def test_batched_sampling_matches_per_layer_sampling():
     arena.draw(None)                                   # sample index from the device word (CUDA-graph replay path)
     ref, _ = BF.sample_weights(arena.layers[1].mu_weight, arena.layers[1].rho_weight, None, 1, 99, 2 * int(arena.layers[1].layer_id), 5)
     assert torch.equal(ref[0], arena.layers[1]._arena_views["weight"])
+
+
+def test_constant_weight_pack_cache_tracks_in_place_updates():
+    """deterministic 1x1 layers pack their weights once (prepacked = 1 on later calls); an in-place weight / norm update or a
+    change of the input's alignment class must trigger a repack"""
+    from bem_b200 import network
+    from bem_b200.ss2d import LayerNorm2d
+    torch.manual_seed(11)
+    conv = network.Conv2d(24, 40, 1, bias=True).cuda()
+    norm = LayerNorm2d(24).cuda()
+    x = torch.randn(2, 24, 12, 16, device="cuda")
+
+    def ref(xx):
+        return torch.nn.functional.conv2d(norm(xx).double(), conv.weight.double(), conv.bias.double())
+
+    with torch.no_grad():
+        for _ in range(3):                                   # first call packs, the others reuse
+            assert nmax_err(conv(x, pre_norm=norm).cpu().numpy(), ref(x).cpu().numpy()) < TOL
+        conv.weight.mul_(1.5)                                # optimizer-style in-place update
+        assert nmax_err(conv(x, pre_norm=norm).cpu().numpy(), ref(x).cpu().numpy()) < TOL
+        norm.weight.add_(0.25)
+        assert nmax_err(conv(x, pre_norm=norm).cpu().numpy(), ref(x).cpu().numpy()) < TOL
+        x_odd = torch.randn(1, 24, 5, 7, device="cuda")      # 35 pixels: the unaligned kernel with its own tiling
+        assert nmax_err(conv(x_odd, pre_norm=norm).cpu().numpy(), ref(x_odd).cpu().numpy()) < TOL
+        assert nmax_err(conv(x, pre_norm=norm).cpu().numpy(), ref(x).cpu().numpy()) < TOL

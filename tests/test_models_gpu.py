@@ -150,3 +150,20 @@ def test_mc_sampler_arena_and_cuda_graph_match_per_layer_path():
     assert nmax_err(graph.cpu().numpy(), base.cpu().numpy()) < 5e-5
     assert nmax_err(graph2.cpu().numpy(), ref2.cpu().numpy()) < 5e-5
     assert float((graph[0] - graph[1]).abs().max()) > 0
+
+
+def test_mc_sampler_host_buffer_call_matches_device_call():
+    """sample_to_host (pinned image in, pinned prediction out; the bench's e2e call) == sample on device, graph and eager"""
+    from bem_b200 import mc, network
+    torch.manual_seed(0)
+    net = network.build_bayesian_model().cuda().eval()
+    xh = torch.rand(1, 3, 32, 48).pin_memory()
+    oh = torch.empty(1, 3, 32, 48).pin_memory()
+    with torch.backends.cudnn.flags(allow_tf32=False):
+        ref = mc.MCSampler(net, seed=9, arena=False).sample(xh.cuda(), [5])
+        for graph in (True, False):
+            s = mc.MCSampler(net, seed=9, arena=True, graph=graph)
+            s.sample_to_host(xh, oh, 5)
+            assert nmax_err(oh.numpy(), ref.cpu().numpy()) < 5e-5
+            s.sample_to_host(xh, oh, 5)        # second call: replay path
+            assert nmax_err(oh.numpy(), ref.cpu().numpy()) < 5e-5
