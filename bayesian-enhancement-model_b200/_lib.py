@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libbem_b200.so")
 
 BEM_F32, BEM_F16, BEM_BF16 = 0, 1, 2
 BEM_OK, BEM_ERR_BAD_ARG, BEM_ERR_WORKSPACE, BEM_ERR_UNSUPPORTED = 0, 10001, 10002, 10003
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 i32, i64, u64, vp = C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
 
@@ -40,8 +40,8 @@ class BemCsmParams(C.Structure):
 
 
 class BemSs2dFwdParams(C.Structure):
-    _fields_ = [(n, i32) for n in ("batch", "d_inner", "H", "W", "dstate", "dtype", "delta_softplus")] + \
-               [(n, vp) for n in ("x", "dts", "Bs", "Cs", "A", "Dskip", "delta_bias", "y", "workspace")] + \
+    _fields_ = [(n, i32) for n in ("batch", "d_inner", "H", "W", "dstate", "dt_rank", "delta_softplus")] + \
+               [(n, vp) for n in ("x", "xdbl", "dt_weight", "A", "Dskip", "delta_bias", "y", "workspace")] + \
                [("workspace_bytes", i64)]
 
 

@@ -135,15 +135,66 @@ int bem_scan_bwd(const BemScanBwdParams* q, void* stream_) {
     return scan_bwd_dispatch(a, q->dtype, q->dout_dtype, sms, stream);
 }
 
-// Fused SS2D core (traversal-aware scan). Entry point reserved in the ABI; until the traversal-aware loader lands the
-// host side composes bem_cross_scan -> bem_scan_fwd -> bem_cross_merge (bem_b200/ss2d.py) and this reports UNSUPPORTED.
-int64_t bem_ss2d_workspace_bytes(int batch, int d_inner, int H, int W, int dstate, int dtype) {
-    return bem_scan_workspace_bytes(batch, 4 * d_inner, H * W, dstate, dtype);
+// SS2D core in one call: cross_scan(x), cross_scan(xdbl, one_by_one), scan with dt_proj fused, cross_merge — the launch
+// sequence of bem_b200/ss2d.py behind a single entry point, intermediates in the caller's workspace.
+static int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
+struct Ss2dLayout {
+    int64_t scan_ws, xs, xdbl_s, ys, total;
+};
+static Ss2dLayout ss2d_layout(int batch, int d_inner, int H, int W, int dstate, int dt_rank) {
+    const int64_t L = (int64_t)H * W, Cx = dt_rank + 2 * dstate;
+    Ss2dLayout l;
+    l.scan_ws = 0;
+    l.xs = align256(bem_scan_workspace_bytes(batch, 4 * d_inner, (int)L, dstate, BEM_F32));
+    l.xdbl_s = l.xs + align256((int64_t)batch * 4 * d_inner * L * 4);
+    l.ys = l.xdbl_s + align256((int64_t)batch * 4 * Cx * L * 4);
+    l.total = l.ys + align256((int64_t)batch * 4 * d_inner * L * 4);
+    return l;
+}
+int64_t bem_ss2d_workspace_bytes(int batch, int d_inner, int H, int W, int dstate, int dt_rank) {
+    if (batch <= 0 || d_inner <= 0 || H <= 0 || W <= 0 || dstate <= 0 || dt_rank <= 0) return 0;
+    return ss2d_layout(batch, d_inner, H, W, dstate, dt_rank).total;
 }
 int bem_ss2d_fwd(const BemSs2dFwdParams* p, void* stream) {
-    (void)p;
-    (void)stream;
-    return BEM_ERR_UNSUPPORTED;
+    if (!p || !p->x || !p->xdbl || !p->dt_weight || !p->A || !p->y) return BEM_ERR_BAD_ARG;
+    if (p->batch <= 0 || p->d_inner <= 0 || p->H <= 0 || p->W <= 0 || p->dstate <= 0 || p->dt_rank <= 0) return BEM_ERR_BAD_ARG;
+    if (p->dstate != 1 || p->dt_rank > kMaxDtRank) return BEM_ERR_UNSUPPORTED;
+    const Ss2dLayout l = ss2d_layout(p->batch, p->d_inner, p->H, p->W, p->dstate, p->dt_rank);
+    if (!p->workspace || p->workspace_bytes < l.total || (reinterpret_cast<uintptr_t>(p->workspace) & 255)) return BEM_ERR_WORKSPACE;
+    unsigned char* ws = reinterpret_cast<unsigned char*>(p->workspace);
+    float* xs = reinterpret_cast<float*>(ws + l.xs);
+    float* xdbl_s = reinterpret_cast<float*>(ws + l.xdbl_s);
+    float* ys = reinterpret_cast<float*>(ws + l.ys);
+    const int64_t L = (int64_t)p->H * p->W;
+    const int D = p->d_inner, N = p->dstate, R = p->dt_rank, Cx = R + 2 * N;
+
+    BemCsmParams c{};
+    c.B = p->batch; c.C = D; c.H = p->H; c.W = p->W; c.dtype = BEM_F32;
+    c.img_channel_first = 1; c.seq_channel_first = 1; c.one_by_one = 0; c.scans = 0;
+    c.src = p->x; c.dst = xs;
+    int rc = bem_cross_scan(&c, stream);                       // xs : (B, 4, D, L)
+    if (rc) return rc;
+    c.C = Cx; c.one_by_one = 1; c.src = p->xdbl; c.dst = xdbl_s;
+    rc = bem_cross_scan(&c, stream);                           // xdbl_s : (B, 4, Cx, L), direction k traverses its own block
+    if (rc) return rc;
+
+    BemScanFwdParams q{};
+    q.batch = p->batch; q.dim = 4 * D; q.seqlen = (int)L; q.dstate = N; q.n_groups = 4;
+    q.dtype = BEM_F32; q.out_dtype = BEM_F32; q.delta_softplus = p->delta_softplus;
+    q.u = xs; q.delta = xdbl_s; q.A = p->A; q.B = xdbl_s + (int64_t)R * L; q.C = xdbl_s + (int64_t)(R + N) * L;
+    q.D = p->Dskip; q.delta_bias = p->delta_bias; q.out = ys; q.x = nullptr;
+    q.u_bs = 4 * (int64_t)D * L; q.u_ds = L;
+    q.delta_bs = 4 * (int64_t)Cx * L; q.delta_gs = (int64_t)Cx * L; q.delta_ds = L;
+    q.A_ds = N; q.A_ns = 1;
+    q.B_bs = q.C_bs = 4 * (int64_t)Cx * L; q.B_gs = q.C_gs = (int64_t)Cx * L; q.B_ns = q.C_ns = L;
+    q.out_bs = 4 * (int64_t)D * L; q.out_ds = L;
+    q.workspace = ws + l.scan_ws; q.workspace_bytes = l.xs;
+    q.dt_rank = R; q.dt_weight = p->dt_weight;
+    rc = bem_scan_fwd(&q, stream);                             // ys : (B, 4*D, L)
+    if (rc) return rc;
+
+    c.C = D; c.one_by_one = 0; c.src = ys; c.dst = p->y;
+    return bem_cross_merge(&c, stream);                        // y : (B, D, L)
 }
 
 }  // extern "C"

@@ -16,9 +16,31 @@ import torch.nn.functional as F
 from .bayesian import functional as BF
 from .csm import cross_merge_fn, cross_scan_fn
 from .selective_scan import fused_dt_rank_ok, selective_scan_fn
-from .selective_scan import fwd as scan_fwd
 
 _SCAN_MODES = dict(cross2d=0, unidi=1, bidi=2)
+
+
+def ss2d_fwd(x, z, dt_weight, A, Dskip, delta_bias, dstate=1, delta_softplus=True):
+    """bem_ss2d_fwd: x (B, D, H, W), z = x_proj output in image order (B, 4*(R+2N), H*W) -> y (B, D, H*W), fp32."""
+    from . import _lib
+    from ._lib import lib
+    _lib.require_cuda(x, z, dt_weight, A)
+    B, D, H, W = x.shape
+    R = dt_weight.shape[1]
+    x = x.contiguous()
+    z = z.contiguous()
+    dt_weight = dt_weight.to(torch.float32).contiguous()
+    A = A.to(torch.float32).contiguous()
+    y = torch.empty((B, D, H * W), dtype=torch.float32, device=x.device)
+    ws = _lib.workspace(x.device, lib.bem_ss2d_workspace_bytes(B, D, H, W, dstate, R), kind="ss2d")
+    p = _lib.BemSs2dFwdParams(batch=B, d_inner=D, H=H, W=W, dstate=dstate, dt_rank=R, delta_softplus=int(delta_softplus),
+                              x=_lib.ptr(x), xdbl=_lib.ptr(z), dt_weight=_lib.ptr(dt_weight), A=_lib.ptr(A),
+                              Dskip=_lib.ptr(Dskip), delta_bias=_lib.ptr(delta_bias), y=_lib.ptr(y), workspace=_lib.ptr(ws),
+                              workspace_bytes=ws.numel())
+    L = H * W
+    _lib.launch("ss2d_fwd", lib.bem_ss2d_fwd, p, x.device, key=(B, D, H, W, R),
+                nbytes=4 * B * L * (D + 4 * (R + 2 * dstate)) * 2 + 4 * B * L * 4 * D * 4 + 4 * B * L * D, kernels=4)
+    return y
 
 
 def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias=None, out_norm=None,
@@ -32,34 +54,34 @@ def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_pr
     N = A_logs.shape[1]
     K, _, R = dt_projs_weight.shape
     L = H * W
-    xs = cross_scan_fn(x, in_channel_first=True, out_channel_first=True, scans=scans)            # (B, 4, D, L)
     needs_grad = torch.is_grad_enabled() and (x.requires_grad or x_proj_weight.requires_grad or dt_projs_weight.requires_grad)
-    if needs_grad or xs.dtype != torch.float32:
+    if needs_grad or x.dtype != torch.float32:
+        xs = cross_scan_fn(x, in_channel_first=True, out_channel_first=True, scans=scans)            # (B, 4, D, L)
         x_dbl = F.conv1d(xs.view(B, -1, L), x_proj_weight.view(-1, D, 1),
                          bias=(x_proj_bias.view(-1) if x_proj_bias is not None else None), groups=K)  # vmamba.py:659
         x_dbl = x_dbl.view(B, K, -1, L)
         dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)                                             # vmamba.py:660
         dts = F.conv1d(dts.contiguous().view(B, -1, L), dt_projs_weight.view(K * D, -1, 1), groups=K)  # vmamba.py:661
     else:
-        # the same two grouped 1x1 contractions on the tcgen05 pointwise kernel, the K directions as its weight sets;
-        # dts is read as a strided channel slice of x_dbl (no .contiguous() copy)
         # x_proj: a 1x1 convolution commutes with the pixel permutation of a traversal, so the K projections are one
         # 1x1 conv of the UN-scanned x (D -> K*(R+2N) channels, x read once instead of the four scanned copies), whose
         # result each direction then traverses on its own channel block (cross_scan, one_by_one) — vmamba.py:659
         Cx = x_proj_weight.shape[1]
         z = BF.pointwise_conv(x.reshape(B, D, L), x_proj_weight.reshape(1, K * Cx, D),
                               None if x_proj_bias is None else x_proj_bias.reshape(1, K * Cx), 1, pack_cache=pack_cache)
-        x_dbl = cross_scan_fn(z.view(B, K, Cx, H, W), in_channel_first=True, out_channel_first=True, one_by_one=True, scans=scans)
-        dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
-        if fused_dt_rank_ok(R, N, xs.dtype) and not force_fp32:
-            # dt_proj inside the scan kernel: the (B, K*D, L) delta tensor is neither written nor read (vmamba.py:661)
-            As = -A_logs.to(torch.float).exp()
-            ys = scan_fwd(xs.view(B, -1, L), dts, As, Bs, Cs, Ds.to(torch.float), dt_projs_bias.view(-1).to(torch.float),
-                          delta_softplus, 1, True, dt_weight=dt_projs_weight.view(K * D, R))[0].view(B, K, -1, H, W)
-            y = cross_merge_fn(ys, in_channel_first=True, out_channel_first=True, scans=scans).view(B, -1, H, W)
+        if scans == 0 and fused_dt_rank_ok(R, N, x.dtype) and not force_fp32:
+            # everything after x_proj in ONE C-ABI call (bem_ss2d_fwd): cross_scan(x), per-direction traversal of z,
+            # selective scan with dt_proj fused (the (B, K*D, L) delta tensor is neither written nor read), cross_merge
+            y = ss2d_fwd(x, z, dt_projs_weight.reshape(K * D, R), -A_logs.to(torch.float).exp(), Ds.to(torch.float),
+                         dt_projs_bias.reshape(-1).to(torch.float), N, bool(delta_softplus)).view(B, -1, H, W)
             if out_norm is not None:
                 y = out_norm(y)
             return y.to(x.dtype)
+        xs = cross_scan_fn(x, in_channel_first=True, out_channel_first=True, scans=scans)
+        x_dbl = cross_scan_fn(z.view(B, K, Cx, H, W), in_channel_first=True, out_channel_first=True, one_by_one=True, scans=scans)
+        dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
+        # dt_proj: the K directions as the weight sets of the tcgen05 pointwise kernel; dts is read as a strided channel
+        # slice of x_dbl (no .contiguous() copy) — vmamba.py:661
         dts = BF.grouped_pointwise(dts, dt_projs_weight)
     xs = xs.view(B, -1, L)
     dts = dts.contiguous().view(B, -1, L)

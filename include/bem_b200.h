@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define BEM_ABI_VERSION 7
+#define BEM_ABI_VERSION 8
 
 /* element types of u/delta/B/C/x-activations */
 enum { BEM_F32 = 0, BEM_F16 = 1, BEM_BF16 = 2 };
@@ -160,26 +160,27 @@ int bem_cross_scan(const BemCsmParams* p, void* stream);
 int bem_cross_merge(const BemCsmParams* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Fused SS2D core: cross-scan gather + selective scan + cross-merge scatter in one pass.
- * Replaces the chain cross_scan_fn -> selective_scan_fn -> cross_merge_fn inside SS2Dv2.forward_corev2
- *   (basicsr/vmamba/models/vmamba.py:656-684), scan_mode "cross2d".
- * x, and the per-direction projections are given in IMAGE order (x_proj/dt_proj are
- * pointwise in l and commute with the traversal):
- *   x     : (B, D, H, W)        dtype
- *   dts   : (B, 4, D, H, W)     dtype   (delta before bias/softplus, direction k's projection at pixel (h,w))
- *   Bs,Cs : (B, 4, N, H, W)     dtype
- *   A     : (4*D, N) fp32; Dskip, delta_bias : (4*D) fp32 (may be NULL)
- *   y     : (B, D, H, W)        fp32  = sum over the 4 directions, already un-traversed
- * Implemented in terms of the traversal-aware loader of the scan kernel; see DESIGN.md.
+ * SS2D core in one call: the part of SS2Dv2.forward_corev2 after x_proj (basicsr/vmamba/models/vmamba.py:656-684, scan_mode
+ * "cross2d", `no_einsum`): split dt/B/C -> dt_proj -> cross_scan -> selective scan -> cross_merge.
+ * x_proj is pointwise in l and commutes with the traversal, so its output is taken in IMAGE order, one
+ * (dt_rank + 2*dstate)-channel block per direction — produced by ONE bem_bayes_pointwise call on x with the concatenated
+ * x_proj weights (bem_b200/ss2d.py). This entry point then runs
+ *     bem_cross_scan(x)  ->  bem_cross_scan(xdbl, one_by_one)  ->  bem_scan_fwd (dt_proj fused, dt_rank > 0)  ->  bem_cross_merge
+ * on the caller's stream with intermediates in `workspace`.
+ *   x         : (B, D, H, W)                         fp32
+ *   xdbl      : (B, 4, dt_rank + 2*dstate, H, W)     fp32, channel order [dt | B | C] per direction
+ *   dt_weight : (4*D, dt_rank) fp32; A : (4*D, dstate) fp32; Dskip, delta_bias : (4*D) fp32 or NULL
+ *   y         : (B, D, H*W)  fp32 = sum over the 4 directions, un-traversed (before out_norm)
+ * fp32, dstate = 1, dt_rank <= 8 (BEM_ERR_UNSUPPORTED otherwise: compose the entry points with a separate dt_proj).
+ * workspace : bem_ss2d_workspace_bytes() bytes, 256-byte aligned, ZERO-FILLED BY THE CALLER BEFORE ITS FIRST USE (it starts
+ *             with the scan look-back workspace, see bem_scan_fwd), then owned by the calls of one stream.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct BemSs2dFwdParams {
-    int32_t batch, d_inner, H, W, dstate;
-    int32_t dtype;
+    int32_t batch, d_inner, H, W, dstate, dt_rank;
     int32_t delta_softplus;
-    const void* x;
-    const void* dts;
-    const void* Bs;
-    const void* Cs;
+    const float* x;
+    const float* xdbl;
+    const float* dt_weight;
     const float* A;
     const float* Dskip;
     const float* delta_bias;
@@ -187,7 +188,7 @@ typedef struct BemSs2dFwdParams {
     void* workspace;
     int64_t workspace_bytes;
 } BemSs2dFwdParams;
-int64_t bem_ss2d_workspace_bytes(int batch, int d_inner, int H, int W, int dstate, int dtype);
+int64_t bem_ss2d_workspace_bytes(int batch, int d_inner, int H, int W, int dstate, int dt_rank);
 int bem_ss2d_fwd(const BemSs2dFwdParams* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
