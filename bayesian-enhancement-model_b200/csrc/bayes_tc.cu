@@ -350,14 +350,14 @@ __global__ void __launch_bounds__(128, 4) bayes_pointwise_tc_kernel(const BemBay
 // Rows of A past the end of the image carry zero-filled or stale values: row m of D depends on row m of A only and
 // those rows are never stored. Input channels past `cin` (last K chunk) are zeroed, they feed every output.
 // ------------------------------------------------------------------------------------------------
-// debug timeline (tools/trace_pointwise.py, BEM_PW_DBG bit 3): (tag, arg, SM clock) records of CTA 0, one region of
+// stage timeline (tools/trace_pointwise.py, env BEM_PW_TRACE=1): (tag, arg, SM clock) records of CTA 0, one region of
 // TRACE_PER records per traced warp, plain stores (nothing on the critical path waits for them)
 constexpr int TRACE_ROLES = 8, TRACE_PER = 2048;
 __device__ uint4 g_trace[TRACE_ROLES * TRACE_PER];
 struct Tracer {
     uint32_t n = 0;
-    __device__ __forceinline__ void operator()(int dbg, int role, uint32_t tag, uint32_t arg) {
-        if ((dbg & 8) && blockIdx.x == 0 && n < TRACE_PER) g_trace[role * TRACE_PER + n++] = make_uint4(tag, arg, (uint32_t)clock64(), 1u);
+    __device__ __forceinline__ void operator()(int on, int role, uint32_t tag, uint32_t arg) {
+        if (on && blockIdx.x == 0 && n < TRACE_PER) g_trace[role * TRACE_PER + n++] = make_uint4(tag, arg, (uint32_t)clock64(), 1u);
     }
 };
 
@@ -410,7 +410,7 @@ template <bool LN>
 __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(const BemBayesPointwiseParams p, const int NT, const int ntiles,
                                                                           const int ptiles, const int64_t n_items,
                                                                           const float* __restrict__ pack, const float* __restrict__ vec,
-                                                                          const uint32_t RS, const uint32_t BS, const int b_resident, const int dbg) {
+                                                                          const uint32_t RS, const uint32_t BS, const int b_resident, const int trace_on) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t b_bytes = (uint32_t)NT * TC_KC * 4;
     unsigned char* s_raw = smem;
@@ -474,10 +474,10 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
                 if (g % P3_PW != (uint32_t)warp) continue;
                 if (lane == 0) mbar_wait(&raw_empty[r.s], r.ph ^ 1, nullptr);
                 __syncwarp();
-                if (warp == 0 && lane == 0) tr(dbg, 0, 2, g);
+                if (warp == 0 && lane == 0) tr(trace_on, 0, 2, g);
                 const uint32_t dst = smem_u32(s_raw + r.s * P3_RAW_BYTES) + lane * 16;
                 const int c0 = kc * TC_KC;
-                if ((dbg & 1) == 0) {
+                {
                     if (c0 + TC_KC <= p.cin) {
                         const float* src = x + (int64_t)c0 * p.P;
 #pragma unroll
@@ -493,14 +493,14 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
                     }
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
-                if (warp == 0 && lane == 0) tr(dbg, 0, 1, g);
+                if (warp == 0 && lane == 0) tr(trace_on, 0, 1, g);
                 if (++issued > lag) {
                     if (lag == 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
                     else if (lag == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
                     else asm volatile("cp.async.wait_group 1;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&raw_full[done.s]);
-                    if (warp == 0 && lane == 0) tr(dbg, 0, 3, g);
+                    if (warp == 0 && lane == 0) tr(trace_on, 0, 3, g);
                     for (int i = 0; i < P3_PW; ++i) done.next(RS);
                 }
             }
@@ -553,14 +553,14 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
                 rb.s = (uint32_t)((w.s_idx * ntiles + w.tile) * nk);
             }
             mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1, nullptr);   // the epilogue has drained this accumulator
-            if (lane == 0) tr(dbg, 3, 20, li);
+            if (lane == 0) tr(trace_on, 3, 20, li);
             const uint32_t d = tmem + buf * P3_ACC_COLS;
             for (int kc = 0; kc < nk; ++kc, ra.next(P3_AS), rb.next(b_resident ? 0xffffffffu : BS)) {
                 mbar_wait(&a_full[ra.s], ra.ph, nullptr);
                 if (!b_resident) mbar_wait(&b_full[rb.s], rb.ph, nullptr);
-                if (lane == 0) tr(dbg, 3, 21, kc);
+                if (lane == 0) tr(trace_on, 3, 21, kc);
                 tc_fence_after();
-                if (elect_one() && !(dbg & 4)) {
+                if (elect_one()) {
                     const uint32_t aH = tmem + P3_A_COL0 + ra.s * (2 * TC_KC), aL = aH + TC_KC;
                     const uint64_t dBh = descB0 + (uint64_t)(rb.s * b_step), dBl = dBh + b_lo;
 #pragma unroll
@@ -573,12 +573,6 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
                     umma_commit(&a_empty[ra.s]);
                     if (!b_resident) umma_commit(&b_empty[rb.s]);
                     if (kc == nk - 1) umma_commit(&acc_full[buf]);
-                } else if (dbg & 4) {
-                    if (elect_one()) {
-                        mbar_arrive(&a_empty[ra.s]);
-                        if (!b_resident) mbar_arrive(&b_empty[rb.s]);
-                        if (kc == nk - 1) mbar_arrive(&acc_full[buf]);
-                    }
                 }
                 __syncwarp();
             }
@@ -600,11 +594,11 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
             for (int kc = 0; kc < nk; ++kc, ++g, rr.next(RS), ra.next(P3_AS)) {
                 if ((g & 1) != (uint32_t)grp) continue;
                 mbar_wait(&raw_full[rr.s], rr.ph, nullptr);
-                if ((warp & 3) == 0 && lane == 0) tr(dbg, 1 + grp, 10 + grp, g);
+                if ((warp & 3) == 0 && lane == 0) tr(trace_on, 1 + grp, 10 + grp, g);
                 const float* raw = reinterpret_cast<const float*>(s_raw + rr.s * P3_RAW_BYTES) + m;
                 float v[TC_KC];
 #pragma unroll
-                for (int e = 0; e < TC_KC; ++e) v[e] = (dbg & 2) ? 1.f : raw[e * TC_M];
+                for (int e = 0; e < TC_KC; ++e) v[e] = raw[e * TC_M];
                 const int left = p.cin - kc * TC_KC;                          // channels of this chunk that exist
                 if (left < TC_KC) {
 #pragma unroll
@@ -625,7 +619,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
                     lo[e] = v[e] - hi[e];
                 }
                 mbar_wait(&a_empty[ra.s], ra.ph ^ 1, nullptr);           // the MMAs that read this stage have completed
-                if ((warp & 3) == 0 && lane == 0) tr(dbg, 1 + grp, 12 + grp, g);
+                if ((warp & 3) == 0 && lane == 0) tr(trace_on, 1 + grp, 12 + grp, g);
                 tc_fence_after();
                 tmem_st16(a_lane + ra.s * (2 * TC_KC), hi);
                 tmem_st16(a_lane + ra.s * (2 * TC_KC) + TC_KC, lo);
@@ -635,7 +629,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
                 if (lane == 0) {
                     mbar_arrive(&a_full[ra.s]);
                     mbar_arrive(&raw_empty[rr.s]);
-                    if ((warp & 3) == 0) tr(dbg, 1 + grp, 14 + grp, g);
+                    if ((warp & 3) == 0) tr(trace_on, 1 + grp, 14 + grp, g);
                 }
             }
             if (LN) {
@@ -665,7 +659,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
                 nmr = -mean * rstd;
             }
             mbar_wait(&acc_full[buf], par, nullptr);
-            if (ew == 0 && lane == 0) tr(dbg, 4, 30, li);
+            if (ew == 0 && lane == 0) tr(trace_on, 4, 30, li);
             tc_fence_after();
             const bool valid = m < w.npx;
             const int64_t P = p.P;
@@ -710,7 +704,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
-            if (ew == 0 && lane == 0) tr(dbg, 4, 31, li);
+            if (ew == 0 && lane == 0) tr(trace_on, 4, 31, li);
         }
     }
     tc_fence_before();
@@ -759,7 +753,7 @@ int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t str
     float* pack = reinterpret_cast<float*>(p.workspace);
     // the persistent kernel moves x with 16-byte cp.async: rows must start and end on 16-byte boundaries
     static const int force_v2 = env_int("BEM_PW_V2", 0);
-    static const int dbg = env_int("BEM_PW_DBG", 0);   // timing experiments only (results are wrong when set)
+    static const int trace_on = env_int("BEM_PW_TRACE", 0);   // record CTA 0's stage timeline (tools/trace_pointwise.py)
     const bool aligned = (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && p.P % 4 == 0 && p.x_img_stride % 4 == 0;
     int ntiles, NT, nk;
     tc_tiling(p.cin, p.cout, P3_NMAX, ntiles, NT, nk);
@@ -795,9 +789,9 @@ int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t str
         if (n_items >= (1ll << 31)) return BEM_ERR_UNSUPPORTED;
         const int grid = (int)std::min<int64_t>(n_items, sms[dev]);
         if (p.ln_gamma)
-            bayes_pointwise_tc3_kernel<true><<<grid, P3_THREADS, smem_bytes, stream>>>(p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS, b_resident, dbg);
+            bayes_pointwise_tc3_kernel<true><<<grid, P3_THREADS, smem_bytes, stream>>>(p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS, b_resident, trace_on);
         else
-            bayes_pointwise_tc3_kernel<false><<<grid, P3_THREADS, smem_bytes, stream>>>(p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS, b_resident, dbg);
+            bayes_pointwise_tc3_kernel<false><<<grid, P3_THREADS, smem_bytes, stream>>>(p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS, b_resident, trace_on);
         return (int)cudaGetLastError();
     }
     uint32_t tmem_cols = 32;

@@ -287,8 +287,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
                 }
                 const float Pa = __shfl_sync(FULL, P, 31), Va = __shfl_sync(FULL, Vv, 31);
                 float Pp = 1.f, hp = 0.f;
-                if (p.lb_dynamic == 2) {   // timing experiment only: no cross-tile dependency at all (WRONG results)
-                } else if (p.lb_dynamic) {   // A/B: classic look-back (timing-dependent association)
+                if (p.lb_dynamic) {   // A/B: classic look-back (timing-dependent association)
                     if (c > 0) {
                         if (lane == 0 && c + 1 < nt) st_desc(aggrow + c, Pa, Va, desc_tag(ep, 1u));
                             const float2 pre = lookback_dynamic(aggrow, 1, c, nt, -1, lane, p.err, ep);
@@ -494,7 +493,7 @@ static int launch_fwd(ScanFwdArgs a, int sm_count, cudaStream_t stream) {
         stages = min(4, (227 * 1024 - 256) / stage_bytes);
         if (stages < 2) return BEM_ERR_UNSUPPORTED;
     }
-    if (const char* ev = getenv("BEM_LB_DYNAMIC")) a.lb_dynamic = atoi(ev);   // tuning knob (tools/)
+    if (const char* ev = getenv("BEM_LB_DYNAMIC")) a.lb_dynamic = atoi(ev) ? 1 : 0;   // A/B knob (tools/): classic look-back
     if (const char* ev = getenv("BEM_FWD_STAGES")) {   // tuning knob (tools/), not a product interface
         const int v = atoi(ev);
         if (v >= 2 && v * stage_bytes + 512 <= 227 * 1024) stages = v;

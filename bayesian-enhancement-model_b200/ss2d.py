@@ -72,7 +72,13 @@ def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_pr
         if scans == 0 and fused_dt_rank_ok(R, N, x.dtype) and not force_fp32:
             # everything after x_proj in ONE C-ABI call (bem_ss2d_fwd): cross_scan(x), per-direction traversal of z,
             # selective scan with dt_proj fused (the (B, K*D, L) delta tensor is neither written nor read), cross_merge
-            y = ss2d_fwd(x, z, dt_projs_weight.reshape(K * D, R), -A_logs.to(torch.float).exp(), Ds.to(torch.float),
+            As = None if pack_cache is None else pack_cache.get("As")
+            akey = (A_logs.data_ptr(), A_logs._version)
+            if As is None or pack_cache.get("As_key") != akey:     # -exp(A_logs) once per parameter version, not per call
+                As = -A_logs.detach().to(torch.float).exp()
+                if pack_cache is not None:
+                    pack_cache["As"], pack_cache["As_key"] = As, akey
+            y = ss2d_fwd(x, z, dt_projs_weight.reshape(K * D, R), As, Ds.to(torch.float),
                          dt_projs_bias.reshape(-1).to(torch.float), N, bool(delta_softplus)).view(B, -1, H, W)
             if out_norm is not None:
                 y = out_norm(y)

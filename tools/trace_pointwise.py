@@ -1,6 +1,6 @@
-"""Timeline of CTA 0 of the persistent pointwise kernel (debug build knob BEM_PW_DBG=8): prints per-role event gaps."""
+"""Timeline of CTA 0 of the persistent pointwise kernel (env BEM_PW_TRACE=1): prints per-role event gaps."""
 import ctypes as C, os, sys, collections
-os.environ["BEM_PW_DBG"] = str(int(os.environ.get("BEM_PW_DBG", "0")) | 8)
+os.environ["BEM_PW_TRACE"] = "1"
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 from bem_b200 import _lib
