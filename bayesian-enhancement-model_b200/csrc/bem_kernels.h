@@ -43,6 +43,7 @@ struct ScanFwdArgs {
     int softplus;
     int stages;
     int lb_dynamic;    // A/B knob: classic timing-dependent look-back instead of the deterministic one
+    int trace;         // record CTA 0's stage timeline (debug, tools/trace_scan.py)
     int R;             // fused dt_proj rank (0: `delta` is given per channel row)
     const float* dt_w; // (dim, R) dt_proj weight, row-major
     int64_t dl_gs;     // group stride of the low-rank delta (B, G, R, L); dl_ds is then the stride between its R rows

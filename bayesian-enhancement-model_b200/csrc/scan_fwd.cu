@@ -21,6 +21,17 @@
 
 namespace bem {
 
+// stage timeline of CTA 0 (tools/trace_scan.py, env BEM_SCAN_TRACE=1): (tag, arg, SM clock) records, one region per traced
+// warp, plain stores — nothing on the critical path waits for them
+constexpr int STRACE_ROLES = 4, STRACE_PER = 2048;
+__device__ uint4 g_scan_trace[STRACE_ROLES * STRACE_PER];
+struct ScanTracer {
+    uint32_t n = 0;
+    __device__ __forceinline__ void operator()(int on, int role, uint32_t tag, uint32_t arg) {
+        if (on && blockIdx.x == 0 && n < STRACE_PER) g_scan_trace[role * STRACE_PER + n++] = make_uint4(tag, arg, (uint32_t)clock64(), 1u);
+    }
+};
+
 // RANK: fused dt_proj rank. 0 = `delta` given per channel row; > 0 = compile-time rank (the BEM ranks 3 and 5: unrolled, weights
 // in registers); -1 = rank read from the arguments (any rank <= kMaxDtRank, runtime loop).
 template <typename T, typename OutT, int ITEMS, int NW, bool N1, int RANK = 0>
@@ -49,6 +60,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    ScanTracer tr;
+    const int trace_on = p.trace;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -120,7 +133,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
                 }
                 scv[q] = v;
             }
+            if (lane == 0) tr(trace_on, 0, 1, t);
             if (use > 0) mbar_wait(&empty[s], (use - 1) & 1, p.err);
+            if (lane == 0) tr(trace_on, 0, 2, t);
             // the next ticket is drawn only once this slot is free: tickets held ahead of time would sit in this CTA's
             // queue while other CTAs' look-backs wait on them
             unsigned int t_next = 0;
@@ -132,6 +147,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
                 const int i = lane + 32 * q;
                 if (i < tc.nrows * NSC) sc[i] = scv[q];
             }
+            if (lane == 0) tr(trace_on, 0, 6, t);
             unsigned char* rows = st + hdr_bytes;
             // jobs: [0, nrows) u rows, then nd delta rows (one per channel row, or the group's R low-rank rows), N B rows, N C rows
             const int nd = R > 0 ? R : tc.nrows;
@@ -168,6 +184,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
                     }
                 }
                 if (pass == 0) {
+                    if (lane == 0) tr(trace_on, 0, 7, t);
                     uint32_t tot = my_bytes;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
@@ -179,6 +196,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
                     __syncwarp();
                 }
             }
+            if (lane == 0) tr(trace_on, 0, 3, t);
             t = __shfl_sync(FULL, t_next, 0);
             if (++s == S) {
                 s = 0;
@@ -195,10 +213,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
     while (true) {
         if (++s == S) s = 0;
         if (s == 0) phase ^= 1;
+        if (lane == 0 && (warp == 0 || warp == 5)) tr(trace_on, warp == 0 ? 1 : 2, 10, 0);
         mbar_wait(&full[s], phase, p.err);
         unsigned char* st = smem + (size_t)s * stage_bytes;
         const TileCoord tc = *reinterpret_cast<const TileCoord*>(st);
         const uint32_t ep = tc.epoch;
+        if (lane == 0 && (warp == 0 || warp == 5)) tr(trace_on, warp == 0 ? 1 : 2, 11, tc.c);
         if (tc.nrows < 0) break;
         const bool active = warp < tc.nrows;
         if (active) {
@@ -279,6 +299,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
                 };
                 if (len < CL) local_scan(std::true_type{});
                 else local_scan(std::false_type{});
+                if (lane == 0 && (warp == 0 || warp == 5)) tr(trace_on, warp == 0 ? 1 : 2, 12, tc.c);
                 warp_scan_fwd(P, Vv, lane);   // (P, Vv): composition of lanes 0..lane
                 float Pe = __shfl_up_sync(FULL, P, 1), Ve = __shfl_up_sync(FULL, Vv, 1);
                 if (lane == 0) {
@@ -315,6 +336,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
                     }
                 }
                 const float seed = fmaf(Pe, hp, Ve);
+                if (lane == 0 && (warp == 0 || warp == 5)) tr(trace_on, warp == 0 ? 1 : 2, 13, tc.c);
 #pragma unroll
                 for (int v = 0; v < ITEMS / V; ++v) {
                     float uv[V], Cv[V];
@@ -436,6 +458,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(con
             // registers are sector-complete; no shared-memory staging, no TMA-store drain before the stage can be reused.
             __syncwarp();   // all lanes of this row are done reading the stage
             if (lane == 0) mbar_arrive(&empty[s]);
+            if (lane == 0 && (warp == 0 || warp == 5)) tr(trace_on, warp == 0 ? 1 : 2, 14, tc.c);
             OutT* gout = reinterpret_cast<OutT*>(p.out) + tc.b * p.out_bs + d * p.out_ds + l0;
             constexpr int VO = ElemTraits<OutT>::kPerVec;
             if (len == CL && (reinterpret_cast<uintptr_t>(gout) & 15) == 0) {
@@ -493,6 +516,7 @@ static int launch_fwd(ScanFwdArgs a, int sm_count, cudaStream_t stream) {
         stages = min(4, (227 * 1024 - 256) / stage_bytes);
         if (stages < 2) return BEM_ERR_UNSUPPORTED;
     }
+    if (const char* ev = getenv("BEM_SCAN_TRACE")) a.trace = atoi(ev);   // stage timeline of CTA 0 (tools/trace_scan.py)
     if (const char* ev = getenv("BEM_LB_DYNAMIC")) a.lb_dynamic = atoi(ev) ? 1 : 0;   // A/B knob (tools/): classic look-back
     if (const char* ev = getenv("BEM_FWD_STAGES")) {   // tuning knob (tools/), not a product interface
         const int v = atoi(ev);
@@ -546,3 +570,15 @@ int scan_fwd_dispatch(const ScanFwdArgs& a, int dtype, int out_dtype, int sm_cou
 }
 
 }  // namespace bem
+
+// not part of the ABI: reads (and clears) the stage timeline of the scan forward kernel (tools/trace_scan.py)
+extern "C" int bem_dbg_scan_trace(unsigned int* out, int max_records) {
+    const int total = bem::STRACE_ROLES * bem::STRACE_PER;
+    if (max_records < total) return -1;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, bem::g_scan_trace, (size_t)total * sizeof(uint4));
+    void* sym = nullptr;
+    cudaGetSymbolAddress(&sym, bem::g_scan_trace);
+    cudaMemset(sym, 0, (size_t)total * sizeof(uint4));
+    return total;
+}
