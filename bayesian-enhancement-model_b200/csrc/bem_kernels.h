@@ -89,6 +89,7 @@ struct ScanBwdArgs {
 };
 
 int scan_fwd_dispatch(const ScanFwdArgs& a, int dtype, int out_dtype, int sm_count, cudaStream_t stream);
+int scan_fwd_deferred_dispatch(const ScanFwdArgs& a, int sm_count, cudaStream_t stream);   // fp32, N = 1: deferred-finish schedule
 int scan_bwd_dispatch(ScanBwdArgs& a, int dtype, int dout_dtype, int sm_count, cudaStream_t stream);
 
 int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t stream);

@@ -548,6 +548,16 @@ int scan_fwd_dispatch(const ScanFwdArgs& a, int dtype, int out_dtype, int sm_cou
     const bool n1 = a.N == 1;
     if (dtype == BEM_F32) {
         if (n1) {
+            // A/B and debugging knobs (tools/) select the classic schedule of this file
+            static const bool classic = (getenv("BEM_FWD_CLASSIC") && atoi(getenv("BEM_FWD_CLASSIC"))) ||
+                                        (getenv("BEM_SCAN_TRACE") && atoi(getenv("BEM_SCAN_TRACE")) == 1) ||
+                                        getenv("BEM_LB_DYNAMIC") || getenv("BEM_FWD_ITEMS") || getenv("BEM_FWD_STAGES");
+            if (!classic) {
+                ScanFwdArgs b = a;
+                if (const char* tv = getenv("BEM_SCAN_TRACE")) b.trace = atoi(tv) == 2;
+                const int rc = scan_fwd_deferred_dispatch(b, sm_count, stream);   // deferred-finish schedule (scan_fwd_deferred.cu)
+                if (rc != BEM_ERR_UNSUPPORTED) return rc;
+            }
             const char* ev = getenv("BEM_FWD_ITEMS");   // tuning knob (tools/), not a product interface
             if (ev && atoi(ev) == 12) return launch_fwd<float, float, 12, true>(a, sm_count, stream);
             return launch_fwd<float, float, kFwdItemsF32N1, true>(a, sm_count, stream);
