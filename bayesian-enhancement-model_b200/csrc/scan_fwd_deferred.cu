@@ -17,6 +17,7 @@
 // Deadlock freedom: a look-back only ever waits for the pass 1 of tiles with smaller tickets, and a warp runs pass 1 of
 // its newest tile before any look-back; the tile with the smallest outstanding ticket waits for nothing but its data.
 #include <cstdlib>
+#include <type_traits>
 
 #include "bem_kernels.h"
 #include "scan_common.cuh"
@@ -41,13 +42,17 @@ struct Tracer {
 
 struct Pending {   // what a lane keeps of a tile between pass 1 and its finish
     int s, c, len, active;
-    int64_t row, out_off;
+    int nlanes, publish_incl;          // look-back plan of the tile (lookback_plan)
+    const uint4* lb_addr;              // this lane's look-back descriptor (nullptr: idle lane)
+    uint4* incl;                       // the tile's inclusive descriptor
+    float2* carry;                     // the tile's carry in `x` (nullptr: not requested)
+    float* gout;                       // the row's output at the tile start
     float Pe, Ve, Pa, Va;
 };
 }  // namespace
 
 // RANK: fused dt_proj rank. 0 = delta per channel row; > 0 compile-time rank; -1 = rank from the arguments (<= kMaxDtRank).
-template <int RANK>
+template <int RANK, bool TRACE = false>
 __global__ void __launch_bounds__(D_THREADS, 2) scan_fwd_deferred_kernel(const ScanFwdArgs p) {
     constexpr int NW = D_NW, CL = D_CL, ITEMS = D_ITEMS, V = D_V, ROW_SLOT = D_ROW_SLOT;
     constexpr bool FUSED = RANK != 0;
@@ -64,7 +69,7 @@ __global__ void __launch_bounds__(D_THREADS, 2) scan_fwd_deferred_kernel(const S
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Tracer tr;
-    const int trace_on = p.trace;
+    constexpr int trace_on = TRACE ? 1 : 0;   // the timeline instantiation is separate: no trace predicates in the product kernel
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 2);        // one expect_tx arrival per producer warp
@@ -245,21 +250,20 @@ __global__ void __launch_bounds__(D_THREADS, 2) scan_fwd_deferred_kernel(const S
 
     // finish of a tile whose pass 1 is done: look-back (descriptor `first` was requested a whole pass ago), publish the
     // inclusive value / carry, pass 2 from the alpha / beta left in the stage, release the stage, store y
-    auto finish = [&](const Pending& q, const uint4* lb_addr, uint4 lb_first) {
+    auto finish = [&](const Pending& q, uint4 lb_first) {
         unsigned char* st = smem + (size_t)q.s * stage_bytes;
         if (!q.active) {
             if (lane == 0) mbar_arrive(&empty[q.s]);
             return;
         }
-        const LookbackPlan plan = lookback_plan(q.c, nt);
         float Pp = 1.f, hp = 0.f;
-        if (plan.nlanes) {
-            const float2 pre = lookback_finish(lb_addr, lb_first, plan.nlanes, lane, p.err, ep);
+        if (q.nlanes) {
+            const float2 pre = lookback_finish(q.lb_addr, lb_first, q.nlanes, lane, p.err, ep);
             Pp = pre.x;
             hp = pre.y;
         }
-        if (lane == 0 && plan.publish_incl) st_desc(p.desc_incl + q.row * nt + q.c, Pp * q.Pa, fmaf(q.Pa, hp, q.Va), desc_tag(ep, DESC_READY));
-        if (p.x && lane == 31) reinterpret_cast<float2*>(p.x)[q.row * p.nxchunks + q.c] = make_float2(Pp * q.Pa, fmaf(q.Pa, hp, q.Va));
+        if (lane == 0 && q.publish_incl) st_desc(q.incl, Pp * q.Pa, fmaf(q.Pa, hp, q.Va), desc_tag(ep, DESC_READY));
+        if (lane == 31 && q.carry) *q.carry = make_float2(Pp * q.Pa, fmaf(q.Pa, hp, q.Va));
         if (lane == 0 && (warp == 0 || warp == 5)) tr(trace_on, warp == 0 ? 1 : 2, 13, q.c);
         const float seed = fmaf(q.Pe, hp, q.Ve);
         const float* sa = reinterpret_cast<const float*>(st + hdr_bytes + warp * ROW_SLOT) + e0;
@@ -270,7 +274,7 @@ __global__ void __launch_bounds__(D_THREADS, 2) scan_fwd_deferred_kernel(const S
         for (int i = 0; i < ITEMS; ++i) y[i] = fmaf(al[i], seed, be[i]);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[q.s]);
-        float* gout = reinterpret_cast<float*>(p.out) + q.out_off;
+        float* gout = q.gout;
         if (q.len == CL && (reinterpret_cast<uintptr_t>(gout) & 15) == 0) {
 #pragma unroll
             for (int v = 0; v < ITEMS / V; ++v)
@@ -294,15 +298,10 @@ __global__ void __launch_bounds__(D_THREADS, 2) scan_fwd_deferred_kernel(const S
         ep = tc.nrows < 0 ? ep : tc.epoch;
         if (lane == 0 && (warp == 0 || warp == 5)) tr(trace_on, warp == 0 ? 1 : 2, 11, tc.c);
         // request the previous tile's look-back descriptors now: they are in flight during this tile's pass 1
-        const uint4* lb_addr = nullptr;
         uint4 lb_first = make_uint4(0u, 0u, 0u, 0u);
-        if (prev.s >= 0 && prev.active) {
-            const LookbackPlan pl = lookback_plan(prev.c, nt);
-            lb_addr = lookback_addr(p.desc + prev.row * nt, p.desc_incl + prev.row * nt, 1, prev.c, -1, pl, lane);
-            lb_first = lookback_prefetch(lb_addr);
-        }
+        if (prev.s >= 0 && prev.active) lb_first = lookback_prefetch(prev.lb_addr);
         if (tc.nrows < 0) {
-            if (prev.s >= 0) finish(prev, lb_addr, lb_first);
+            if (prev.s >= 0) finish(prev, lb_first);
             break;
         }
         Pending cur;
@@ -314,13 +313,24 @@ __global__ void __launch_bounds__(D_THREADS, 2) scan_fwd_deferred_kernel(const S
         cur.Ve = 0.f;
         cur.Pa = 1.f;
         cur.Va = 0.f;
-        cur.row = 0;
-        cur.out_off = 0;
+        cur.nlanes = cur.publish_incl = 0;
+        cur.lb_addr = nullptr;
+        cur.incl = nullptr;
+        cur.carry = nullptr;
+        cur.gout = nullptr;
         if (cur.active) {
             // ------------------------------ pass 1: local scan, alpha / beta in place ------------------------------
             const int64_t d = (int64_t)tc.g * p.Dg + tc.row0 + warp;
-            cur.row = (int64_t)tc.b * p.dim + d;
-            cur.out_off = tc.b * p.out_bs + d * p.out_ds + (int64_t)tc.c * CL;
+            const int64_t row = (int64_t)tc.b * p.dim + d;
+            const LookbackPlan plan = lookback_plan(tc.c, nt);
+            uint4* aggrow = p.desc + row * nt;
+            uint4* inclrow = p.desc_incl + row * nt;
+            cur.nlanes = plan.nlanes;
+            cur.publish_incl = plan.publish_incl;
+            cur.lb_addr = lookback_addr(aggrow, inclrow, 1, tc.c, -1, plan, lane);
+            cur.incl = inclrow + tc.c;
+            cur.carry = p.x ? reinterpret_cast<float2*>(p.x) + row * p.nxchunks + tc.c : nullptr;
+            cur.gout = reinterpret_cast<float*>(p.out) + tc.b * p.out_bs + d * p.out_ds + (int64_t)tc.c * CL;
             const float* sc = reinterpret_cast<const float*>(st + 128) + warp * NSC;
             unsigned char* rows = st + hdr_bytes;
             float* su = reinterpret_cast<float*>(rows + warp * ROW_SLOT) + e0;
@@ -333,8 +343,9 @@ __global__ void __launch_bounds__(D_THREADS, 2) scan_fwd_deferred_kernel(const S
 #pragma unroll
                 for (int r = 0; r < RANK; ++r) wdt[r] = sc[3 + r];
             }
-            const bool part = tc.len < CL;
             float P = 1.f, Vv = 0.f;
+            auto local_scan = [&](auto tag) {
+            constexpr bool PART = decltype(tag)::value;   // ragged last tile of a row: identity padding past `len`
 #pragma unroll
             for (int v = 0; v < ITEMS / V; ++v) {
                 float uv[V], dl[V], Bv[V], Cv[V], al[V], be[V];
@@ -368,7 +379,7 @@ __global__ void __launch_bounds__(D_THREADS, 2) scan_fwd_deferred_kernel(const S
                     if (p.softplus) xd = softplus_f(xd);
                     float e = decay_m1<true>(xd * A1);
                     float b = xd * uv[k] * Bv[k];
-                    if (part && e0 + v * V + k >= tc.len) {   // identity padding so the carried state stays exact
+                    if (PART && e0 + v * V + k >= tc.len) {   // identity padding so the carried state stays exact
                         e = 0.f;
                         b = 0.f;
                     }
@@ -379,6 +390,9 @@ __global__ void __launch_bounds__(D_THREADS, 2) scan_fwd_deferred_kernel(const S
                 sts_items<float, V>(su + v * V, al);
                 sts_items<float, V>(su + CL + v * V, be);
             }
+            };
+            if (tc.len < CL) local_scan(std::true_type{});
+            else local_scan(std::false_type{});
             warp_scan_fwd(P, Vv, lane);   // (P, Vv): composition of lanes 0..lane
             cur.Pe = __shfl_up_sync(FULL, P, 1);
             cur.Ve = __shfl_up_sync(FULL, Vv, 1);
@@ -388,11 +402,10 @@ __global__ void __launch_bounds__(D_THREADS, 2) scan_fwd_deferred_kernel(const S
             }
             cur.Pa = __shfl_sync(FULL, P, 31);
             cur.Va = __shfl_sync(FULL, Vv, 31);
-            const LookbackPlan plan = lookback_plan(tc.c, nt);
-            if (lane == 0 && plan.publish_agg) st_desc(p.desc + cur.row * nt + tc.c, cur.Pa, cur.Va, desc_tag(ep, DESC_READY));
+            if (lane == 0 && plan.publish_agg) st_desc(aggrow + tc.c, cur.Pa, cur.Va, desc_tag(ep, DESC_READY));
         }
         if (lane == 0 && (warp == 0 || warp == 5)) tr(trace_on, warp == 0 ? 1 : 2, 12, tc.c);
-        if (prev.s >= 0) finish(prev, lb_addr, lb_first);
+        if (prev.s >= 0) finish(prev, lb_first);
         if (lane == 0 && (warp == 0 || warp == 5)) tr(trace_on, warp == 0 ? 1 : 2, 14, tc.c);
         prev = cur;
     }
@@ -417,7 +430,7 @@ static int launch_deferred(ScanFwdArgs a, int sm_count, cudaStream_t stream) {
     if (stages < 3) return BEM_ERR_UNSUPPORTED;
     a.stages = stages;
     const int smem_bytes = stages * stage_bytes + stages * 3 * 8 + 64;
-    auto kernel = scan_fwd_deferred_kernel<RANK>;
+    auto kernel = (RANK == 0 && a.trace) ? scan_fwd_deferred_kernel<RANK == 0 ? 0 : RANK, RANK == 0> : scan_fwd_deferred_kernel<RANK, false>;
     static int cached_smem[64] = {0}, cached_per_sm[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
