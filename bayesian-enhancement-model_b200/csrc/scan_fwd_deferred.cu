@@ -321,15 +321,15 @@ __global__ void __launch_bounds__(D_THREADS, 2) scan_fwd_deferred_kernel(const S
         if (cur.active) {
             // ------------------------------ pass 1: local scan, alpha / beta in place ------------------------------
             const int64_t d = (int64_t)tc.g * p.Dg + tc.row0 + warp;
-            const int64_t row = (int64_t)tc.b * p.dim + d;
+            const int row = tc.b * p.dim + (int)d;                      // (batch, dim) row index: fits 32 bits (host check)
             const LookbackPlan plan = lookback_plan(tc.c, nt);
-            uint4* aggrow = p.desc + row * nt;
-            uint4* inclrow = p.desc_incl + row * nt;
+            uint4* aggrow = p.desc + (uint32_t)(row * nt);             // 32-bit index arithmetic, one widening add per pointer
+            uint4* inclrow = p.desc_incl + (uint32_t)(row * nt);
             cur.nlanes = plan.nlanes;
             cur.publish_incl = plan.publish_incl;
             cur.lb_addr = lookback_addr(aggrow, inclrow, 1, tc.c, -1, plan, lane);
             cur.incl = inclrow + tc.c;
-            cur.carry = p.x ? reinterpret_cast<float2*>(p.x) + row * p.nxchunks + tc.c : nullptr;
+            cur.carry = p.x ? reinterpret_cast<float2*>(p.x) + (uint32_t)(row * p.nxchunks + tc.c) : nullptr;
             cur.gout = reinterpret_cast<float*>(p.out) + tc.b * p.out_bs + d * p.out_ds + (int64_t)tc.c * CL;
             const float* sc = reinterpret_cast<const float*>(st + 128) + warp * NSC;
             unsigned char* rows = st + hdr_bytes;
@@ -421,6 +421,7 @@ static int launch_deferred(ScanFwdArgs a, int sm_count, cudaStream_t stream) {
     if (total > 0x7fffffff) return BEM_ERR_UNSUPPORTED;
     a.total_tiles = (int)total;
     a.desc_incl = a.desc + (int64_t)a.batch * a.dim * a.nchunks;
+    if ((int64_t)a.batch * a.dim * a.nchunks >= (1ll << 31)) return BEM_ERR_UNSUPPORTED;   // 32-bit descriptor indices in the kernel
     if (a.R > 0 && (RANK == 0 || a.R > kMaxDtRank || !a.dt_w)) return BEM_ERR_UNSUPPORTED;
     const int hdr_bytes = 128 + ((NW * (3 + a.R) * 4 + 127) / 128) * 128;
     const int stage_bytes = hdr_bytes + NW * D_ROW_SLOT + 2 * CL * 4 + a.R * CL * 4;
