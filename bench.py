@@ -309,7 +309,7 @@ def main_ours(args):
     peak, peak_src = measured_peaks()
     # dominant kernel of the hot path: the level-0 scan forward (largest traffic per launch of the section-8 rows)
     sr = scan_rooflines(dev, peak)
-    roof = dict(sr["fwd"], kernel="scan_fwd_kernel<float,float,24,8,N1> (B1, KD160, N1, L240000, fp32)", peak_source=peak_src,
+    roof = dict(sr["fwd"], kernel="scan_fwd_deferred_kernel<0> (B1, KD160, N1, L240000, fp32)", peak_source=peak_src,
                 timing="8 back-to-back C-ABI calls per CUDA-graph replay, CUDA events around the replay / 8; working set 468 MB >> 126 MB L2")
     eager_fwd = prof.get("scan_fwd")
     if eager_fwd:   # the same launches as they ran inside the eager per-kernel pass (adds host launch gaps)
