@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libbem_b200.so")
 
 BEM_F32, BEM_F16, BEM_BF16 = 0, 1, 2
 BEM_OK, BEM_ERR_BAD_ARG, BEM_ERR_WORKSPACE, BEM_ERR_UNSUPPORTED = 0, 10001, 10002, 10003
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 i32, i64, u64, vp = C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
 
@@ -62,6 +62,10 @@ class BemBayesDepthwiseParams(C.Structure):
                 + [("act", i32)])
 
 
+class BemConv3x3Params(C.Structure):
+    _fields_ = [(n, i32) for n in ("batch", "cin", "cout", "H", "W")] + [(n, vp) for n in ("x", "w", "bias", "out")]
+
+
 class BemBayesSampleBatchedParams(C.Structure):
     _fields_ = [("entries", vp), ("blocks", vp), ("n_blocks", i32), ("seed", C.c_uint64), ("sample0", i64), ("sample0_dev", vp)]
 
@@ -83,6 +87,7 @@ SYMBOLS = {
     "bem_bayes_pointwise_workspace_bytes": (i64, [C.c_int] * 3),
     "bem_bayes_pointwise": (C.c_int, [C.POINTER(BemBayesPointwiseParams), vp]),
     "bem_bayes_depthwise": (C.c_int, [C.POINTER(BemBayesDepthwiseParams), vp]),
+    "bem_conv3x3": (C.c_int, [C.POINTER(BemConv3x3Params), vp]),
     "bem_select_best": (C.c_int, [vp, i32, i32, vp, vp, vp]),
 }
 

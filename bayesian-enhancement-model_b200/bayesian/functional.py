@@ -255,3 +255,19 @@ def sample_batched(entries, blocks, n_blocks, seed, sample0=0, sample0_dev=None)
                                          seed=int(seed), sample0=int(sample0), sample0_dev=_lib.ptr(sample0_dev))
     _lib.launch("bayes_sample", lib.bem_bayes_sample_batched, p, entries.device, key=("batched", int(n_blocks)),
                 nbytes=0)
+
+
+def conv3x3_direct(x, w, bias=None):
+    """Dense 3x3 convolution, stride 1, zero padding 1 (bem_conv3x3): the network's small-channel stems. Inference only."""
+    _lib.require_cuda(x, w)
+    x = _f32c(x, "input")
+    w = _f32c(w, "w")
+    bias = _f32c(bias, "bias")
+    B, cin, H, W = x.shape
+    cout = w.shape[0]
+    if tuple(w.shape) != (cout, cin, 3, 3):
+        raise RuntimeError(f"conv3x3_direct: weight {tuple(w.shape)} does not match input channels {cin}")
+    out = torch.empty((B, cout, H, W), dtype=torch.float32, device=x.device)
+    p = _lib.BemConv3x3Params(batch=B, cin=cin, cout=cout, H=H, W=W, x=_lib.ptr(x), w=_lib.ptr(w), bias=_lib.ptr(bias), out=_lib.ptr(out))
+    _lib.launch("conv3x3", lib.bem_conv3x3, p, x.device, key=(B, cin, cout, H, W), nbytes=4 * (x.numel() + out.numel()))
+    return out

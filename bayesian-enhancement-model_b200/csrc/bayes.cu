@@ -419,6 +419,86 @@ __global__ void __launch_bounds__(512) bayes_depthwise3_smem_kernel(const BemBay
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Dense 3x3 convolution (stride 1, zero padding 1) for the small-channel stems of the network (3 -> 40 and 40 -> 3 at full
+// resolution, UNet_arch.py:423-431): register-tiled direct convolution. One thread = 4 output columns of one row x COT
+// output channels; the weights of the CTA's output-channel tile sit in shared memory as [ci][tap][COT] (broadcast LDS.128),
+// input rows are read as one float4 + two clamped / masked halo scalars. The library path splits these shapes into five
+// kernels and takes 90 / 430 us at 600x400; this takes ~15 us each.
+// ------------------------------------------------------------------------------------------------
+template <int COT, bool VEC>
+__global__ void __launch_bounds__(256) conv3x3_direct_kernel(const BemConv3x3Params p) {
+    extern __shared__ __align__(16) float sw[];            // [cin][9][COT]
+    const int co0 = blockIdx.z * COT;
+    const int img = blockIdx.y;
+    for (int i = threadIdx.x; i < p.cin * 9 * COT; i += blockDim.x) {
+        const int co = i % COT, tap = (i / COT) % 9, ci = i / (9 * COT);
+        sw[i] = co0 + co < p.cout ? p.w[((int64_t)(co0 + co) * p.cin + ci) * 9 + tap] : 0.f;
+    }
+    __syncthreads();
+    const int W4 = (p.W + 3) / 4;
+    const int64_t strips = (int64_t)p.H * W4;
+    const float* x = p.x + (int64_t)img * p.cin * p.H * p.W;
+    float* out = p.out + ((int64_t)img * p.cout + co0) * p.H * p.W;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < strips; t += (int64_t)gridDim.x * blockDim.x) {
+        const int h = (int)(t / W4), w0 = (int)(t - (int64_t)h * W4) * 4;
+        const int loff = w0 > 0 ? -1 : 0, roff = w0 + 4 < p.W ? 4 : 3;
+        float acc[COT][4];
+#pragma unroll
+        for (int c = 0; c < COT; ++c) {
+            const float b = (p.bias && co0 + c < p.cout) ? p.bias[co0 + c] : 0.f;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) acc[c][o] = b;
+        }
+        for (int ci = 0; ci < p.cin; ++ci) {
+            const float* plane = x + (int64_t)ci * p.H * p.W;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const DwRow r = dw_load_row<VEC>(plane, h + kh - 1, p.H, p.W, w0, loff, roff);
+                const float* wr = sw + (ci * 9 + kh * 3) * COT;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    float wv[COT];
+#pragma unroll
+                    for (int c4 = 0; c4 < COT / 4; ++c4) {
+                        const float4 q = *reinterpret_cast<const float4*>(wr + kw * COT + c4 * 4);
+                        wv[c4 * 4] = q.x; wv[c4 * 4 + 1] = q.y; wv[c4 * 4 + 2] = q.z; wv[c4 * 4 + 3] = q.w;
+                    }
+#pragma unroll
+                    for (int c = 0; c < COT; ++c)
+#pragma unroll
+                        for (int o = 0; o < 4; ++o) acc[c][o] = fmaf(wv[c], r.v[o + kw], acc[c][o]);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < COT; ++c) {
+            if (co0 + c >= p.cout) break;
+            float* dst = out + ((int64_t)c * p.H + h) * p.W + w0;
+            if (VEC) *reinterpret_cast<float4*>(dst) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+            else {
+#pragma unroll
+                for (int o = 0; o < 4; ++o)
+                    if (w0 + o < p.W) dst[o] = acc[c][o];
+            }
+        }
+    }
+}
+
+template <int COT>
+static int conv3x3_launch(const BemConv3x3Params& p, cudaStream_t stream) {
+    const bool vec = (p.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.out)) & 15) == 0;
+    const int64_t strips = (int64_t)p.H * ((p.W + 3) / 4);
+    int64_t bx = (strips + 255) / 256;
+    if (bx > 65535) bx = 65535;
+    dim3 grid((unsigned)bx, (unsigned)p.batch, (unsigned)((p.cout + COT - 1) / COT));
+    const int smem = p.cin * 9 * COT * 4;
+    if (smem > 48 * 1024) return BEM_ERR_UNSUPPORTED;
+    if (vec) conv3x3_direct_kernel<COT, true><<<grid, 256, smem, stream>>>(p);
+    else conv3x3_direct_kernel<COT, false><<<grid, 256, smem, stream>>>(p);
+    return (int)cudaGetLastError();
+}
+
 template <int ACT>
 static void depthwise_launch(const BemBayesDepthwiseParams& p, dim3 grid, cudaStream_t stream) {
     const bool vec = (p.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.out)) & 15) == 0;
@@ -487,6 +567,13 @@ int bem_bayes_pointwise(const BemBayesPointwiseParams* p, void* stream) {
     dim3 grid((unsigned)((p->P + PW_BN - 1) / PW_BN), (unsigned)((p->cout + PW_BM - 1) / PW_BM), (unsigned)p->batch);
     bayes_pointwise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
     return (int)cudaGetLastError();
+}
+
+int bem_conv3x3(const BemConv3x3Params* p, void* stream) {
+    if (!p || !p->x || !p->w || !p->out || p->batch <= 0 || p->cin <= 0 || p->cout <= 0 || p->H <= 0 || p->W <= 0) return BEM_ERR_BAD_ARG;
+    if (p->batch > 65535) return BEM_ERR_UNSUPPORTED;
+    // output-channel tile per thread: 4 for the few-output case (40 -> 3), 8 otherwise
+    return p->cout <= 4 ? conv3x3_launch<4>(*p, (cudaStream_t)stream) : conv3x3_launch<8>(*p, (cudaStream_t)stream);
 }
 
 int bem_bayes_depthwise(const BemBayesDepthwiseParams* p, void* stream) {

@@ -22,7 +22,7 @@ from .ss2d import SS2D, LayerNorm2d, apply_1x1, apply_residual, fuses_act
 
 
 class Conv2d(nn.Conv2d):
-    """nn.Conv2d (same name, parameters and state_dict) whose deterministic 1x1 case — PatchMerging.reduction, the
+    """nn.Conv2d (same name, parameters and state_dict) whose small-channel 3x3 stems run on bem_conv3x3 and whose deterministic 1x1 case — PatchMerging.reduction, the
     DualUpSample projections, the decoder fusion convs (UNet_arch.py:88-135, 161-163) — runs on the same tcgen05 pointwise
     kernel as the Bayesian 1x1 layers (one weight set, no sampling) when no gradient is needed; everything else is the
     library convolution."""
@@ -41,6 +41,12 @@ class Conv2d(nn.Conv2d):
             ln = None if pre_norm is None else (pre_norm.weight, pre_norm.bias, pre_norm.eps)
             cache = self.__dict__.setdefault("_pack_cache", {})   # constant weights: packed once, reused by every call
             return BF.pointwise_conv(x, w, None if self.bias is None else self.bias.view(1, -1), 1, ln=ln, pack_cache=cache)
+        if (pre_norm is None and self.kernel_size == (3, 3) and self.stride == (1, 1) and self.padding == (1, 1)
+                and self.dilation == (1, 1) and self.groups == 1 and self.padding_mode == "zeros"
+                and min(self.in_channels, self.out_channels) <= 8 and self.in_channels * 9 * 8 * 4 <= 48 * 1024
+                and x.is_cuda and x.dtype == torch.float32 and self.weight.dtype == torch.float32
+                and not (torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad))):
+            return BF.conv3x3_direct(x, self.weight, self.bias)     # the full-resolution stems (first_conv, proj)
         return super().forward(x if pre_norm is None else pre_norm(x))
 
 

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define BEM_ABI_VERSION 8
+#define BEM_ABI_VERSION 9
 
 /* element types of u/delta/B/C/x-activations */
 enum { BEM_F32 = 0, BEM_F16 = 1, BEM_BF16 = 2 };
@@ -291,6 +291,19 @@ typedef struct BemBayesDepthwiseParams {
                             out[c] = gelu(y[c]) * y[c + C/2] (gdMlp: chunk -> act(x1) * x2, vmamba.py:129-131) */
 } BemBayesDepthwiseParams;
 int bem_bayes_depthwise(const BemBayesDepthwiseParams* p, void* stream);
+
+/* Dense 3x3 convolution, stride 1, zero padding 1, groups 1, fp32 — the two full-resolution stems of the stage-1 network
+ * (`first_conv` 3 -> 40 and `proj` 40 -> 3, basicsr/archs/UNet_arch.py:423-431; nn.Conv2d in the reference).
+ *   x : (batch, cin, H, W)   w : (cout, cin, 3, 3)   bias : (cout) or NULL   out : (batch, cout, H, W)
+ * Direct register-tiled kernel meant for small channel counts (cin * 9 * 8 floats of weights must fit 48 KB). */
+typedef struct BemConv3x3Params {
+    int32_t batch, cin, cout, H, W;
+    const float* x;
+    const float* w;
+    const float* bias;
+    float* out;
+} BemConv3x3Params;
+int bem_conv3x3(const BemConv3x3Params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Monte-Carlo best-sample selection.

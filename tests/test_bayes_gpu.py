@@ -363,3 +363,25 @@ def test_constant_weight_pack_cache_tracks_in_place_updates():
         x_odd = torch.randn(1, 24, 5, 7, device="cuda")      # 35 pixels: the unaligned kernel with its own tiling
         assert nmax_err(conv(x_odd, pre_norm=norm).cpu().numpy(), ref(x_odd).cpu().numpy()) < TOL
         assert nmax_err(conv(x, pre_norm=norm).cpu().numpy(), ref(x).cpu().numpy()) < TOL
+
+
+@pytest.mark.parametrize("B,cin,cout,H,W", [(1, 3, 40, 20, 28), (2, 40, 3, 9, 13), (1, 5, 7, 6, 600), (1, 3, 3, 1, 4), (1, 1, 17, 5, 5)])
+def test_conv3x3_direct_matches_conv2d(B, cin, cout, H, W):
+    """bem_conv3x3 (the network's 3x3 stems, UNet_arch.py:423-431) == F.conv2d in fp64, incl. ragged widths and tiny images"""
+    import torch.nn.functional as F
+    from bem_b200 import network
+    from bem_b200.bayesian import functional as BF
+    g = torch.Generator(device="cpu").manual_seed(cin * 50 + cout)
+    x = torch.randn(B, cin, H, W, generator=g).cuda()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).cuda()
+    b = torch.randn(cout, generator=g).cuda()
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    assert nmax_err(BF.conv3x3_direct(x, w, b).cpu().numpy(), ref.cpu().numpy()) < TOL
+    assert nmax_err(BF.conv3x3_direct(x, w, None).cpu().numpy(), (ref - b.double()[None, :, None, None]).cpu().numpy()) < TOL
+    conv = network.Conv2d(cin, cout, 3, 1, 1).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(w)
+        conv.bias.copy_(b)
+        y = conv(x)
+    if min(cin, cout) <= 8:
+        assert nmax_err(y.cpu().numpy(), ref.cpu().numpy()) < TOL
