@@ -136,7 +136,25 @@ class DualUpSample(nn.Module):
             raise NotImplementedError(scale_factor)
 
     def forward(self, x):
-        return self.conv(torch.cat([self.up_p(x), self.up_b(x)], dim=1))
+        """UNet_arch.py:150-156: conv(cat([up_p(x), up_b(x)])). At inference two exact rewrites of the linear pieces save the
+        full-resolution intermediates: the bias-free 1x1 conv that follows the bilinear upsampling is applied BEFORE it (both
+        are linear, the interpolation weights sum to one, so they commute: half the channels to upsample, a quarter of the
+        pixels to convolve), and conv(cat([p, b])) = W_p p + W_b b is evaluated as two 1x1 launches, the second adding onto
+        the first in its epilogue, instead of materialising the concatenation."""
+        fast = (x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled() and self.up_b[3].bias is None
+                and self.conv.bias is None and isinstance(self.up_b[2], nn.Upsample) and self.up_b[2].mode == "bilinear")
+        if not fast:
+            return self.conv(torch.cat([self.up_p(x), self.up_b(x)], dim=1))
+        p = self.up_p(x)
+        b = self.up_b[2](self.up_b[3](self.up_b[1](self.up_b[0](x))))
+        cp = p.shape[1]
+        cache = self.__dict__.setdefault("_split_cache", {})
+        key = (self.conv.weight.data_ptr(), self.conv.weight._version)
+        if cache.get("key") != key:
+            w = self.conv.weight.detach().view(self.conv.out_channels, -1)
+            cache.update(key=key, wp=w[:, :cp].contiguous().unsqueeze(0), wb=w[:, cp:].contiguous().unsqueeze(0), pc_p={}, pc_b={})
+        y = BF.pointwise_conv(p, cache["wp"], None, 1, pack_cache=cache["pc_p"])
+        return BF.pointwise_conv(b, cache["wb"], None, 1, residual=y, pack_cache=cache["pc_b"])
 
 
 class BasicBlock(nn.Module):
