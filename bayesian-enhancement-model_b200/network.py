@@ -50,6 +50,23 @@ class Conv2d(nn.Conv2d):
         return super().forward(x if pre_norm is None else pre_norm(x))
 
 
+def conv1x1_of_cat(conv, a, b):
+    """conv(torch.cat([a, b], dim=1)) for a bias-free 1x1 `conv`: W_a a + W_b b as two 1x1 launches, the second adding onto
+    the first in its epilogue — the concatenation is never materialised. Inference fast path; otherwise the plain form."""
+    fast = (isinstance(conv, Conv2d) and conv._is_1x1() and conv.bias is None and a.is_cuda and a.dtype == torch.float32
+            and b.dtype == torch.float32 and not torch.is_grad_enabled())
+    if not fast:
+        return conv(torch.cat([a, b], dim=1))
+    ca = a.shape[1]
+    cache = conv.__dict__.setdefault("_split_cache", {})
+    key = (conv.weight.data_ptr(), conv.weight._version, ca)
+    if cache.get("key") != key:
+        w = conv.weight.detach().view(conv.out_channels, -1)
+        cache.update(key=key, wa=w[:, :ca].contiguous().unsqueeze(0), wb=w[:, ca:].contiguous().unsqueeze(0), pa={}, pb={})
+    y = BF.pointwise_conv(a, cache["wa"], None, 1, pack_cache=cache["pa"])
+    return BF.pointwise_conv(b, cache["wb"], None, 1, residual=y, pack_cache=cache["pb"])
+
+
 class gdMlp(nn.Module):
     """Gated-Dconv MLP (vmamba.py:116-133)."""
 
@@ -142,19 +159,12 @@ class DualUpSample(nn.Module):
         pixels to convolve), and conv(cat([p, b])) = W_p p + W_b b is evaluated as two 1x1 launches, the second adding onto
         the first in its epilogue, instead of materialising the concatenation."""
         fast = (x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled() and self.up_b[3].bias is None
-                and self.conv.bias is None and isinstance(self.up_b[2], nn.Upsample) and self.up_b[2].mode == "bilinear")
+                and isinstance(self.up_b[2], nn.Upsample) and self.up_b[2].mode == "bilinear")
         if not fast:
             return self.conv(torch.cat([self.up_p(x), self.up_b(x)], dim=1))
         p = self.up_p(x)
         b = self.up_b[2](self.up_b[3](self.up_b[1](self.up_b[0](x))))
-        cp = p.shape[1]
-        cache = self.__dict__.setdefault("_split_cache", {})
-        key = (self.conv.weight.data_ptr(), self.conv.weight._version)
-        if cache.get("key") != key:
-            w = self.conv.weight.detach().view(self.conv.out_channels, -1)
-            cache.update(key=key, wp=w[:, :cp].contiguous().unsqueeze(0), wb=w[:, cp:].contiguous().unsqueeze(0), pc_p={}, pc_b={})
-        y = BF.pointwise_conv(p, cache["wp"], None, 1, pack_cache=cache["pc_p"])
-        return BF.pointwise_conv(b, cache["wb"], None, 1, residual=y, pack_cache=cache["pc_b"])
+        return conv1x1_of_cat(self.conv, p, b)
 
 
 class BasicBlock(nn.Module):
@@ -234,7 +244,7 @@ class SubNetwork(nn.Module):
         fea = self.bottleneck(fea)
         for i, (up, fusion, de_block) in enumerate(self.decoder_layers):
             fea = up(fea)
-            fea = fusion(torch.cat([fea, skips[self.level - 1 - i]], dim=1))
+            fea = conv1x1_of_cat(fusion, fea, skips[self.level - 1 - i])
             fea = de_block(fea)
         return x + self.drop_path(fea)
 
