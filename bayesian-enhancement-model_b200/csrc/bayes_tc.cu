@@ -406,11 +406,11 @@ __device__ __forceinline__ P3Item p3_item(const BemBayesPointwiseParams& p, int6
     return r;
 }
 
-template <bool LN>
+template <bool LN, bool TRACE = false>
 __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(const BemBayesPointwiseParams p, const int NT, const int ntiles,
                                                                           const int ptiles, const int64_t n_items,
                                                                           const float* __restrict__ pack, const float* __restrict__ vec,
-                                                                          const uint32_t RS, const uint32_t BS, const int b_resident, const int trace_on) {
+                                                                          const uint32_t RS, const uint32_t BS, const int b_resident) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t b_bytes = (uint32_t)NT * TC_KC * 4;
     unsigned char* s_raw = smem;
@@ -434,6 +434,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nk = (p.cin + TC_KC - 1) / TC_KC;
     Tracer tr;
+    constexpr int trace_on = TRACE ? 1 : 0;   // the timeline build is its own instantiation: no trace predicates in the product kernel
 
     if (tid == 0) {
         for (int i = 0; i < (int)RS; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], P3_XW / 2); }
@@ -788,10 +789,10 @@ int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t str
         const int64_t n_items = (int64_t)p.batch * ptiles * ntiles;
         if (n_items >= (1ll << 31)) return BEM_ERR_UNSUPPORTED;
         const int grid = (int)std::min<int64_t>(n_items, sms[dev]);
-        if (p.ln_gamma)
-            bayes_pointwise_tc3_kernel<true><<<grid, P3_THREADS, smem_bytes, stream>>>(p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS, b_resident, trace_on);
-        else
-            bayes_pointwise_tc3_kernel<false><<<grid, P3_THREADS, smem_bytes, stream>>>(p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS, b_resident, trace_on);
+        auto kernel = p.ln_gamma ? (trace_on ? bayes_pointwise_tc3_kernel<true, true> : bayes_pointwise_tc3_kernel<true, false>)
+                                 : (trace_on ? bayes_pointwise_tc3_kernel<false, true> : bayes_pointwise_tc3_kernel<false, false>);
+        if (trace_on) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        kernel<<<grid, P3_THREADS, smem_bytes, stream>>>(p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS, b_resident);
         return (int)cudaGetLastError();
     }
     uint32_t tmem_cols = 32;

@@ -326,3 +326,36 @@ def test_scan_fused_dt_proj_matches_projection_then_scan(Bn, G, Dg, L, R):
     assert nmax_err(xc.cpu().numpy(), xref.cpu().numpy()) < 1e-5
     out2, _ = ss.fwd(u, dtl, A, Bm, Cm, D, bias, True, 1, True, dt_weight=Wdt)
     assert torch.equal(out, out2)                                           # deterministic
+
+
+def test_classic_schedule_still_matches_the_deferred_one():
+    """fp32 / dstate-1 launches take the deferred-finish kernel (384-position tiles); the classic schedule (768-position
+    tiles) still serves 16-bit inputs and general dstate, and this shape under BEM_FWD_CLASSIC=1. The two associate the
+    recurrence differently across tiles, so they are compared at the fp32 parity tolerance, out and carries."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    from bem_b200 import selective_scan as ss
+    torch.manual_seed(21)
+    Bn, KD, G, N, L = 2, 16, 2, 1, 5000
+    u = torch.randn(Bn, KD, L, device="cuda")
+    dl = 0.5 * torch.randn(Bn, KD, L, device="cuda")
+    A = -torch.rand(KD, N, device="cuda") - 0.2
+    Bm = torch.randn(Bn, G, N, L, device="cuda")
+    Cm = torch.randn(Bn, G, N, L, device="cuda")
+    D = torch.randn(KD, device="cuda")
+    bias = torch.randn(KD, device="cuda")
+    out, x = ss.fwd(u, dl, A, Bm, Cm, D, bias, True, 1, True)
+    with tempfile.TemporaryDirectory() as td:
+        f = os.path.join(td, "io.pt")
+        torch.save({k: v.cpu() for k, v in dict(u=u, dl=dl, A=A, Bm=Bm, Cm=Cm, D=D, bias=bias).items()}, f)
+        code = ("import torch, sys; sys.path.insert(0, %r); from bem_b200 import selective_scan as ss; t = torch.load(%r);"
+                "t = {k: v.cuda() for k, v in t.items()};"
+                "o, x = ss.fwd(t['u'], t['dl'], t['A'], t['Bm'], t['Cm'], t['D'], t['bias'], True, 1, True);"
+                "torch.save({'o': o.cpu(), 'x': x.cpu()}, %r)") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), f, f + ".out")
+        env = dict(os.environ, BEM_FWD_CLASSIC="1")
+        subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
+        ref = torch.load(f + ".out")
+    assert nmax_err(out.cpu().numpy(), ref["o"].numpy()) < 2e-6
+    assert nmax_err(x.cpu().numpy(), ref["x"].numpy()) < 2e-6
