@@ -2,7 +2,7 @@
 
     selective scan      bem_b200.selective_scan_fn / SelectiveScanCuda / selective_scan_cuda_oflex / build_selective_scan_fn
     traversal           bem_b200.cross_scan_fn / cross_merge_fn
-    SS2D core           bem_b200.ss2d_core, bem_b200.SS2D
+    SS2D core           bem_b200.ss2d_core, bem_b200.ss2d_scan (fused operator), bem_b200.ss2d_fwd (C-ABI bem_ss2d_fwd), bem_b200.SS2D
     Bayesian layers     bem_b200.bayesian.{Conv2d,Linear2d,Linear}Reparameterization, convert2bnn*, set_prediction_type, ...
     MC inference        bem_b200.mc.{MCSampler, mc_infer, select_best}
     stage-1 network     bem_b200.network.{Network, build_model, build_bayesian_model}
@@ -16,6 +16,6 @@ from . import bayesian, mc, network, patch  # noqa: F401
 from .csm import CrossMergeF, CrossScanF, cross_merge_fn, cross_scan_fn  # noqa: F401
 from .selective_scan import (SelectiveScanCuda, build_selective_scan_fn, chunk_len, selective_scan_cuda_oflex,  # noqa: F401
                              selective_scan_fn, selective_scan_fn_test_api)
-from .ss2d import SS2D, LayerNorm2d, Linear2d, ss2d_core  # noqa: F401
+from .ss2d import SS2D, LayerNorm2d, Linear2d, ss2d_core, ss2d_fwd, ss2d_scan  # noqa: F401
 
 __version__ = "0.1.0"

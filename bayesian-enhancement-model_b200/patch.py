@@ -7,6 +7,8 @@
 What gets replaced:
   * `csms6s.selective_scan_fn` and the name imported into vmamba.py (basicsr/vmamba/models/vmamba.py:27-30)
   * `csm_triton.cross_scan_fn` / `cross_merge_fn` and the names imported into vmamba.py (:22-25)
+  * `SS2D.forward_corev2` (vmamba.py:547-698) by `ss2d.forward_corev2_patched` (one x_proj launch on the un-scanned x + the
+    fused bem_ss2d_fwd call at inference; the reference op sequence on this package's kernels when a gradient is needed)
   * the top-level `bayesian` package that basicsr/bayesian/tools.py:1 and the model wrappers import
 """
 from __future__ import annotations
@@ -18,6 +20,7 @@ def install(vmamba=None, csms6s=None, csm_triton=None, replace_bayesian=True):
     from . import bayesian as _bayes
     from .csm import cross_merge_fn, cross_scan_fn
     from .selective_scan import SelectiveScanCuda, selective_scan_cuda_oflex, selective_scan_fn
+    from .ss2d import forward_corev2_patched
 
     patched = []
     mods = dict(sys.modules)
@@ -39,6 +42,10 @@ def install(vmamba=None, csms6s=None, csm_triton=None, replace_bayesian=True):
             mod.selective_scan_fn = selective_scan_fn
             mod.cross_scan_fn = cross_scan_fn
             mod.cross_merge_fn = cross_merge_fn
+            for cls_name in ("SS2Dv2", "SS2D"):
+                cls = getattr(mod, cls_name, None)
+                if cls is not None and "forward_corev2" in vars(cls):
+                    cls.forward_corev2 = forward_corev2_patched
             patched.append(name)
     if replace_bayesian:
         sys.modules["bayesian"] = _bayes

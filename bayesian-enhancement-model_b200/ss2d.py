@@ -43,6 +43,39 @@ def ss2d_fwd(x, z, dt_weight, A, Dskip, delta_bias, dstate=1, delta_softplus=Tru
     return y
 
 
+def ss2d_scan(x, dts, As, Bs, Cs, Ds, delta_bias, H, W, delta_softplus=True, ssoflex=True, scans=0):
+    """Fused operator of the SS2D core: cross_scan -> selective scan -> cross_merge for already projected
+    inputs, i.e. vmamba.py:657 + :672-684 in one call.
+      x          : (B, D, H, W) (or (B, D, H*W)) image-order input of the scan
+      dts        : (B, K*D, L) delta before bias / softplus, in TRAVERSAL order (as forward_corev2 computes it from xs)
+      As         : (K*D, N);  Bs, Cs : (B, K, N, L) traversal order;  Ds, delta_bias : (K*D) or None
+    -> y : (B, D, L), the four directions merged back to image order (before out_norm). Differentiable: it composes the
+    autograd functions of cross_scan_fn / selective_scan_fn / cross_merge_fn."""
+    B, D = x.shape[0], x.shape[1]
+    x = x.reshape(B, D, H, W)
+    K = Bs.shape[1]
+    xs = cross_scan_fn(x, in_channel_first=True, out_channel_first=True, scans=scans)            # (B, K, D, L)
+    ys = selective_scan_fn(xs.view(B, -1, H * W), dts, As, Bs, Cs, Ds, delta_bias, delta_softplus, ssoflex)
+    return cross_merge_fn(ys.view(B, K, -1, H, W), in_channel_first=True, out_channel_first=True, scans=scans)
+
+
+def forward_corev2_patched(self, x=None, force_fp32=False, ssoflex=True, no_einsum=False, selective_scan_backend=None,
+                           scan_mode="cross2d", scan_force_torch=False, **kwargs):
+    """Replacement for SS2Dv2.forward_corev2 (vmamba.py:547-698) installed by bem_b200.patch: same signature, same result,
+    the whole core on this package's kernels (ss2d_core). Modes this package does not build raise instead of falling
+    back; channel_last SS2D (unused by the BEM archs) permutes around the channel-first core."""
+    if selective_scan_backend not in (None, "oflex"):
+        raise RuntimeError(f"bem_b200: selective_scan_backend {selective_scan_backend!r} is not built (oflex only)")
+    if scan_mode == "cascade2d":
+        raise RuntimeError("bem_b200: scan_mode 'cascade2d' is not built (cross2d / unidi / bidi)")
+    y = ss2d_core(x, self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias, self.A_logs, self.Ds,
+                  x_proj_bias=getattr(self, "x_proj_bias", None), out_norm=None, scan_mode=scan_mode, force_fp32=force_fp32,
+                  ssoflex=ssoflex, pack_cache=self.__dict__.setdefault("_pack_cache", {}))
+    if not self.channel_first:
+        y = y.permute(0, 2, 3, 1).contiguous()
+    return self.out_norm(y).to(x.dtype)
+
+
 def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias=None, out_norm=None,
               scan_mode="cross2d", force_fp32=False, ssoflex=True, delta_softplus=True, pack_cache=None):
     """x: (B, D, H, W) -> y: (B, D, H, W) (after `out_norm` when given), following vmamba.py:656-698 line by line:
