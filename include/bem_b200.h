@@ -204,10 +204,11 @@ int bem_ss2d_fwd(const BemSs2dFwdParams* p, void* stream);
  *     eps_out != NULL -> the eps used is also written there (what the reference leaves in eps_weight).
  * bem_bayes_pointwise : 1x1 convolution / Linear2d with per-sample weights on tcgen05 (3xTF32: fp32-accurate)
  *     x : (S*Bx, Cin, P)  w : (S or 1, Cout, Cin)  bias : (S or 1, Cout) or NULL  out : (S*Bx, Cout, P), fp32
- *     mu/sigma/eps given instead of w  -> the sample step w = mu + sigma * eps is fused into the weight load;
- *     ln_gamma given -> the LayerNorm2d that precedes the layer (vmamba.py:59-64, eps = ln_eps) is fused in as well.
+ *     mu/sigma/eps given instead of w  -> the sample step w = mu + sigma * eps is fused into the weight pack;
+ *     ln_gamma given -> the LayerNorm2d that precedes the layer (vmamba.py:59-64, eps = ln_eps) is fused in as well;
+ *     residual given -> out = residual + conv (the block's skip connection); prepacked -> weights packed by an earlier call.
  * bem_bayes_depthwise : depthwise KxK (groups == channels, stride 1, dilation 1, zero padding K/2), K in {3}
- *     x : (S*Bx, C, H, W)  w : (S or 1, C, K, K)  bias : (S or 1, C) or NULL
+ *     x : (S*Bx, C, H, W)  w : (S or 1, C, K, K)  bias : (S or 1, C) or NULL; `act` fuses the SiLU / gated GELU that follows
  * ---------------------------------------------------------------------------------------------- */
 typedef struct BemBayesSampleParams {
     int64_t numel;       /* elements of one weight tensor */
