@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libbem_b200.so")
 
 BEM_F32, BEM_F16, BEM_BF16 = 0, 1, 2
 BEM_OK, BEM_ERR_BAD_ARG, BEM_ERR_WORKSPACE, BEM_ERR_UNSUPPORTED = 0, 10001, 10002, 10003
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 i32, i64, u64, vp = C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
 
@@ -54,7 +54,7 @@ class BemBayesPointwiseParams(C.Structure):
     _fields_ = [(n, i32) for n in ("n_samples", "batch", "cin", "cout")] + [("P", i64)] + \
                [(n, vp) for n in ("x", "w", "mu", "rho", "eps", "bias", "out", "sigma", "ln_gamma", "ln_beta")] + \
                [("ln_eps", C.c_float), ("force_simt", i32), ("x_img_stride", i64), ("sample_interleave", i32),
-                ("workspace", vp), ("workspace_bytes", i64), ("residual", vp), ("prepacked", i32)]
+                ("workspace", vp), ("workspace_bytes", i64), ("residual", vp), ("prelu_slope", vp), ("prelu_n", i32), ("prepacked", i32)]
 
 
 class BemBayesDepthwiseParams(C.Structure):

@@ -67,7 +67,7 @@ def sample_weights(mu, rho, eps=None, n_samples=1, seed=0, stream_id=0, sample0=
 
 # ---------------------------------------------------------------------------------------------------
 def _pointwise_raw(x, w=None, bias=None, mu=None, sigma=None, eps=None, n_samples=1, ln=None, force_simt=False,
-                   interleave=False, residual=None, pack_cache=None):
+                   interleave=False, residual=None, pack_cache=None, prelu=None):
     """x: (S*Bx, Cin, *spatial) fp32 — any image stride, channels P apart; w: (S|1, Cout, Cin) or mu/sigma/eps for the
     fused sample-on-load path; ln = (gamma, beta, eps): LayerNorm over the channels of every pixel fused into the
     activation staging; interleave: image i uses weight set i % S instead of i // Bx; residual: (batch, Cout, *spatial)
@@ -98,6 +98,9 @@ def _pointwise_raw(x, w=None, bias=None, mu=None, sigma=None, eps=None, n_sample
         residual = _f32c(residual, "residual")
         if tuple(residual.shape) != tuple(out.shape):
             raise RuntimeError(f"pointwise conv: residual {tuple(residual.shape)} does not match output {tuple(out.shape)}")
+    prelu = _f32c(prelu, "prelu slope")
+    if prelu is not None and prelu.numel() not in (1, cout):
+        raise RuntimeError(f"pointwise conv: PReLU with {prelu.numel()} slopes does not match {cout} output channels")
     need = lib.bem_bayes_pointwise_workspace_bytes(n_samples, cin, cout)
     prepacked = 0
     if pack_cache is not None and not force_simt:
@@ -118,7 +121,8 @@ def _pointwise_raw(x, w=None, bias=None, mu=None, sigma=None, eps=None, n_sample
                                      out=_lib.ptr(out), sigma=_lib.ptr(sigma), ln_gamma=_lib.ptr(g), ln_beta=_lib.ptr(b),
                                      ln_eps=ln_eps, force_simt=int(bool(force_simt)), x_img_stride=int(img_stride),
                                      sample_interleave=int(bool(interleave)), workspace=_lib.ptr(ws), workspace_bytes=ws.numel(),
-                                     residual=_lib.ptr(residual), prepacked=prepacked)
+                                     residual=_lib.ptr(residual), prepacked=prepacked, prelu_slope=_lib.ptr(prelu),
+                                     prelu_n=0 if prelu is None else prelu.numel())
     _lib.launch("bayes_pointwise", lib.bem_bayes_pointwise, p, x.device, key=(batch, cin, cout, P),
                 nbytes=4 * batch * P * (cin + cout * (2 if residual is not None else 1)), kernels=1 if (force_simt or prepacked) else 2)
     return out
@@ -162,16 +166,17 @@ def grouped_pointwise(x, w, bias=None):
     return out.view(B, K, -1, L)
 
 
-def pointwise_conv(x, w, bias=None, n_samples=1, ln=None, force_simt=False, residual=None, pack_cache=None):
+def pointwise_conv(x, w, bias=None, n_samples=1, ln=None, force_simt=False, residual=None, pack_cache=None, prelu=None):
     """out[img] = w[s(img)] @ LN(x[img]) + bias[s(img)] (+ residual[img]); w: (S, Cout, Cin), bias: (S, Cout) | None.
     ln = (gamma, beta, eps) fuses the preceding LayerNorm2d, residual the skip connection (both inference only)."""
     if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or (bias is not None and bias.requires_grad)):
         if ln is not None:
             raise RuntimeError("the fused LayerNorm path has no backward; apply the norm module separately when training")
         y = _PointwiseFn.apply(x, w, bias, n_samples)
-        return y if residual is None else residual + y
+        y = y if residual is None else residual + y
+        return y if prelu is None else torch.nn.functional.prelu(y, prelu)
     return _pointwise_raw(x, w=w, bias=bias, n_samples=n_samples, ln=ln, force_simt=force_simt, residual=residual,
-                          pack_cache=pack_cache)
+                          pack_cache=pack_cache, prelu=prelu)
 
 
 def pointwise_conv_sampled(x, mu, sigma, eps, bias=None, n_samples=1, ln=None, force_simt=False, residual=None):

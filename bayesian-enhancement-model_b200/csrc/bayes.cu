@@ -189,6 +189,13 @@ __global__ void __launch_bounds__(256) bayes_pointwise_kernel(const BemBayesPoin
                 if (pp + 2 < p.P) v.z += rs[2];
                 if (pp + 3 < p.P) v.w += rs[3];
             }
+            if (p.prelu_slope) {
+                const float sl = p.prelu_slope[p.prelu_n > 1 ? co : 0];
+                v.x = v.x > 0.f ? v.x : v.x * sl;
+                v.y = v.y > 0.f ? v.y : v.y * sl;
+                v.z = v.z > 0.f ? v.z : v.z * sl;
+                v.w = v.w > 0.f ? v.w : v.w * sl;
+            }
             if (vec_ok && pp + 3 < p.P) *reinterpret_cast<float4*>(dst) = v;
             else {
                 if (pp + 0 < p.P) dst[0] = v.x;
@@ -585,6 +592,7 @@ int bem_bayes_pointwise(const BemBayesPointwiseParams* p, void* stream) {
         return BEM_ERR_BAD_ARG;
     if (p->batch % p->n_samples != 0) return BEM_ERR_BAD_ARG;
     if (!p->w && !p->mu) return BEM_ERR_BAD_ARG;
+    if (p->prelu_slope && p->prelu_n != 1 && p->prelu_n != p->cout) return BEM_ERR_BAD_ARG;
     if (!p->w && (p->rho || p->sigma) && !p->eps) return BEM_ERR_BAD_ARG;
     if (p->batch > 65535) return BEM_ERR_UNSUPPORTED;
     if (!p->force_simt) return bayes_pointwise_tc_launch(*p, (cudaStream_t)stream);

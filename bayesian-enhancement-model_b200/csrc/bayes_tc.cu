@@ -330,7 +330,9 @@ __global__ void __launch_bounds__(128, 4) bayes_pointwise_tc_kernel(const BemBay
                 if (c0 + i < nvalid) {
                     const float b = p.bias ? p.bias[(int64_t)s_idx * p.cout + co] : 0.f;
                     const int64_t oi = (int64_t)co * p.P + pix;
-                    out[oi] = v[i] + b + (p.residual ? p.residual[(int64_t)img * p.cout * p.P + oi] : 0.f);
+                    float r = v[i] + b + (p.residual ? p.residual[(int64_t)img * p.cout * p.P + oi] : 0.f);
+                    if (p.prelu_slope) r = r > 0.f ? r : r * p.prelu_slope[p.prelu_n > 1 ? co : 0];
+                    out[oi] = r;
                 }
             }
         }
@@ -673,6 +675,8 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
             const float* res = p.residual ? p.residual + obase : nullptr;
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * P3_ACC_COLS;
             const float2* sv = s_vec + (w.s_idx * ntiles + w.tile) * NT;
+            const float* slope = p.prelu_slope;                 // PReLU after the conv (uniform branch), one slope or one per channel
+            const int slope_step = p.prelu_n > 1 ? 1 : 0;
             const int ngrp = (nvalid + 15) >> 4;
             for (int gi = half; gi < ngrp; gi += 2) {
                 const int c0 = gi * 16;
@@ -688,20 +692,30 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
                     for (int i = 0; i < 16; ++i, rp += P)
                         if (c0 + i < nvalid) rv[i] = *rp;
                 }
+                // per-channel affine (+ skip connection) on the 16 values; the optional PReLU is one uniform branch per group,
+                // kept out of the store loop (a per-element predicate there doubles the epilogue of the write-heavy layers)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float2 st = sv[c0 + i];   // c0 + i < NT: groups of 16 within the NT-padded tile
+                    v[i] = (LN ? fmaf(rstd, v[i], fmaf(nmr, st.x, st.y)) : v[i] + st.y) + rv[i];
+                }
+                if (slope != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float sl = slope[min(n0 + c0 + i, p.cout - 1) * slope_step];
+                        v[i] = v[i] > 0.f ? v[i] : v[i] * sl;
+                    }
+                }
                 if (c0 + 16 <= nvalid) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float2 st = sv[c0 + i];
-                        const float r = (LN ? fmaf(rstd, v[i], fmaf(nmr, st.x, st.y)) : v[i] + st.y) + rv[i];
-                        if (valid) *o = r;
+                        if (valid) *o = v[i];
                         o += P;
                     }
                 } else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float2 st = sv[min(c0 + i, NT - 1)];
-                        const float r = (LN ? fmaf(rstd, v[i], fmaf(nmr, st.x, st.y)) : v[i] + st.y) + rv[i];
-                        if (valid && c0 + i < nvalid) *o = r;
+                        if (valid && c0 + i < nvalid) *o = v[i];
                         o += P;
                     }
                 }

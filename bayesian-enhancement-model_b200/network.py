@@ -33,21 +33,25 @@ class Conv2d(nn.Conv2d):
     def _fuses_norm(self):
         return self._is_1x1()
 
-    def forward(self, x, pre_norm=None):
-        """pre_norm: a LayerNorm2d that precedes the conv (PatchMerging, UNet_arch.py:80-82), fused when the kernel runs"""
+    def forward(self, x, pre_norm=None, post_prelu=None):
+        """pre_norm: a LayerNorm2d that precedes the conv (PatchMerging, UNet_arch.py:80-82); post_prelu: an nn.PReLU that
+        follows it (DualUpSample); both fused when the 1x1 kernel runs, applied separately otherwise"""
         if (self._is_1x1() and x.is_cuda and x.dtype == torch.float32 and self.weight.dtype == torch.float32
                 and not (torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad))):
             w = self.weight.view(1, self.out_channels, self.in_channels)
             ln = None if pre_norm is None else (pre_norm.weight, pre_norm.bias, pre_norm.eps)
             cache = self.__dict__.setdefault("_pack_cache", {})   # constant weights: packed once, reused by every call
-            return BF.pointwise_conv(x, w, None if self.bias is None else self.bias.view(1, -1), 1, ln=ln, pack_cache=cache)
+            return BF.pointwise_conv(x, w, None if self.bias is None else self.bias.view(1, -1), 1, ln=ln, pack_cache=cache,
+                                     prelu=None if post_prelu is None else post_prelu.weight)
         if (pre_norm is None and self.kernel_size == (3, 3) and self.stride == (1, 1) and self.padding == (1, 1)
                 and self.dilation == (1, 1) and self.groups == 1 and self.padding_mode == "zeros"
                 and min(self.in_channels, self.out_channels) <= 8 and self.in_channels * 9 * 8 * 4 <= 48 * 1024
                 and x.is_cuda and x.dtype == torch.float32 and self.weight.dtype == torch.float32
                 and not (torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad))):
-            return BF.conv3x3_direct(x, self.weight, self.bias)     # the full-resolution stems (first_conv, proj)
-        return super().forward(x if pre_norm is None else pre_norm(x))
+            y = BF.conv3x3_direct(x, self.weight, self.bias)     # the full-resolution stems (first_conv, proj)
+            return y if post_prelu is None else post_prelu(y)
+        y = super().forward(x if pre_norm is None else pre_norm(x))
+        return y if post_prelu is None else post_prelu(y)
 
 
 def conv1x1_of_cat(conv, a, b):
@@ -162,8 +166,13 @@ class DualUpSample(nn.Module):
                 and isinstance(self.up_b[2], nn.Upsample) and self.up_b[2].mode == "bilinear")
         if not fast:
             return self.conv(torch.cat([self.up_p(x), self.up_b(x)], dim=1))
-        p = self.up_p(x)
-        b = self.up_b[2](self.up_b[3](self.up_b[1](self.up_b[0](x))))
+        prelu_ok = isinstance(self.up_p[1], nn.PReLU) and isinstance(self.up_b[1], nn.PReLU) and isinstance(self.up_p[0], Conv2d)
+        if prelu_ok:   # conv -> PReLU in one launch
+            p = self.up_p[3](self.up_p[2](self.up_p[0](x, post_prelu=self.up_p[1])))
+            b = self.up_b[2](self.up_b[3](self.up_b[0](x, post_prelu=self.up_b[1])))
+        else:
+            p = self.up_p(x)
+            b = self.up_b[2](self.up_b[3](self.up_b[1](self.up_b[0](x))))
         return conv1x1_of_cat(self.conv, p, b)
 
 

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define BEM_ABI_VERSION 9
+#define BEM_ABI_VERSION 10
 
 /* element types of u/delta/B/C/x-activations */
 enum { BEM_F32 = 0, BEM_F16 = 1, BEM_BF16 = 2 };
@@ -272,6 +272,9 @@ typedef struct BemBayesPointwiseParams {
     int64_t workspace_bytes;
     const float* residual;  /* (batch, cout, P) or NULL: out = residual + conv(x) — the block's skip connection
                                (vmamba.py:1331-1333) folded into the epilogue; may alias `out` */
+    const float* prelu_slope; /* NULL, or the negative slope(s) of the nn.PReLU that follows the conv (DualUpSample,
+                                 basicsr/archs/UNet_arch.py:113-135): out = v > 0 ? v : slope * v, applied last */
+    int32_t prelu_n;          /* number of slopes: 1 (nn.PReLU() default) or cout */
     int32_t prepacked;      /* 1: `workspace` still holds the packed tiles written by an earlier call with the same weights,
                                bias, LayerNorm parameters, n_samples / cin / cout and the same alignment class of x
                                (deterministic layers: pack once, reuse) — the pack kernel is skipped */

@@ -385,3 +385,24 @@ def test_conv3x3_direct_matches_conv2d(B, cin, cout, H, W):
         y = conv(x)
     if min(cin, cout) <= 8:
         assert nmax_err(y.cpu().numpy(), ref.cpu().numpy()) < TOL
+
+
+@pytest.mark.parametrize("cin,cout,H,W,nslopes", [(160, 320, 10, 12, 1), (80, 80, 7, 5, 1), (24, 40, 8, 8, 40)])
+def test_pointwise_fused_prelu(cin, cout, H, W, nslopes):
+    """nn.PReLU after a 1x1 conv (DualUpSample, UNet_arch.py:113-135) folded into the epilogue, tensor-core kernels (aligned and
+    unaligned inputs) and CUDA-core kernel; single slope and per-channel slopes"""
+    import torch.nn.functional as F
+    from bem_b200 import network
+    from bem_b200.bayesian import functional as BF
+    torch.manual_seed(cin + cout)
+    conv = network.Conv2d(cin, cout, 1, bias=True).cuda()
+    act = torch.nn.PReLU(nslopes).cuda()
+    with torch.no_grad():
+        act.weight.uniform_(0.05, 0.4)
+    x = torch.randn(2, cin, H, W, device="cuda")
+    with torch.no_grad():
+        y = conv(x, post_prelu=act)
+        ref = F.prelu(F.conv2d(x.double(), conv.weight.double(), conv.bias.double()), act.weight.double())
+        simt = BF.pointwise_conv(x, conv.weight.view(1, cout, cin), conv.bias.view(1, -1), 1, force_simt=True, prelu=act.weight)
+    assert nmax_err(y.cpu().numpy(), ref.cpu().numpy()) < TOL
+    assert nmax_err(simt.cpu().numpy(), ref.cpu().numpy()) < TOL
