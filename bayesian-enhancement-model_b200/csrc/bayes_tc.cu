@@ -412,7 +412,7 @@ __device__ __forceinline__ P3Item p3_item(const BemBayesPointwiseParams& p, int6
     return r;
 }
 
-template <bool LN, bool TRACE = false>
+template <bool LN, bool TRACE = false, bool PRELU = false>
 __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(const BemBayesPointwiseParams p, const int NT, const int ntiles,
                                                                           const int ptiles, const int64_t n_items,
                                                                           const float* __restrict__ pack, const float* __restrict__ vec,
@@ -692,30 +692,24 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
                     for (int i = 0; i < 16; ++i, rp += P)
                         if (c0 + i < nvalid) rv[i] = *rp;
                 }
-                // per-channel affine (+ skip connection) on the 16 values; the optional PReLU is one uniform branch per group,
-                // kept out of the store loop (a per-element predicate there doubles the epilogue of the write-heavy layers)
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float2 st = sv[c0 + i];   // c0 + i < NT: groups of 16 within the NT-padded tile
-                    v[i] = (LN ? fmaf(rstd, v[i], fmaf(nmr, st.x, st.y)) : v[i] + st.y) + rv[i];
-                }
-                if (slope != nullptr) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float sl = slope[min(n0 + c0 + i, p.cout - 1) * slope_step];
-                        v[i] = v[i] > 0.f ? v[i] : v[i] * sl;
-                    }
-                }
+                // per-channel affine (+ skip connection) (+ PReLU: its own instantiation — even one uniform branch per group
+                // here costs the write-heavy layers 4-6 %, a per-element predicate doubles their epilogue)
                 if (c0 + 16 <= nvalid) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        if (valid) *o = v[i];
+                        const float2 st = sv[c0 + i];
+                        float r = (LN ? fmaf(rstd, v[i], fmaf(nmr, st.x, st.y)) : v[i] + st.y) + rv[i];
+                        if constexpr (PRELU) r = r > 0.f ? r : r * slope[(n0 + c0 + i) * slope_step];
+                        if (valid) *o = r;
                         o += P;
                     }
                 } else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        if (valid && c0 + i < nvalid) *o = v[i];
+                        const float2 st = sv[c0 + i];   // c0 + i < NT: groups of 16 within the NT-padded tile
+                        float r = (LN ? fmaf(rstd, v[i], fmaf(nmr, st.x, st.y)) : v[i] + st.y) + rv[i];
+                        if constexpr (PRELU) r = r > 0.f ? r : r * slope[min(n0 + c0 + i, p.cout - 1) * slope_step];
+                        if (valid && c0 + i < nvalid) *o = r;
                         o += P;
                     }
                 }
@@ -809,7 +803,8 @@ int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t str
         const int grid = (int)std::min<int64_t>(n_items, sms[dev]);
         auto kernel = p.ln_gamma ? (trace_on ? bayes_pointwise_tc3_kernel<true, true> : bayes_pointwise_tc3_kernel<true, false>)
                                  : (trace_on ? bayes_pointwise_tc3_kernel<false, true> : bayes_pointwise_tc3_kernel<false, false>);
-        if (trace_on) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (p.prelu_slope) kernel = p.ln_gamma ? bayes_pointwise_tc3_kernel<true, false, true> : bayes_pointwise_tc3_kernel<false, false, true>;
+        if (trace_on || p.prelu_slope) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         kernel<<<grid, P3_THREADS, smem_bytes, stream>>>(p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS, b_resident);
         return (int)cudaGetLastError();
     }
