@@ -175,6 +175,9 @@ def pointwise_conv(x, w, bias=None, n_samples=1, ln=None, force_simt=False, resi
         y = _PointwiseFn.apply(x, w, bias, n_samples)
         y = y if residual is None else residual + y
         return y if prelu is None else torch.nn.functional.prelu(y, prelu)
+    if residual is not None and prelu is not None and not force_simt:   # not a combination the tensor-core epilogue is built for
+        y = _pointwise_raw(x, w=w, bias=bias, n_samples=n_samples, ln=ln, residual=residual, pack_cache=pack_cache)
+        return torch.nn.functional.prelu(y, prelu)
     return _pointwise_raw(x, w=w, bias=bias, n_samples=n_samples, ln=ln, force_simt=force_simt, residual=residual,
                           pack_cache=pack_cache, prelu=prelu)
 

@@ -412,7 +412,9 @@ __device__ __forceinline__ P3Item p3_item(const BemBayesPointwiseParams& p, int6
     return r;
 }
 
-template <bool LN, bool TRACE = false, bool PRELU = false>
+// EPI: what the epilogue adds to the per-channel affine — 0 nothing, 1 the skip connection (`residual`), 2 a PReLU. Separate
+// instantiations: the store loop of the write-heavy layers is sensitive to every extra instruction and branch.
+template <bool LN, bool TRACE = false, int EPI = 0>
 __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(const BemBayesPointwiseParams p, const int NT, const int ntiles,
                                                                           const int ptiles, const int64_t n_items,
                                                                           const float* __restrict__ pack, const float* __restrict__ vec,
@@ -672,7 +674,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
             const int64_t P = p.P;
             const int64_t obase = ((int64_t)w.img * p.cout + n0) * P + w.p0 + m;
             float* out = p.out + obase;
-            const float* res = p.residual ? p.residual + obase : nullptr;
+            const float* res = EPI == 1 ? p.residual + obase : nullptr;
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * P3_ACC_COLS;
             const float2* sv = s_vec + (w.s_idx * ntiles + w.tile) * NT;
             const float* slope = p.prelu_slope;                 // PReLU after the conv (uniform branch), one slope or one per channel
@@ -683,14 +685,16 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
                 float v[16];
                 tmem_ld16(taddr + (uint32_t)c0, v);
                 float* o = out + (int64_t)c0 * P;
-                float rv[16];
+                float rv[EPI == 1 ? 16 : 1];
+                if constexpr (EPI == 1) {   // skip connection: the loads go out together, ahead of the stores
 #pragma unroll
-                for (int i = 0; i < 16; ++i) rv[i] = 0.f;
-                if (res != nullptr && valid) {   // skip connection: the loads go out together, ahead of the stores
-                    const float* rp = res + (int64_t)c0 * P;
+                    for (int i = 0; i < 16; ++i) rv[i] = 0.f;
+                    if (valid) {
+                        const float* rp = res + (int64_t)c0 * P;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i, rp += P)
-                        if (c0 + i < nvalid) rv[i] = *rp;
+                        for (int i = 0; i < 16; ++i, rp += P)
+                            if (c0 + i < nvalid) rv[i] = *rp;
+                    }
                 }
                 // per-channel affine (+ skip connection) (+ PReLU: its own instantiation — even one uniform branch per group
                 // here costs the write-heavy layers 4-6 %, a per-element predicate doubles their epilogue)
@@ -698,8 +702,9 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const float2 st = sv[c0 + i];
-                        float r = (LN ? fmaf(rstd, v[i], fmaf(nmr, st.x, st.y)) : v[i] + st.y) + rv[i];
-                        if constexpr (PRELU) r = r > 0.f ? r : r * slope[(n0 + c0 + i) * slope_step];
+                        float r = LN ? fmaf(rstd, v[i], fmaf(nmr, st.x, st.y)) : v[i] + st.y;
+                        if constexpr (EPI == 1) r += rv[i];
+                        if constexpr (EPI == 2) r = r > 0.f ? r : r * slope[(n0 + c0 + i) * slope_step];
                         if (valid) *o = r;
                         o += P;
                     }
@@ -707,8 +712,9 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const float2 st = sv[c0 + i];   // c0 + i < NT: groups of 16 within the NT-padded tile
-                        float r = (LN ? fmaf(rstd, v[i], fmaf(nmr, st.x, st.y)) : v[i] + st.y) + rv[i];
-                        if constexpr (PRELU) r = r > 0.f ? r : r * slope[min(n0 + c0 + i, p.cout - 1) * slope_step];
+                        float r = LN ? fmaf(rstd, v[i], fmaf(nmr, st.x, st.y)) : v[i] + st.y;
+                        if constexpr (EPI == 1) r += rv[i];
+                        if constexpr (EPI == 2) r = r > 0.f ? r : r * slope[min(n0 + c0 + i, p.cout - 1) * slope_step];
                         if (valid && c0 + i < nvalid) *o = r;
                         o += P;
                     }
@@ -803,8 +809,10 @@ int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t str
         const int grid = (int)std::min<int64_t>(n_items, sms[dev]);
         auto kernel = p.ln_gamma ? (trace_on ? bayes_pointwise_tc3_kernel<true, true> : bayes_pointwise_tc3_kernel<true, false>)
                                  : (trace_on ? bayes_pointwise_tc3_kernel<false, true> : bayes_pointwise_tc3_kernel<false, false>);
-        if (p.prelu_slope) kernel = p.ln_gamma ? bayes_pointwise_tc3_kernel<true, false, true> : bayes_pointwise_tc3_kernel<false, false, true>;
-        if (trace_on || p.prelu_slope) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (p.residual && p.prelu_slope) return BEM_ERR_UNSUPPORTED;   // no caller combines them (the PReLU layers have no skip)
+        if (p.prelu_slope) kernel = p.ln_gamma ? bayes_pointwise_tc3_kernel<true, false, 2> : bayes_pointwise_tc3_kernel<false, false, 2>;
+        if (p.residual) kernel = p.ln_gamma ? bayes_pointwise_tc3_kernel<true, false, 1> : bayes_pointwise_tc3_kernel<false, false, 1>;
+        if (trace_on || p.prelu_slope || p.residual) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         kernel<<<grid, P3_THREADS, smem_bytes, stream>>>(p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS, b_resident);
         return (int)cudaGetLastError();
     }
