@@ -14,67 +14,69 @@ def _layer_cls(name):
         raise AttributeError(f"module 'bayesian' has no attribute '{name}'")
 
 
-def bnn_linear_layer(params, d):
-    layer_fn = _layer_cls(d.__class__.__name__ + "Reparameterization")
-    bnn_layer = layer_fn(in_features=d.in_features, out_features=d.out_features, bias=d.bias is not None,
-                         decay=params["decay"], sigma_init=params["sigma_init"])
+_LINEAR_ARGS = ("in_features", "out_features")
+_CONV_ARGS = ("in_channels", "out_channels", "kernel_size", "stride", "padding", "dilation", "groups")
+
+
+def _reparameterize(params, src, geometry):
+    """Bayesian twin of the deterministic layer `src`: same geometry (the attributes named in `geometry`), the twin's class
+    looked up by name as the reference does (`<ClassName>Reparameterization`, tools.py:5,25); with params["pretrain"] the
+    posterior and prior means start from the deterministic weights (tools.py:11-18, 37-44)."""
+    twin_cls = _layer_cls(type(src).__name__ + "Reparameterization")
+    kwargs = {k: getattr(src, k) for k in geometry}
+    twin = twin_cls(bias=src.bias is not None, decay=params["decay"], sigma_init=params["sigma_init"], **kwargs)
     if params["pretrain"]:
-        bnn_layer.mu_weight.data.copy_(d.weight.data)
-        bnn_layer.prior_mu_weight.data.copy_(d.weight.data)
-        if bnn_layer.bias:
-            bnn_layer.mu_bias.data.copy_(d.bias.data)
-            bnn_layer.prior_mu_bias.data.copy_(d.bias.data)
-    return bnn_layer
+        pairs = [("weight", src.weight)] + ([("bias", src.bias)] if twin.bias else [])
+        for which, value in pairs:
+            for target in ("mu_", "prior_mu_"):
+                getattr(twin, target + which).data.copy_(value.data)
+    return twin
+
+
+def bnn_linear_layer(params, d):
+    return _reparameterize(params, d, _LINEAR_ARGS)
 
 
 def bnn_conv_layer(params, d):
-    layer_fn = _layer_cls(d.__class__.__name__ + "Reparameterization")
-    bnn_layer = layer_fn(in_channels=d.in_channels, out_channels=d.out_channels, kernel_size=d.kernel_size,
-                         stride=d.stride, padding=d.padding, dilation=d.dilation, groups=d.groups,
-                         bias=d.bias is not None, decay=params["decay"], sigma_init=params["sigma_init"])
-    if params["pretrain"]:
-        bnn_layer.mu_weight.data.copy_(d.weight.data)
-        bnn_layer.prior_mu_weight.data.copy_(d.weight.data)
-        if bnn_layer.bias:
-            bnn_layer.mu_bias.data.copy_(d.bias.data)
-            bnn_layer.prior_mu_bias.data.copy_(d.bias.data)
-    return bnn_layer
-
-
-def convert2bnn_selective(model, config):
-    for name, module in model.named_modules():
-        if getattr(module, 'bayesian', False):
-            convert2bnn(module, config)
+    return _reparameterize(params, d, _CONV_ARGS)
 
 
 def convert2bnn(m, config):
-    for name, value in list(m._modules.items()):
-        if m._modules[name]._modules:
-            convert2bnn(m._modules[name], config)
-        elif "Linear" in m._modules[name].__class__.__name__:
-            setattr(m, name, bnn_linear_layer(config, m._modules[name]))
-        elif "Conv" in m._modules[name].__class__.__name__:
-            setattr(m, name, bnn_conv_layer(config, m._modules[name]))
-        else:
-            pass
-    return
+    """Replace, in place and recursively, every leaf child whose class name contains "Linear" / "Conv" by its Bayesian twin
+    (tools.py:52-63: containers are descended into, leaves are matched by class NAME, "Linear" tested first)."""
+    for child_name, child in list(m.named_children()):
+        if len(child._modules) > 0:
+            convert2bnn(child, config)
+            continue
+        cls_name = type(child).__name__
+        builder = bnn_linear_layer if "Linear" in cls_name else bnn_conv_layer if "Conv" in cls_name else None
+        if builder is not None:
+            setattr(m, child_name, builder(config, child))
+
+
+def convert2bnn_selective(model, config):
+    """convert2bnn on every sub-module flagged `.bayesian = True` (tools.py:47-50)."""
+    flagged = [mod for mod in model.modules() if getattr(mod, "bayesian", False)]
+    for mod in flagged:
+        convert2bnn(mod, config)
 
 
 def set_prediction_type(model, deterministic=True):
-    for name, module in model.named_modules():
-        if hasattr(module, 'deterministic'):
-            module.deterministic = bool(deterministic)
+    """switch every layer that has a `.deterministic` flag (tools.py:65-73)"""
+    for mod in model.modules():
+        if hasattr(mod, "deterministic"):
+            mod.deterministic = bool(deterministic)
 
 
 def get_kl_loss(m):
-    kl_loss = None
-    for layer in m.modules():
-        if hasattr(layer, "kl_loss"):
-            if kl_loss is None:
-                kl_loss = layer.kl_loss()
-            else:
-                kl_loss += layer.kl_loss()
-    return kl_loss
+    """sum of `.kl_loss()` over the layers that define it; None when there is none (tools.py:76-84)"""
+    terms = [layer.kl_loss() for layer in m.modules() if hasattr(layer, "kl_loss")]
+    if not terms:
+        return None
+    total = terms[0]
+    for t in terms[1:]:
+        total = total + t
+    return total
 
 
 # ---------------------------------------------------------------------------------------------------------------------
