@@ -1,5 +1,5 @@
 """One pass over the hot-path kernels at their level-0 (600x400) shapes, each launched twice (the second launch is the one
-to read in an ncu capture): `ncu --set full -k regex:'scan_|pointwise_tc3|depthwise3|csm_' python tools/profile_all_once.py`."""
+to read in an ncu capture): `ncu --set full -k regex:'scan_|pointwise_tc3|depthwise3|csm_|conv3x3' python tools/profile_all_once.py`."""
 import os
 import sys
 
@@ -38,6 +38,8 @@ for rep in range(2):
     BF.pointwise_conv(x40, w(40, 40), None, 1, ln=ln40)                                        # SS2D.in_proj
     BF.depthwise_conv3x3(x320, torch.randn(1, 320, 3, 3, device=dev), torch.randn(1, 320, device=dev), 1, act="gelu_gate")
     BF.depthwise_conv3x3(x40, torch.randn(1, 40, 3, 3, device=dev), torch.randn(1, 40, device=dev), 1, act="silu")
+    BF.conv3x3_direct(torch.randn(1, 3, H, W, device=dev), torch.randn(40, 3, 3, 3, device=dev), torch.randn(40, device=dev))   # first_conv
+    BF.conv3x3_direct(x40, torch.randn(3, 40, 3, 3, device=dev), torch.randn(3, device=dev))                                     # proj
     xs = csm.cross_scan_fn(x40, True, True, 0)
     csm.cross_merge_fn(xs.view(1, 4, 40, H, W), True, True, 0)
 torch.cuda.synchronize()
