@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libbem_b200.so")
 
 BEM_F32, BEM_F16, BEM_BF16 = 0, 1, 2
 BEM_OK, BEM_ERR_BAD_ARG, BEM_ERR_WORKSPACE, BEM_ERR_UNSUPPORTED = 0, 10001, 10002, 10003
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 i32, i64, u64, vp = C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
 
@@ -86,6 +86,9 @@ SYMBOLS = {
     "bem_bayes_sample_batched": (C.c_int, [C.POINTER(BemBayesSampleBatchedParams), vp]),
     "bem_bayes_pointwise_workspace_bytes": (i64, [C.c_int] * 3),
     "bem_bayes_pointwise": (C.c_int, [C.POINTER(BemBayesPointwiseParams), vp]),
+    "bem_bayes_pointwise_pack_table_bytes": (i64, [C.c_int]),
+    "bem_bayes_pointwise_pack_table": (C.c_int, [C.POINTER(BemBayesPointwiseParams), C.c_int, vp, C.POINTER(i32)]),
+    "bem_bayes_pointwise_pack_run": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "bem_bayes_depthwise": (C.c_int, [C.POINTER(BemBayesDepthwiseParams), vp]),
     "bem_conv3x3": (C.c_int, [C.POINTER(BemConv3x3Params), vp]),
     "bem_select_best": (C.c_int, [vp, i32, i32, vp, vp, vp]),

@@ -9,6 +9,8 @@ data gradients; the tiny weight-gradient reductions use torch ops.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
 from .. import _lib
@@ -66,6 +68,91 @@ def sample_weights(mu, rho, eps=None, n_samples=1, seed=0, stream_id=0, sample0=
 
 
 # ---------------------------------------------------------------------------------------------------
+class PackPlan:
+    """The pack steps of the 1x1 layers of one forward, batched into one launch (bem_bayes_pointwise_pack_run).
+
+    A Monte-Carlo forward re-draws all Bayesian weights first (mc.MCArena.draw), so nothing a layer's pack kernel reads
+    depends on the layers before it. recording(): one ordinary forward during which every eligible pointwise call (weights
+    given as a tensor, no per-layer pack cache) gets a workspace of its own and is noted; build() turns the notes into the
+    device table; run() packs them all; playing(): the same forward again, each call now passing `prepacked`. Calls are
+    matched by position and checked against the recorded signature (weight / bias / LayerNorm pointers, shape, alignment
+    class of x) — a call that does not match simply packs for itself as before. Only calls whose weight (and bias) live
+    inside `stable` = (first, last) byte address of the buffer the draw fills are eligible: anything computed during the
+    forward is not there yet when run() packs."""
+
+    def __init__(self, stable):
+        self.stable = (int(stable[0]), int(stable[1]))
+        self.entries = []      # (signature, params, workspace, tensors kept alive)
+        self.table = None
+        self.total_blocks = 0
+        self.mode = None
+        self.cursor = 0
+        self.misses = 0
+
+    def recording(self):
+        self.entries, self.table, self.mode, self.cursor = [], None, "record", 0
+        return _PlanScope(self)
+
+    def playing(self):
+        self.mode, self.cursor = "play", 0
+        return _PlanScope(self)
+
+    def build(self, device):
+        n = len(self.entries)
+        if n == 0:
+            return False
+        arr = (_lib.BemBayesPointwiseParams * n)(*[e[1] for e in self.entries])
+        nbytes = lib.bem_bayes_pointwise_pack_table_bytes(n)
+        host = torch.empty(nbytes, dtype=torch.uint8)
+        total = C.c_int32(0)
+        _lib.check(lib.bem_bayes_pointwise_pack_table(arr, n, C.c_void_p(host.data_ptr()), C.byref(total)), "bayes_pointwise_pack_table")
+        self.table = host.to(device)
+        self.total_blocks = int(total.value)
+        return True
+
+    def run(self):
+        """pack every recorded layer from the current contents of its weight tensors (one launch, current stream)"""
+        if self.table is None:
+            return
+        dev = self.table.device
+        with torch.cuda.device(dev):
+            code = lib.bem_bayes_pointwise_pack_run(_lib.ptr(self.table), len(self.entries), self.total_blocks, _lib.stream_ptr(dev))
+        _lib.profile.launches += 1
+        _lib.check(code, "bayes_pointwise_pack_run")
+
+    def eligible(self, w, bias):
+        lo, hi = self.stable
+        return w is not None and lo <= w.data_ptr() < hi and (bias is None or lo <= bias.data_ptr() < hi)
+
+    def _lookup(self, sig):
+        if self.cursor < len(self.entries) and self.entries[self.cursor][0] == sig and self.table is not None:
+            ws = self.entries[self.cursor][2]
+            self.cursor += 1
+            return ws
+        self.misses += 1
+        self.cursor = len(self.entries)      # out of step: every later call packs for itself
+        return None
+
+
+class _PlanScope:
+    def __init__(self, plan):
+        self.plan = plan
+
+    def __enter__(self):
+        global _ACTIVE_PLAN
+        self.prev, _ACTIVE_PLAN = _ACTIVE_PLAN, self.plan
+        return self.plan
+
+    def __exit__(self, *exc):
+        global _ACTIVE_PLAN
+        _ACTIVE_PLAN = self.prev
+        self.plan.mode = None
+        return False
+
+
+_ACTIVE_PLAN = None
+
+
 def _pointwise_raw(x, w=None, bias=None, mu=None, sigma=None, eps=None, n_samples=1, ln=None, force_simt=False,
                    interleave=False, residual=None, pack_cache=None, prelu=None):
     """x: (S*Bx, Cin, *spatial) fp32 — any image stride, channels P apart; w: (S|1, Cout, Cin) or mu/sigma/eps for the
@@ -103,6 +190,7 @@ def _pointwise_raw(x, w=None, bias=None, mu=None, sigma=None, eps=None, n_sample
         raise RuntimeError(f"pointwise conv: PReLU with {prelu.numel()} slopes does not match {cout} output channels")
     need = lib.bem_bayes_pointwise_workspace_bytes(n_samples, cin, cout)
     prepacked = 0
+    sig = None
     if pack_cache is not None and not force_simt:
         # constant weights (deterministic layers): the packed tiles live in the layer's own buffer and are rebuilt only when
         # a participating tensor changes (in-place updates bump ._version) or x changes alignment class
@@ -115,7 +203,18 @@ def _pointwise_raw(x, w=None, bias=None, mu=None, sigma=None, eps=None, n_sample
         prepacked = int(pack_cache.get("key") == key)
         pack_cache["key"] = key
     else:
-        ws = _lib.workspace(x.device, need, kind="pointwise")
+        ws = None
+        plan = _ACTIVE_PLAN
+        if plan is not None and not force_simt and plan.eligible(w, bias):
+            sig = (w.data_ptr(), tuple(w.shape)) + tuple(None if t is None else t.data_ptr() for t in (bias, g, b)) + (
+                float(ln_eps), n_samples, batch, P, int(img_stride) % 4 == 0, x.data_ptr() % 16 == 0, bool(interleave))
+            if plan.mode == "play":
+                ws = plan._lookup(sig)
+                prepacked = int(ws is not None)
+            elif plan.mode == "record":
+                ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        if ws is None:
+            ws = _lib.workspace(x.device, need, kind="pointwise")
     p = _lib.BemBayesPointwiseParams(n_samples=n_samples, batch=batch, cin=cin, cout=cout, P=P, x=_lib.ptr(x),
                                      w=_lib.ptr(w), mu=_lib.ptr(mu), rho=None, eps=_lib.ptr(eps), bias=_lib.ptr(bias),
                                      out=_lib.ptr(out), sigma=_lib.ptr(sigma), ln_gamma=_lib.ptr(g), ln_beta=_lib.ptr(b),
@@ -123,6 +222,9 @@ def _pointwise_raw(x, w=None, bias=None, mu=None, sigma=None, eps=None, n_sample
                                      sample_interleave=int(bool(interleave)), workspace=_lib.ptr(ws), workspace_bytes=ws.numel(),
                                      residual=_lib.ptr(residual), prepacked=prepacked, prelu_slope=_lib.ptr(prelu),
                                      prelu_n=0 if prelu is None else prelu.numel())
+    if pack_cache is None and _ACTIVE_PLAN is not None and _ACTIVE_PLAN.mode == "record" and sig is not None:
+        q = _lib.BemBayesPointwiseParams.from_buffer_copy(p)
+        _ACTIVE_PLAN.entries.append((sig, q, ws, (w, bias, g, b)))
     _lib.launch("bayes_pointwise", lib.bem_bayes_pointwise, p, x.device, key=(batch, cin, cout, P),
                 nbytes=4 * batch * P * (cin + cout * (2 if residual is not None else 1)), kernels=1 if (force_simt or prepacked) else 2)
     return out

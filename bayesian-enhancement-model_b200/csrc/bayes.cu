@@ -51,6 +51,8 @@ __device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t stream_id
 __device__ __forceinline__ float sigma_of_rho(float rho) { return log1pf(expf(rho)); }   // conv.py:106
 
 __global__ void __launch_bounds__(256) bayes_sample_kernel(const BemBayesSampleParams p) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t nblk = (p.numel + 3) / 4;
     const int64_t total = nblk * p.n_samples;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -74,6 +76,8 @@ __global__ void __launch_bounds__(256) bayes_sample_kernel(const BemBayesSampleP
 
 // every Bayesian tensor of a network in one launch (one Monte-Carlo draw); same numbers as bayes_sample_kernel
 __global__ void __launch_bounds__(256) bayes_sample_batched_kernel(const BemBayesSampleBatchedParams p) {
+    pdl_trigger();
+    pdl_wait();
     const int e = p.blocks[2 * blockIdx.x];
     const int64_t blk = (int64_t)p.blocks[2 * blockIdx.x + 1] + threadIdx.x;
     const BemBayesSampleEntry en = p.entries[e];
@@ -97,6 +101,8 @@ __global__ void __launch_bounds__(256) bayes_sample_batched_kernel(const BemBaye
 constexpr int PW_BM = 64, PW_BN = 256, PW_BK = 16;
 
 __global__ void __launch_bounds__(256) bayes_pointwise_kernel(const BemBayesPointwiseParams p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float sW[PW_BK][PW_BM + 4];   // +4: the transposing store is 2-way instead of 16-way conflicted
     __shared__ __align__(16) float sX[PW_BK][PW_BN];
     const int img = blockIdx.z;
@@ -280,6 +286,8 @@ __device__ __forceinline__ void dw_fma_row(const DwRow& r, const float* __restri
 
 template <int ACT, bool VEC>
 __global__ void __launch_bounds__(256, 3) bayes_depthwise3_kernel(const BemBayesDepthwiseParams p) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int NP = ACT == 2 ? 2 : 1;                 // input planes per thread
     const int Cout = ACT == 2 ? p.C / 2 : p.C;
     const int W4 = (p.W + 3) / 4, HS = (p.H + DW_ROWS - 1) / DW_ROWS;
@@ -355,6 +363,8 @@ constexpr int DWS_RPT = 4;
 
 template <int ACT>
 __global__ void __launch_bounds__(512) bayes_depthwise3_smem_kernel(const BemBayesDepthwiseParams p, const int R) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int NP = ACT == 2 ? 2 : 1;
     extern __shared__ __align__(128) unsigned char dsm[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(dsm);
@@ -460,6 +470,8 @@ __global__ void __launch_bounds__(512) bayes_depthwise3_smem_kernel(const BemBay
 // ------------------------------------------------------------------------------------------------
 template <int COT, bool VEC>
 __global__ void __launch_bounds__(256) conv3x3_direct_kernel(const BemConv3x3Params p) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) float sw[];            // [cin][9][COT]
     const int co0 = blockIdx.z * COT;
     const int img = blockIdx.y;
@@ -526,8 +538,8 @@ static int conv3x3_launch(const BemConv3x3Params& p, cudaStream_t stream) {
     dim3 grid((unsigned)bx, (unsigned)p.batch, (unsigned)((p.cout + COT - 1) / COT));
     const int smem = p.cin * 9 * COT * 4;
     if (smem > 48 * 1024) return BEM_ERR_UNSUPPORTED;
-    if (vec) conv3x3_direct_kernel<COT, true><<<grid, 256, smem, stream>>>(p);
-    else conv3x3_direct_kernel<COT, false><<<grid, 256, smem, stream>>>(p);
+    if (vec) launch_pdl(conv3x3_direct_kernel<COT, true>, dim3(grid), dim3(256), smem, stream, p);
+    else launch_pdl(conv3x3_direct_kernel<COT, false>, dim3(grid), dim3(256), smem, stream, p);
     return (int)cudaGetLastError();
 }
 
@@ -552,12 +564,12 @@ static void depthwise_launch(const BemBayesDepthwiseParams& p, dim3 grid, cudaSt
                 attr[dev & 63] = 100 * 1024;
             }
             dim3 g2(grid.x, (unsigned)((p.H + R - 1) / R));
-            bayes_depthwise3_smem_kernel<ACT><<<g2, threads, smem, stream>>>(p, R);
+            launch_pdl(bayes_depthwise3_smem_kernel<ACT>, dim3(g2), dim3(threads), smem, stream, p, R);
             return;
         }
     }
-    if (vec) bayes_depthwise3_kernel<ACT, true><<<grid, 256, 0, stream>>>(p);
-    else bayes_depthwise3_kernel<ACT, false><<<grid, 256, 0, stream>>>(p);
+    if (vec) launch_pdl(bayes_depthwise3_kernel<ACT, true>, dim3(grid), dim3(256), 0, stream, p);
+    else launch_pdl(bayes_depthwise3_kernel<ACT, false>, dim3(grid), dim3(256), 0, stream, p);
 }
 
 }  // namespace bem
@@ -572,13 +584,13 @@ int bem_bayes_sample(const BemBayesSampleParams* p, void* stream) {
     int64_t blocks = (total + 255) / 256;
     const int64_t cap = (int64_t)device_sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    bayes_sample_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+    launch_pdl(bayes_sample_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, *p);
     return (int)cudaGetLastError();
 }
 
 int bem_bayes_sample_batched(const BemBayesSampleBatchedParams* p, void* stream) {
     if (!p || !p->entries || !p->blocks || p->n_blocks <= 0) return BEM_ERR_BAD_ARG;
-    bayes_sample_batched_kernel<<<p->n_blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+    launch_pdl(bayes_sample_batched_kernel, dim3(p->n_blocks), dim3(256), 0, (cudaStream_t)stream, *p);
     return (int)cudaGetLastError();
 }
 
@@ -598,8 +610,26 @@ int bem_bayes_pointwise(const BemBayesPointwiseParams* p, void* stream) {
     if (!p->force_simt) return bayes_pointwise_tc_launch(*p, (cudaStream_t)stream);
     if (p->ln_gamma) return BEM_ERR_UNSUPPORTED;   // the LayerNorm fusion lives in the tensor-core kernel
     dim3 grid((unsigned)((p->P + PW_BN - 1) / PW_BN), (unsigned)((p->cout + PW_BM - 1) / PW_BM), (unsigned)p->batch);
-    bayes_pointwise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+    launch_pdl(bayes_pointwise_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, *p);
     return (int)cudaGetLastError();
+}
+
+int64_t bem_bayes_pointwise_pack_table_bytes(int n) { return n > 0 ? bayes_pointwise_pack_table_bytes(n) : 0; }
+
+int bem_bayes_pointwise_pack_table(const BemBayesPointwiseParams* params, int n, void* table_host, int32_t* total_blocks) {
+    if (!params || n <= 0 || !table_host || !total_blocks) return BEM_ERR_BAD_ARG;
+    for (int i = 0; i < n; ++i) {
+        const BemBayesPointwiseParams& q = params[i];
+        if (q.n_samples <= 0 || q.cin <= 0 || q.cout <= 0 || q.P <= 0 || q.batch <= 0 || q.force_simt) return BEM_ERR_BAD_ARG;
+        if (!q.w && !q.mu) return BEM_ERR_BAD_ARG;
+        if (!q.w && (q.rho || q.sigma) && !q.eps) return BEM_ERR_BAD_ARG;
+    }
+    return bayes_pointwise_pack_table(params, n, table_host, total_blocks);
+}
+
+int bem_bayes_pointwise_pack_run(const void* table_dev, int n, int total_blocks, void* stream) {
+    if (!table_dev || n <= 0 || total_blocks <= 0) return BEM_ERR_BAD_ARG;
+    return bayes_pointwise_pack_run(table_dev, n, total_blocks, (cudaStream_t)stream);
 }
 
 int bem_conv3x3(const BemConv3x3Params* p, void* stream) {

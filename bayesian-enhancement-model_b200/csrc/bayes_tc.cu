@@ -131,13 +131,12 @@ __device__ __forceinline__ float sampled_weight(const BemBayesPointwiseParams& p
 // `fold_ln` (persistent kernel): the LayerNorm weight is folded into the packed tiles, W' = gamma * W, and the blocks
 // past the tile blocks write, per (sample, output channel n), vec = ( s_n = sum_ci W'[n][ci], t_n = sum_ci beta[ci] *
 // W[n][ci] + bias[n] ), so that LN(x) . W = rstd * (x . W' - mean * s) + t is finished in the GEMM epilogue.
-__global__ void __launch_bounds__(256) bayes_weight_pack_kernel(const BemBayesPointwiseParams p, const int NT, const int ntiles,
-                                                              const int nk, float* __restrict__ pack, const int fold_ln,
-                                                              float* __restrict__ vec) {
+__device__ __forceinline__ void weight_pack_block(const BemBayesPointwiseParams& p, const int NT, const int ntiles, const int nk,
+                                                  float* __restrict__ pack, const int fold_ln, float* __restrict__ vec, const int block) {
     const int tile_blocks = p.n_samples * ntiles * nk;
-    if ((int)blockIdx.x >= tile_blocks) {
+    if (block >= tile_blocks) {
         const int cblocks = (p.cout + 7) / 8;
-        const int vb = blockIdx.x - tile_blocks;
+        const int vb = block - tile_blocks;
         const int s = vb / cblocks, co = (vb - s * cblocks) * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
         if (co >= p.cout) return;
         const int64_t wofs = (int64_t)s * p.cout * p.cin;
@@ -162,7 +161,7 @@ __global__ void __launch_bounds__(256) bayes_weight_pack_kernel(const BemBayesPo
         }
         return;
     }
-    const int blk = blockIdx.x;             // (s, tile, kc)
+    const int blk = block;                  // (s, tile, kc)
     const int kc = blk % nk;
     const int tile = (blk / nk) % ntiles;
     const int s = blk / (nk * ntiles);
@@ -190,8 +189,47 @@ __global__ void __launch_bounds__(256) bayes_weight_pack_kernel(const BemBayesPo
     }
 }
 
+__global__ void __launch_bounds__(256) bayes_weight_pack_kernel(const BemBayesPointwiseParams p, const int NT, const int ntiles,
+                                                              const int nk, float* __restrict__ pack, const int fold_ln,
+                                                              float* __restrict__ vec) {
+    pdl_trigger();
+    pdl_wait();
+    weight_pack_block(p, NT, ntiles, nk, pack, fold_ln, vec, (int)blockIdx.x);
+}
+
+// The pack step of MANY layers in one launch (bem_bayes_pointwise_pack_run): a Monte-Carlo forward re-draws every Bayesian
+// weight first (bem_bayes_sample_batched), so all its 1x1 layers can be packed right after, and each layer's own call then
+// runs with `prepacked` — one launch per sample instead of one per layer. Block b belongs to the last entry whose first
+// block is <= b.
+struct PackEntry {
+    BemBayesPointwiseParams p;
+    float* pack;
+    float* vec;
+    int32_t NT, ntiles, nk, fold_ln, block0, nblocks;
+};
+static_assert(sizeof(PackEntry) % 4 == 0 && sizeof(PackEntry) <= 1024, "PackEntry is staged through shared memory by one pass of 256 threads");
+
+__global__ void __launch_bounds__(256) bayes_weight_pack_batched_kernel(const PackEntry* __restrict__ table, const int n) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ PackEntry e;
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (table[mid].block0 <= (int)blockIdx.x) lo = mid;
+        else hi = mid - 1;
+    }
+    if (threadIdx.x < sizeof(PackEntry) / 4)
+        reinterpret_cast<uint32_t*>(&e)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&table[lo])[threadIdx.x];
+    __syncthreads();
+    const int block = (int)blockIdx.x - e.block0;
+    if (block < e.nblocks) weight_pack_block(e.p, e.NT, e.ntiles, e.nk, e.pack, e.fold_ln, e.vec, block);
+}
+
 __global__ void __launch_bounds__(128, 4) bayes_pointwise_tc_kernel(const BemBayesPointwiseParams p, const int NT, const int ntiles,
                                                                   const float* __restrict__ pack, const uint32_t tmem_cols) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(1024) unsigned char smem[];
     // stage s: [A hi | A lo | B hi | B lo]; A tiles 128 x KC (staged by the threads), B tiles NT x KC (TMA from `pack`)
     const uint32_t a_bytes = TC_M * TC_KC * 4;
@@ -457,11 +495,13 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
         fence_barrier_init();
         fence_proxy_async();
     }
+    pdl_trigger();
     if (warp == P3_W_MMA) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();   // barriers initialised and TMEM allocated while the previous kernel drains
 
     if (warp < P3_PW) {
         // ---------------- producers: activations (LDGSTS, 16 B per lane, one 512-byte row per instruction) ----------------
@@ -761,27 +801,77 @@ static int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
-int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t stream) {
+// which kernel a call takes, its tiling, and where its packed tiles / epilogue vectors live in the workspace
+struct TcPlan {
+    int ntiles, NT, nk, pack_blocks, vec_blocks;
+    int64_t ptiles;
+    bool persistent;
+    float* pack;
+    float* vec;
+};
+static int tc_plan(const BemBayesPointwiseParams& p, TcPlan& t) {
     const int64_t need = bayes_pointwise_tc_workspace(p.n_samples, p.cin, p.cout);
     if (!p.workspace || p.workspace_bytes < need || (reinterpret_cast<uintptr_t>(p.workspace) & 15)) return BEM_ERR_WORKSPACE;
-    const int64_t ptiles = (p.P + TC_M - 1) / TC_M;
-    if (ptiles > 65535 || p.batch > 65535) return BEM_ERR_UNSUPPORTED;
+    t.ptiles = (p.P + TC_M - 1) / TC_M;
+    if (t.ptiles > 65535 || p.batch > 65535) return BEM_ERR_UNSUPPORTED;
+    t.pack = reinterpret_cast<float*>(p.workspace);
+    // the persistent kernel moves x with 16-byte cp.async: rows must start and end on 16-byte boundaries
+    static const int force_v2 = env_int("BEM_PW_V2", 0);
+    const bool aligned = (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && p.P % 4 == 0 && p.x_img_stride % 4 == 0;
+    tc_tiling(p.cin, p.cout, P3_NMAX, t.ntiles, t.NT, t.nk);
+    // the persistent kernel keeps the epilogue vectors of every (sample, tile) in shared memory
+    t.persistent = aligned && !force_v2 && (int64_t)p.n_samples * t.ntiles * t.NT * 8 <= 16 * 1024;
+    if (!t.persistent) tc_tiling(p.cin, p.cout, TC_NMAX, t.ntiles, t.NT, t.nk);
+    t.vec = t.pack + tc_pack_floats(p.n_samples, p.cin, p.cout, t.persistent ? P3_NMAX : TC_NMAX);
+    t.pack_blocks = p.n_samples * t.ntiles * t.nk;
+    t.vec_blocks = p.n_samples * ((p.cout + 7) / 8);
+    return BEM_OK;
+}
+
+int64_t bayes_pointwise_pack_table_bytes(int n) { return (int64_t)n * (int64_t)sizeof(PackEntry); }
+
+int bayes_pointwise_pack_table(const BemBayesPointwiseParams* params, int n, void* table_host, int32_t* total_blocks) {
+    PackEntry* tab = reinterpret_cast<PackEntry*>(table_host);
+    int64_t blocks = 0;
+    for (int i = 0; i < n; ++i) {
+        TcPlan t;
+        const int rc = tc_plan(params[i], t);
+        if (rc != BEM_OK) return rc;
+        PackEntry& e = tab[i];
+        e.p = params[i];
+        e.pack = t.pack;
+        e.vec = t.vec;
+        e.NT = t.NT;
+        e.ntiles = t.ntiles;
+        e.nk = t.nk;
+        e.fold_ln = t.persistent ? 1 : 0;
+        e.block0 = (int32_t)blocks;
+        e.nblocks = t.pack_blocks + (t.persistent ? t.vec_blocks : 0);
+        blocks += e.nblocks;
+        if (blocks > 0x7fffffff) return BEM_ERR_UNSUPPORTED;
+    }
+    *total_blocks = (int32_t)blocks;
+    return BEM_OK;
+}
+
+int bayes_pointwise_pack_run(const void* table_dev, int n, int total_blocks, cudaStream_t stream) {
+    launch_pdl(bayes_weight_pack_batched_kernel, dim3(total_blocks), dim3(256), 0, stream, reinterpret_cast<const PackEntry*>(table_dev), n);
+    return (int)cudaGetLastError();
+}
+
+int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t stream) {
+    TcPlan t;
+    const int rc = tc_plan(p, t);
+    if (rc != BEM_OK) return rc;
+    const int64_t ptiles = t.ptiles;
+    const int ntiles = t.ntiles, NT = t.NT, nk = t.nk, pack_blocks = t.pack_blocks, vec_blocks = t.vec_blocks;
+    const bool persistent = t.persistent;
+    float* pack = t.pack;
+    float* vec = t.vec;
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
-    float* pack = reinterpret_cast<float*>(p.workspace);
-    // the persistent kernel moves x with 16-byte cp.async: rows must start and end on 16-byte boundaries
-    static const int force_v2 = env_int("BEM_PW_V2", 0);
     static const int trace_on = env_int("BEM_PW_TRACE", 0);   // record CTA 0's stage timeline (tools/trace_pointwise.py)
-    const bool aligned = (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && p.P % 4 == 0 && p.x_img_stride % 4 == 0;
-    int ntiles, NT, nk;
-    tc_tiling(p.cin, p.cout, P3_NMAX, ntiles, NT, nk);
-    // the persistent kernel keeps the epilogue vectors of every (sample, tile) in shared memory
-    const bool persistent = aligned && !force_v2 && (int64_t)p.n_samples * ntiles * NT * 8 <= 16 * 1024;
-    if (!persistent) tc_tiling(p.cin, p.cout, TC_NMAX, ntiles, NT, nk);
-    float* vec = pack + tc_pack_floats(p.n_samples, p.cin, p.cout, persistent ? P3_NMAX : TC_NMAX);
-    const int pack_blocks = p.n_samples * ntiles * nk;
-    const int vec_blocks = p.n_samples * ((p.cout + 7) / 8);
     if (persistent) {
         // shared-memory plan: the layer's packed tiles resident when they fit in 120 KB, else a B ring of >= 3 stages
         // (up to ~48 KB); the epilogue vectors resident; the rest goes to raw x stages in flight
@@ -803,7 +893,7 @@ int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t str
             attr3[dev] = smem_bytes;
         }
         if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
-        if (!p.prepacked) bayes_weight_pack_kernel<<<pack_blocks + vec_blocks, 256, 0, stream>>>(p, NT, ntiles, nk, pack, 1, vec);
+        if (!p.prepacked) launch_pdl(bayes_weight_pack_kernel, dim3(pack_blocks + vec_blocks), dim3(256), 0, stream, p, NT, ntiles, nk, pack, 1, vec);
         const int64_t n_items = (int64_t)p.batch * ptiles * ntiles;
         if (n_items >= (1ll << 31)) return BEM_ERR_UNSUPPORTED;
         const int grid = (int)std::min<int64_t>(n_items, sms[dev]);
@@ -813,7 +903,7 @@ int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t str
         if (p.prelu_slope) kernel = p.ln_gamma ? bayes_pointwise_tc3_kernel<true, false, 2> : bayes_pointwise_tc3_kernel<false, false, 2>;
         if (p.residual) kernel = p.ln_gamma ? bayes_pointwise_tc3_kernel<true, false, 1> : bayes_pointwise_tc3_kernel<false, false, 1>;
         if (trace_on || p.prelu_slope || p.residual) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-        kernel<<<grid, P3_THREADS, smem_bytes, stream>>>(p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS, b_resident);
+        launch_pdl(kernel, dim3(grid), dim3(P3_THREADS), smem_bytes, stream, p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS, b_resident);
         return (int)cudaGetLastError();
     }
     uint32_t tmem_cols = 32;
@@ -826,9 +916,9 @@ int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t str
         if (e != cudaSuccess) return (int)e;
         attr_set[dev] = smem_bytes;
     }
-    if (!p.prepacked) bayes_weight_pack_kernel<<<pack_blocks, 256, 0, stream>>>(p, NT, ntiles, nk, pack, 0, vec);
+    if (!p.prepacked) launch_pdl(bayes_weight_pack_kernel, dim3(pack_blocks), dim3(256), 0, stream, p, NT, ntiles, nk, pack, 0, vec);
     dim3 grid((unsigned)ntiles, (unsigned)ptiles, (unsigned)p.batch);
-    bayes_pointwise_tc_kernel<<<grid, 128, smem_bytes, stream>>>(p, NT, ntiles, pack, tmem_cols);
+    launch_pdl(bayes_pointwise_tc_kernel, dim3(grid), dim3(128), smem_bytes, stream, p, NT, ntiles, pack, tmem_cols);
     return (int)cudaGetLastError();
 }
 

@@ -2,9 +2,19 @@
 // launch parameter packing. No torch types, no allocation, no synchronisation.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "bem_kernels.h"
 
 namespace bem {
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* v = getenv("BEM_NO_PDL");
+        return !(v && atoi(v) != 0);
+    }();
+    return on;
+}
 
 int device_sm_count() {
     static int cached[64] = {0};

@@ -76,6 +76,8 @@ __device__ __forceinline__ int64_t img_off(const CsmArgs& p, int b, int k, int c
 // ---------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void csm_scan_generic(const CsmArgs p) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t L = (int64_t)p.H * p.W;
     const int64_t total = (int64_t)p.B * 4 * p.C * L;
     const T* src = reinterpret_cast<const T*>(p.src);
@@ -106,6 +108,8 @@ __global__ void csm_scan_generic(const CsmArgs p) {
 
 template <typename T>
 __global__ void csm_merge_generic(const CsmArgs p) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t L = (int64_t)p.H * p.W;
     const int K = p.obo ? 4 : 1;
     const int64_t total = (int64_t)p.B * K * p.C * L;
@@ -155,6 +159,8 @@ __global__ void csm_merge_generic(const CsmArgs p) {
 // ---------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) csm_scan_tiled(const CsmArgs p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ T tile[32][33];
     const int H = p.H, W = p.W;
     const int64_t L = (int64_t)H * W;
@@ -202,6 +208,8 @@ __global__ void __launch_bounds__(256) csm_scan_tiled(const CsmArgs p) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) csm_merge_tiled(const CsmArgs p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ T tile[32][33];
     const int H = p.H, W = p.W;
     const int64_t L = (int64_t)H * W;
@@ -263,8 +271,8 @@ static int csm_launch(const CsmArgs& a, bool merge, cudaStream_t stream) {
     const bool tiled = a.img_cf && a.seq_cf && a.scans == 0 && a.C <= 65535 && a.B <= 65535;
     if (tiled) {
         dim3 grid(((a.W + 31) / 32) * ((a.H + 31) / 32), a.C, a.B), block(32, 8);
-        if (merge) csm_merge_tiled<T><<<grid, block, 0, stream>>>(a);
-        else csm_scan_tiled<T><<<grid, block, 0, stream>>>(a);
+        if (merge) launch_pdl(csm_merge_tiled<T>, dim3(grid), dim3(block), 0, stream, a);
+        else launch_pdl(csm_scan_tiled<T>, dim3(grid), dim3(block), 0, stream, a);
     } else {
         const int64_t total = (int64_t)a.B * ((merge && !a.obo) ? 1 : 4) * a.C * a.H * a.W;
         const int threads = 256;
@@ -272,8 +280,8 @@ static int csm_launch(const CsmArgs& a, bool merge, cudaStream_t stream) {
         const int64_t cap = (int64_t)device_sm_count() * 32;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        if (merge) csm_merge_generic<T><<<(int)blocks, threads, 0, stream>>>(a);
-        else csm_scan_generic<T><<<(int)blocks, threads, 0, stream>>>(a);
+        if (merge) launch_pdl(csm_merge_generic<T>, dim3((int)blocks), dim3(threads), 0, stream, a);
+        else launch_pdl(csm_scan_generic<T>, dim3((int)blocks), dim3(threads), 0, stream, a);
     }
     return (int)cudaGetLastError();
 }

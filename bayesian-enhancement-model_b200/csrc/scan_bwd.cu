@@ -22,6 +22,8 @@ namespace bem {
 
 template <typename T, typename DT, int ITEMS, int NW, bool N1>
 __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1) scan_bwd_kernel(const ScanBwdArgs p) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int CL = 32 * ITEMS;
     constexpr bool kAcc = sizeof(T) == 4;   // fp32 inputs: full-precision decay rate (scan_common.cuh decay_m1)
     constexpr int ROW_SLOT = 2 * CL * (int)sizeof(T) + CL * (int)sizeof(DT);   // [u | delta | dout]
@@ -681,7 +683,7 @@ static int launch_bwd(ScanBwdArgs& a, int sm_count, cudaStream_t stream) {
     const int64_t ndesc = (int64_t)a.batch * a.dim * a.nchunks * a.N;
     a.desc_incl = a.desc + ndesc;
     const int grid = min(a.total_tiles, sm_count * ctas_per_sm);
-    kernel<<<grid, (NW + 1) * 32, smem_bytes, stream>>>(a);
+    launch_pdl(kernel, dim3(grid), dim3((NW + 1) * 32), smem_bytes, stream, a);
     return (int)cudaGetLastError();
 }
 

@@ -36,6 +36,8 @@ struct ScanTracer {
 // in registers); -1 = rank read from the arguments (any rank <= kMaxDtRank, runtime loop).
 template <typename T, typename OutT, int ITEMS, int NW, bool N1, int RANK = 0>
 __global__ void __launch_bounds__((NW + 1) * 32, N1 ? 2 : 1) scan_fwd_kernel(const ScanFwdArgs p) {
+    pdl_trigger();
+    pdl_wait();
     constexpr bool FUSED = RANK != 0;
     constexpr int CL = 32 * ITEMS;
     constexpr bool kAcc = sizeof(T) == 4;   // fp32 inputs: full-precision decay rate (scan_common.cuh decay_m1)
@@ -540,7 +542,7 @@ static int launch_fwd(ScanFwdArgs a, int sm_count, cudaStream_t stream) {
         cached_smem[dev] = smem_bytes;
     }
     const int grid = min(a.total_tiles, sm_count * cached_per_sm[dev]);
-    kernel<<<grid, (NW + 1) * 32, smem_bytes, stream>>>(a);
+    launch_pdl(kernel, dim3(grid), dim3((NW + 1) * 32), smem_bytes, stream, a);
     return (int)cudaGetLastError();
 }
 

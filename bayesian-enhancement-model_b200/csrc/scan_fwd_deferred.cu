@@ -54,6 +54,8 @@ struct Pending {   // what a lane keeps of a tile between pass 1 and its finish
 // RANK: fused dt_proj rank. 0 = delta per channel row; > 0 compile-time rank; -1 = rank from the arguments (<= kMaxDtRank).
 template <int RANK, bool TRACE = false>
 __global__ void __launch_bounds__(D_THREADS, 2) scan_fwd_deferred_kernel(const ScanFwdArgs p) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int NW = D_NW, CL = D_CL, ITEMS = D_ITEMS, V = D_V, ROW_SLOT = D_ROW_SLOT;
     constexpr bool FUSED = RANK != 0;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -446,7 +448,7 @@ static int launch_deferred(ScanFwdArgs a, int sm_count, cudaStream_t stream) {
         cached_smem[dev] = smem_bytes;
     }
     const int grid = min(a.total_tiles, sm_count * cached_per_sm[dev]);
-    kernel<<<grid, D_THREADS, smem_bytes, stream>>>(a);
+    launch_pdl(kernel, dim3(grid), dim3(D_THREADS), smem_bytes, stream, a);
     return (int)cudaGetLastError();
 }
 

@@ -14,6 +14,8 @@ __device__ __forceinline__ bool sel_better(float v, int i, float bv, int bi, boo
 
 __global__ void __launch_bounds__(256) select_best_kernel(const float* __restrict__ scores, int n, int take_min_,
                                                           int* __restrict__ out_index, float* __restrict__ out_value) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sv[256];
     __shared__ int si[256];
     const bool take_min = take_min_ != 0;
@@ -58,6 +60,6 @@ __global__ void __launch_bounds__(256) select_best_kernel(const float* __restric
 extern "C" int bem_select_best(const float* scores, int32_t n, int32_t take_min, int32_t* out_index, float* out_value,
                                void* stream) {
     if (!scores || !out_index || n <= 0) return BEM_ERR_BAD_ARG;
-    bem::select_best_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(scores, n, take_min, out_index, out_value);
+    bem::launch_pdl(bem::select_best_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, scores, n, take_min, out_index, out_value);
     return (int)cudaGetLastError();
 }

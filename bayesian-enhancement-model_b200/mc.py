@@ -98,6 +98,7 @@ class MCArena:
         self.blocks = torch.tensor(blocks, dtype=torch.int32).to(self.device)
         self.n_blocks = len(blocks)
         self.sample0 = torch.zeros((), dtype=torch.int64, device=self.device)   # device-side sample index (graph replay)
+        self.plans = {}   # input shape -> functional.PackPlan: the pack steps of all Bayesian 1x1 layers in one launch per draw
 
     def valid(self) -> bool:
         return all(mu.data_ptr() == pm and rho.data_ptr() == pr for mu, rho, pm, pr in self._ptrs)
@@ -106,13 +107,33 @@ class MCArena:
         for L in self.layers:
             L._arena = L.__dict__.get("_arena_views") if on else None
 
-    def draw(self, sample_id: Optional[int] = None):
-        """fill the arena for global sample `sample_id`; None = read the index from the device word `self.sample0`"""
+    def draw(self, sample_id: Optional[int] = None, plan=None):
+        """fill the arena for global sample `sample_id`; None = read the index from the device word `self.sample0`.
+        `plan`: a built PackPlan whose layers are packed from the fresh draw (one more launch)."""
         from .bayesian import functional as BF
         if sample_id is None:
             BF.sample_batched(self.entries, self.blocks, self.n_blocks, self.seed, 0, self.sample0)
         else:
             BF.sample_batched(self.entries, self.blocks, self.n_blocks, self.seed, int(sample_id), None)
+        if plan is not None:
+            plan.run()
+
+    def forward_planned(self, key, sample_id, fn):
+        """draw + fn() with the pack steps of the Bayesian 1x1 layers batched: the first call for `key` (the input's shape)
+        runs fn() as it is and records the plan, later calls pack everything right after the draw."""
+        from .bayesian import functional as BF
+        plan = self.plans.get(key)
+        if plan is None:
+            plan = BF.PackPlan((self.buffer.data_ptr(), self.buffer.data_ptr() + 4 * self.buffer.numel()))
+            self.draw(sample_id)
+            with plan.recording():
+                y = fn()
+            plan.build(self.device)
+            self.plans[key] = plan
+            return y
+        self.draw(sample_id, plan)
+        with plan.playing():
+            return fn()
 
 
 class MCSampler:
@@ -162,14 +183,12 @@ class MCSampler:
             side = torch.cuda.Stream(device=x.device)
             side.wait_stream(torch.cuda.current_stream(x.device))
             with torch.cuda.stream(side):            # warm-up off the capture: lazy initialisation, workspace growth
-                for _ in range(2):
-                    arena.draw(None)
-                    self._forward_one(static_x)
+                for _ in range(2):               # the first of them records the pack plan of this shape
+                    arena.forward_planned(key, None, lambda: self._forward_one(static_x))
             torch.cuda.current_stream(x.device).wait_stream(side)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                arena.draw(None)
-                static_y = self._forward_one(static_x)
+                static_y = arena.forward_planned(key, None, lambda: self._forward_one(static_x))
             rec = (g, static_x, static_y)
             self._graphs[key] = rec
         return rec
@@ -221,9 +240,9 @@ class MCSampler:
                         g.replay()
                         outs.append(static_y.clone())
                 else:
+                    key = (tuple(x.shape), x.dtype, x.device)
                     for sid in ids:
-                        arena.draw(int(sid))
-                        outs.append(self._forward_one(x))
+                        outs.append(arena.forward_planned(key, int(sid), lambda: self._forward_one(x)))
             finally:
                 arena.attach(False)
             return torch.cat(outs, dim=0)

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define BEM_ABI_VERSION 10
+#define BEM_ABI_VERSION 11
 
 /* element types of u/delta/B/C/x-activations */
 enum { BEM_F32 = 0, BEM_F16 = 1, BEM_BF16 = 2 };
@@ -281,6 +281,20 @@ typedef struct BemBayesPointwiseParams {
 } BemBayesPointwiseParams;
 int64_t bem_bayes_pointwise_workspace_bytes(int n_samples, int cin, int cout);
 int bem_bayes_pointwise(const BemBayesPointwiseParams* p, void* stream);
+
+/* The pack step of many bem_bayes_pointwise calls in ONE launch. A Monte-Carlo forward re-draws every Bayesian weight first
+ * (bem_bayes_sample_batched; the reference samples inside each layer's forward, bayesian/conv.py:105-111), so the weight
+ * tiles of all its 1x1 layers can be packed right after the draw; each layer's own call then passes `prepacked = 1` and the
+ * same workspace, and launches one kernel instead of two.
+ *   bem_bayes_pointwise_pack_table : host only. `params[i]` is the parameter block of the i-th later call (its x / out
+ *       pointers are not dereferenced; only the alignment class of x, P and x_img_stride must be the later call's, and
+ *       `workspace` must be that call's own buffer, not shared with another entry). Fills `table_host`
+ *       (bem_bayes_pointwise_pack_table_bytes(n) bytes), which the caller copies to device memory once, and
+ *       `*total_blocks`.
+ *   bem_bayes_pointwise_pack_run   : one launch that packs every entry of the device copy of the table. */
+int64_t bem_bayes_pointwise_pack_table_bytes(int n);
+int bem_bayes_pointwise_pack_table(const BemBayesPointwiseParams* params, int n, void* table_host, int32_t* total_blocks);
+int bem_bayes_pointwise_pack_run(const void* table_dev, int n, int total_blocks, void* stream);
 
 typedef struct BemBayesDepthwiseParams {
     int32_t n_samples;

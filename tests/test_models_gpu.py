@@ -152,6 +152,33 @@ def test_mc_sampler_arena_and_cuda_graph_match_per_layer_path():
     assert float((graph[0] - graph[1]).abs().max()) > 0
 
 
+def test_pack_plan_batches_the_pack_steps_without_changing_a_bit():
+    """MCArena.forward_planned: first call records (ordinary per-layer packing), later calls pack all Bayesian 1x1 layers in one
+    launch after the draw and run every layer with `prepacked` — same bits, fewer launches, no call out of step"""
+    from bem_b200 import _lib, mc, network
+    torch.manual_seed(0)
+    net = network.build_bayesian_model().cuda().eval()
+    x = torch.rand(1, 3, 32, 48, device="cuda")
+    s = mc.MCSampler(net, seed=3, arena=True)
+    with torch.no_grad():
+        first = s.sample(x, [6])                 # records
+        arena = s._arena
+        (plan,) = arena.plans.values()
+        assert len(plan.entries) >= 20 and plan.table is not None and plan.total_blocks > 0
+        _lib.profile.reset()
+        again = s.sample(x, [6])                 # plays
+        planned_launches = _lib.profile.launches
+        other = s.sample(x, [7])
+        arena.plans.clear()
+        _lib.profile.reset()
+        s.sample(x, [6])                         # records again: per-layer packing
+        plain_launches = _lib.profile.launches
+    assert plan.misses == 0
+    assert torch.equal(first, again)
+    assert float((other - again).abs().max()) > 0
+    assert planned_launches == plain_launches - len(plan.entries) + 1
+
+
 def test_mc_sampler_host_buffer_call_matches_device_call():
     """sample_to_host (pinned image in, pinned prediction out; the bench's e2e call) == sample on device, graph and eager"""
     from bem_b200 import mc, network
