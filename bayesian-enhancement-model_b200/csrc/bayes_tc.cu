@@ -92,6 +92,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// two 16-column loads in flight, one wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float (&va)[16], float (&vb)[16]) {
+    uint32_t r[16], q[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(ta)
+        : "memory");
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+          "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+        : "r"(tb)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        va[i] = __uint_as_float(r[i]);
+        vb[i] = __uint_as_float(q[i]);
+    }
+}
 // K-major, no-swizzle shared-memory descriptor (cute::UMMA::SmemDescriptor, version 1):
 // start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | 1 << 46
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -414,7 +436,9 @@ constexpr int P3_XW = 8;       // transform warps
 constexpr int P3_EW = 8;       // epilogue warps (two per TMEM lane quarter, alternating 16-column groups)
 constexpr int P3_PW = 4;       // activation producer warps (TC_KC / P3_PW rows of every chunk each)
 constexpr int P3_W_MMA = P3_PW, P3_W_WGT = P3_PW + 1, P3_W_X0 = P3_PW + 2, P3_W_E0 = P3_W_X0 + P3_XW;   // first warp of each role
-constexpr int P3_THREADS = (P3_W_E0 + P3_EW) * 32;
+constexpr int P3_W_MMA2 = P3_W_E0 + P3_EW;   // second MMA issuer (DUAL)
+constexpr int P3_THREADS = (P3_W_MMA2 + 1) * 32;
+constexpr int P3_DUAL_NMAX = 96;             // DUAL: two partial accumulators of <= 96 columns per buffer
 
 struct Ring {   // position in a ring of `n` stages and the phase bit of its mbarriers
     uint32_t s = 0, ph = 0;
@@ -452,7 +476,13 @@ __device__ __forceinline__ P3Item p3_item(const BemBayesPointwiseParams& p, int6
 
 // EPI: what the epilogue adds to the per-channel affine — 0 nothing, 1 the skip connection (`residual`), 2 a PReLU. Separate
 // instantiations: the store loop of the write-heavy layers is sensitive to every extra instruction and branch.
-template <bool LN, bool TRACE = false, int EPI = 0>
+// DUAL (tiles of <= 96 output channels, >= 2 chunks): a `tcgen05.mma` costs its issuing thread ~50-100 clk whatever its N and
+// a `tcgen05.commit` ~270 (tools/micro/mma_rate.cu: 105 clk per MMA at N = 16 .. 192 from one thread, the same per thread
+// from two or four issuing warps), so with narrow tiles and many input channels one issuer bounds the pipeline at ~550 clk
+// per 16-channel chunk. Two issuers take the chunks of even / odd running index (the transform groups' split) into their own
+// accumulators (columns +0 / +96 of the buffer — no ordering between the two instruction streams is needed, and the sums
+// stay deterministic); the epilogue adds the two partial sums. 160 -> 40: 56 -> 49 us, 320 -> 80: 45 -> 39 us.
+template <bool LN, bool TRACE = false, int EPI = 0, bool DUAL = false>
 __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(const BemBayesPointwiseParams p, const int NT, const int ntiles,
                                                                           const int ptiles, const int64_t n_items,
                                                                           const float* __restrict__ pack, const float* __restrict__ vec,
@@ -481,6 +511,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
     const int nk = (p.cin + TC_KC - 1) / TC_KC;
     Tracer tr;
     constexpr int trace_on = TRACE ? 1 : 0;   // the timeline build is its own instantiation: no trace predicates in the product kernel
+    if (TRACE && tid == 0) tr(trace_on, 6, 40, 0);
 
     if (tid == 0) {
         for (int i = 0; i < (int)RS; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], P3_XW / 2); }
@@ -488,7 +519,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
         for (int i = 0; i < (b_resident ? 1 : (int)BS); ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         mbar_init(&vec_full[0], 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_full[i], DUAL ? 2 : 1);
             mbar_init(&acc_empty[i], P3_EW);
             mbar_init(&stats_full[i], P3_XW);
         }
@@ -501,7 +532,9 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    if (TRACE && tid == 0) tr(trace_on, 6, 41, 0);
     pdl_wait();   // barriers initialised and TMEM allocated while the previous kernel drains
+    if (TRACE && tid == 0) tr(trace_on, 6, 42, 0);
 
     if (warp < P3_PW) {
         // ---------------- producers: activations (LDGSTS, 16 B per lane, one 512-byte row per instruction) ----------------
@@ -585,15 +618,18 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
             }
         }
         __syncwarp();
-    } else if (warp == P3_W_MMA) {
-        // ---------------- MMA issuer ----------------
+    } else if (warp == P3_W_MMA2 && !DUAL) {
+        // spare warp
+    } else if (warp == P3_W_MMA || warp == P3_W_MMA2) {
+        // ---------------- MMA issuer(s) ----------------
+        const int issuer = warp == P3_W_MMA ? 0 : 1, istep = DUAL ? 2 : 1;
         // The whole warp walks the loop (uniform control flow keeps descriptors in uniform registers); one elected lane
         // issues. B descriptors are one base plus the stage / K-step offset in the 14-bit address field.
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
         const uint64_t descB0 = make_desc(smem_u32(s_b), TC_LBO, TC_SBO);
         const uint32_t b_step = (2 * b_bytes) >> 4, b_lo = b_bytes >> 4;
         Ring ra, rb;
-        uint32_t li = 0;
+        uint32_t li = 0, g = 0;
         if (b_resident) mbar_wait(&b_full[0], 0, nullptr);
         for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
             const uint32_t buf = li & 1;
@@ -602,12 +638,13 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
                 rb.s = (uint32_t)((w.s_idx * ntiles + w.tile) * nk);
             }
             mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1, nullptr);   // the epilogue has drained this accumulator
-            if (lane == 0) tr(trace_on, 3, 20, li);
-            const uint32_t d = tmem + buf * P3_ACC_COLS;
-            for (int kc = 0; kc < nk; ++kc, ra.next(P3_AS), rb.next(b_resident ? 0xffffffffu : BS)) {
+            if (lane == 0) tr(trace_on, 3 + 2 * issuer, 20 + 2 * issuer, li);
+            const uint32_t d = tmem + buf * P3_ACC_COLS + (DUAL ? issuer * P3_DUAL_NMAX : 0);
+            for (int kc = 0; kc < nk; ++kc, ++g, ra.next(P3_AS), rb.next(b_resident ? 0xffffffffu : BS)) {
+                if (DUAL && (g & 1) != (uint32_t)issuer) continue;
                 mbar_wait(&a_full[ra.s], ra.ph, nullptr);
                 if (!b_resident) mbar_wait(&b_full[rb.s], rb.ph, nullptr);
-                if (lane == 0) tr(trace_on, 3, 21, kc);
+                if (lane == 0) tr(trace_on, 3 + 2 * issuer, 21 + 2 * issuer, kc);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t aH = tmem + P3_A_COL0 + ra.s * (2 * TC_KC), aL = aH + TC_KC;
@@ -615,13 +652,13 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
 #pragma unroll
                     for (int ks = 0; ks < TC_KC / 8; ++ks) {
                         const uint64_t adv = (uint64_t)(ks * ((2 * TC_LBO) >> 4));
-                        umma_tf32_ts(d, aH + ks * 8, dBh + adv, idesc, ks ? 1u : (uint32_t)(kc != 0));
+                        umma_tf32_ts(d, aH + ks * 8, dBh + adv, idesc, ks ? 1u : (uint32_t)(kc >= istep));
                         umma_tf32_ts(d, aH + ks * 8, dBl + adv, idesc, 1);
                         umma_tf32_ts(d, aL + ks * 8, dBh + adv, idesc, 1);
                     }
                     umma_commit(&a_empty[ra.s]);
                     if (!b_resident) umma_commit(&b_empty[rb.s]);
-                    if (kc == nk - 1) umma_commit(&acc_full[buf]);
+                    if (kc + istep >= nk) umma_commit(&acc_full[buf]);
                 }
                 __syncwarp();
             }
@@ -723,7 +760,14 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
             for (int gi = half; gi < ngrp; gi += 2) {
                 const int c0 = gi * 16;
                 float v[16];
-                tmem_ld16(taddr + (uint32_t)c0, v);
+                if constexpr (DUAL) {
+                    float v2[16];
+                    tmem_ld16x2(taddr + (uint32_t)c0, taddr + (uint32_t)(P3_DUAL_NMAX + c0), v, v2);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += v2[i];
+                } else {
+                    tmem_ld16(taddr + (uint32_t)c0, v);
+                }
                 float* o = out + (int64_t)c0 * P;
                 float rv[EPI == 1 ? 16 : 1];
                 if constexpr (EPI == 1) {   // skip connection: the loads go out together, ahead of the stores
@@ -768,7 +812,19 @@ __global__ void __launch_bounds__(P3_THREADS, 1) bayes_pointwise_tc3_kernel(cons
     }
     tc_fence_before();
     __syncthreads();
+    if (TRACE && tid == 0) tr(trace_on, 6, 43, 0);
     if (warp == P3_W_MMA) tmem_dealloc(tmem, 512);
+}
+
+using P3Kernel = void (*)(const BemBayesPointwiseParams, int, int, int, int64_t, const float*, const float*, uint32_t, uint32_t, int);
+template <bool LN, bool DUAL>
+static P3Kernel p3_pick(int variant) {   // 0 plain, 1 skip connection, 2 PReLU, 3 plain + timeline
+    switch (variant) {
+        case 1: return bayes_pointwise_tc3_kernel<LN, false, 1, DUAL>;
+        case 2: return bayes_pointwise_tc3_kernel<LN, false, 2, DUAL>;
+        case 3: return bayes_pointwise_tc3_kernel<LN, true, 0, DUAL>;
+        default: return bayes_pointwise_tc3_kernel<LN, false, 0, DUAL>;
+    }
 }
 
 static void tc_tiling(int cin, int cout, int nmax, int& ntiles, int& NT, int& nk) {
@@ -884,25 +940,24 @@ int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t str
         const int RS = std::max(2 * P3_PW, std::min(P3_RS_MAX, (int)((220 * 1024 - fixed) / (int)P3_RAW_BYTES)) / P3_PW * P3_PW);
         const int smem_bytes = RS * (int)P3_RAW_BYTES + fixed;
         if (smem_bytes > 227 * 1024) return BEM_ERR_UNSUPPORTED;
-        static int attr3[64] = {0}, sms[64] = {0};
-        if (attr3[dev] < smem_bytes) {
-            cudaError_t e = cudaFuncSetAttribute(bayes_pointwise_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-            if (e == cudaSuccess)
-                e = cudaFuncSetAttribute(bayes_pointwise_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-            if (e != cudaSuccess) return (int)e;
-            attr3[dev] = smem_bytes;
-        }
+        static int attr3[64][2][2][4] = {}, sms[64] = {0};
         if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
         if (!p.prepacked) launch_pdl(bayes_weight_pack_kernel, dim3(pack_blocks + vec_blocks), dim3(256), 0, stream, p, NT, ntiles, nk, pack, 1, vec);
         const int64_t n_items = (int64_t)p.batch * ptiles * ntiles;
         if (n_items >= (1ll << 31)) return BEM_ERR_UNSUPPORTED;
         const int grid = (int)std::min<int64_t>(n_items, sms[dev]);
-        auto kernel = p.ln_gamma ? (trace_on ? bayes_pointwise_tc3_kernel<true, true> : bayes_pointwise_tc3_kernel<true, false>)
-                                 : (trace_on ? bayes_pointwise_tc3_kernel<false, true> : bayes_pointwise_tc3_kernel<false, false>);
         if (p.residual && p.prelu_slope) return BEM_ERR_UNSUPPORTED;   // no caller combines them (the PReLU layers have no skip)
-        if (p.prelu_slope) kernel = p.ln_gamma ? bayes_pointwise_tc3_kernel<true, false, 2> : bayes_pointwise_tc3_kernel<false, false, 2>;
-        if (p.residual) kernel = p.ln_gamma ? bayes_pointwise_tc3_kernel<true, false, 1> : bayes_pointwise_tc3_kernel<false, false, 1>;
-        if (trace_on || p.prelu_slope || p.residual) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        // two MMA issuers pay off when the issue rate bounds the tile: many input channels into a narrow tile (A/B knob: BEM_PW_NO_DUAL)
+        static const int no_dual = env_int("BEM_PW_NO_DUAL", 0);
+        const int ln = p.ln_gamma ? 1 : 0, dual = (NT <= P3_DUAL_NMAX && nk >= 4 && !no_dual) ? 1 : 0;
+        const int variant = p.residual ? 1 : p.prelu_slope ? 2 : trace_on ? 3 : 0;   // the timeline build has the plain epilogue only
+        const P3Kernel kernel = ln ? (dual ? p3_pick<true, true>(variant) : p3_pick<true, false>(variant))
+                                   : (dual ? p3_pick<false, true>(variant) : p3_pick<false, false>(variant));
+        if (attr3[dev][ln][dual][variant] < smem_bytes) {
+            const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+            if (e != cudaSuccess) return (int)e;
+            attr3[dev][ln][dual][variant] = smem_bytes;
+        }
         launch_pdl(kernel, dim3(grid), dim3(P3_THREADS), smem_bytes, stream, p, NT, ntiles, (int)ptiles, n_items, pack, vec, RS, BS, b_resident);
         return (int)cudaGetLastError();
     }

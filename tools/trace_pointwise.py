@@ -17,7 +17,7 @@ rec = sorted(((buf[4 * i + 2], buf[4 * i], buf[4 * i + 1]) for i in range(n) if 
 n = len(rec)
 t0 = rec[0][0]
 names = {2: "prod slot free", 3: "prod landed", 1: "prod issue", 10: "xf0 raw_full", 11: "xf1 raw_full", 12: "xf0 a_empty", 13: "xf1 a_empty", 14: "xf0 arrive", 15: "xf1 arrive",
-         20: "mma acc_empty", 21: "mma a_full", 30: "epi acc_full", 31: "epi done"}
+         40: "cta entry", 41: "prologue done", 42: "pdl wait done", 43: "cta exit", 20: "mma acc_empty", 21: "mma a_full", 22: "mma2 acc_empty", 23: "mma2 a_full", 30: "epi acc_full", 31: "epi done"}
 print("records", n, "span clk", rec[-1][0] - t0)
 lim = int(os.environ.get("LINES", 150)); skip = int(os.environ.get("SKIP", 400))
 only = os.environ.get("ONLY")
