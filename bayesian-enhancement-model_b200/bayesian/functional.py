@@ -258,13 +258,13 @@ class _PointwiseFn(torch.autograd.Function):
         return dx, dw, db, None
 
 
-def grouped_pointwise(x, w, bias=None):
+def grouped_pointwise(x, w, bias=None, pack_cache=None):
     """Grouped 1x1 convolution as the reference's `F.conv1d(x.view(B, K*Cin, L), w.view(K*Cout, Cin, 1), groups=K)`
     (vmamba.py:659-661): x: (B, K, Cin, L) (any stride between (b, k) images), w: (K, Cout, Cin) -> (B, K, Cout, L).
     The K groups are the kernel's weight sets. Inference only (no autograd)."""
     B, K, Cin, L = x.shape
     xv = x.reshape(B * K, Cin, L) if x.is_contiguous() else x.flatten(0, 1)
-    out = _pointwise_raw(xv, w=w, bias=bias, n_samples=K, interleave=True)
+    out = _pointwise_raw(xv, w=w, bias=bias, n_samples=K, interleave=True, pack_cache=pack_cache)
     return out.view(B, K, -1, L)
 
 

@@ -121,7 +121,7 @@ def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_pr
         dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
         # dt_proj: the K directions as the weight sets of the tcgen05 pointwise kernel; dts is read as a strided channel
         # slice of x_dbl (no .contiguous() copy) — vmamba.py:661
-        dts = BF.grouped_pointwise(dts, dt_projs_weight)
+        dts = BF.grouped_pointwise(dts, dt_projs_weight, pack_cache=None if pack_cache is None else pack_cache.setdefault("dt_pack", {}))
     xs = xs.view(B, -1, L)
     dts = dts.contiguous().view(B, -1, L)
     As = -A_logs.to(torch.float).exp()                  # (K * D, N)
