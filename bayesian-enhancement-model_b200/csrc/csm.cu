@@ -161,7 +161,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) csm_scan_tiled(const CsmArgs p) {
     pdl_trigger();
     pdl_wait();
-    __shared__ T tile[32][33];
+    __shared__ T tile[4][32][33];   // one_by_one: a tile per direction, all loads in flight before the one barrier
     const int H = p.H, W = p.W;
     const int64_t L = (int64_t)H * W;
     const int tilesW = (W + 31) / 32;
@@ -170,17 +170,30 @@ __global__ void __launch_bounds__(256) csm_scan_tiled(const CsmArgs p) {
     const int tx = threadIdx.x, ty = threadIdx.y;
     const T* src = reinterpret_cast<const T*>(p.src);
     T* dst = reinterpret_cast<T*>(p.dst);
+    const int nsrc = p.obo ? 4 : 1;
+    T r[4][4];
+#pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if (k == 0 || p.obo) {
-            if (k > 0) __syncthreads();
+        if (k < nsrc) {
             const T* s = src + (p.obo ? (((int64_t)b * 4 + k) * p.C + c) : ((int64_t)b * p.C + c)) * L;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int h = h0 + ty + 8 * i, w = w0 + tx;
-                if (h < H && w < W) tile[ty + 8 * i][tx] = s[(int64_t)h * W + w];
+                r[k][i] = (h < H && w < W) ? s[(int64_t)h * W + w] : csm_from_f<T>(0.f);
             }
-            __syncthreads();
         }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < nsrc) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tile[k][ty + 8 * i][tx] = r[k][i];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int ks = p.obo ? k : 0;
         T* d = dst + (((int64_t)b * 4 + k) * p.C + c) * L;
         if ((k & 1) == 0) {
 #pragma unroll
@@ -189,7 +202,7 @@ __global__ void __launch_bounds__(256) csm_scan_tiled(const CsmArgs p) {
                 if (h < H && w < W) {
                     int64_t pos = (int64_t)h * W + w;
                     if (k == 2) pos = L - 1 - pos;
-                    d[pos] = tile[ty + 8 * i][tx];
+                    d[pos] = tile[ks][ty + 8 * i][tx];
                 }
             }
         } else {
@@ -199,7 +212,7 @@ __global__ void __launch_bounds__(256) csm_scan_tiled(const CsmArgs p) {
                 if (h < H && w < W) {
                     int64_t pos = (int64_t)w * H + h;
                     if (k == 3) pos = L - 1 - pos;
-                    d[pos] = tile[tx][ty + 8 * i];
+                    d[pos] = tile[ks][tx][ty + 8 * i];
                 }
             }
         }
@@ -210,7 +223,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) csm_merge_tiled(const CsmArgs p) {
     pdl_trigger();
     pdl_wait();
-    __shared__ T tile[32][33];
+    __shared__ T tile[2][32][33];   // the two column-major directions are transposed through shared memory
     const int H = p.H, W = p.W;
     const int64_t L = (int64_t)H * W;
     const int tilesW = (W + 31) / 32;
@@ -219,7 +232,7 @@ __global__ void __launch_bounds__(256) csm_merge_tiled(const CsmArgs p) {
     const int tx = threadIdx.x, ty = threadIdx.y;
     const T* src = reinterpret_cast<const T*>(p.src);
     T* dst = reinterpret_cast<T*>(p.dst);
-    T v[4][4];   // [k][i]
+    T v[4][4];   // [k][i]; all 16 loads of a thread are in flight before the one barrier
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const T* s = src + (((int64_t)b * 4 + k) * p.C + c) * L;
@@ -227,29 +240,30 @@ __global__ void __launch_bounds__(256) csm_merge_tiled(const CsmArgs p) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int h = h0 + ty + 8 * i, w = w0 + tx;
-                if (h < H && w < W) {
-                    int64_t pos = (int64_t)h * W + w;
-                    if (k == 2) pos = L - 1 - pos;
-                    v[k][i] = s[pos];
-                } else {
-                    v[k][i] = csm_from_f<T>(0.f);
-                }
+                int64_t pos = (int64_t)h * W + w;
+                if (k == 2) pos = L - 1 - pos;
+                v[k][i] = (h < H && w < W) ? s[pos] : csm_from_f<T>(0.f);
             }
         } else {
-            __syncthreads();
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int w = w0 + ty + 8 * i, h = h0 + tx;
-                if (h < H && w < W) {
-                    int64_t pos = (int64_t)w * H + h;
-                    if (k == 3) pos = L - 1 - pos;
-                    tile[ty + 8 * i][tx] = s[pos];   // tile[w][h]
-                }
+                int64_t pos = (int64_t)w * H + h;
+                if (k == 3) pos = L - 1 - pos;
+                v[k][i] = (h < H && w < W) ? s[pos] : csm_from_f<T>(0.f);   // element (w, h) of the transposed tile
             }
-            __syncthreads();
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[k][i] = tile[tx][ty + 8 * i];   // (h = ty + 8i, w = tx)
         }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        tile[0][ty + 8 * i][tx] = v[1][i];   // tile[w][h]
+        tile[1][ty + 8 * i][tx] = v[3][i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[1][i] = tile[0][tx][ty + 8 * i];   // (h = ty + 8i, w = tx)
+        v[3][i] = tile[1][tx][ty + 8 * i];
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
