@@ -280,10 +280,159 @@ __global__ void __launch_bounds__(256) csm_merge_tiled(const CsmArgs p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// fp32, H % 4 == 0 and W % 4 == 0 (levels 0 and 1 of the BEM nets): the same tile transposes with 16-byte global accesses.
+// Tile = 64 x 64; a thread owns four float4: along w for the row-major directions, along h for the column-major ones
+// (position w * H + h is contiguous in h); a reversed direction stores its float4 mirrored at L - 4 - pos.
+// grid = (tilesW * tilesH, C, B), block = 256
+// ---------------------------------------------------------------------------------------------------
+constexpr int CSM_T = 64, CSM_LD = 65;
+__device__ __forceinline__ float4 csm_rev4(float4 v) { return make_float4(v.w, v.z, v.y, v.x); }
+
+__global__ void __launch_bounds__(256) csm_scan_tiled4(const CsmArgs p) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float tile[2][CSM_T][CSM_LD];
+    const int H = p.H, W = p.W;
+    const int64_t L = (int64_t)H * W;
+    const int tilesW = (W + CSM_T - 1) / CSM_T;
+    const int h0 = (blockIdx.x / tilesW) * CSM_T, w0 = (blockIdx.x % tilesW) * CSM_T;
+    const int c = blockIdx.y, b = blockIdx.z;
+    const int q = threadIdx.x & 15, r = threadIdx.x >> 4;   // float4 column / row within a 16-row band
+    const float* src = reinterpret_cast<const float*>(p.src);
+    float* dst = reinterpret_cast<float*>(p.dst);
+    const int nsrc = p.obo ? 4 : 1;
+    float4 v[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < nsrc) {
+            const float* s = src + (p.obo ? (((int64_t)b * 4 + k) * p.C + c) : ((int64_t)b * p.C + c)) * L;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int h = h0 + r + 16 * i, w = w0 + 4 * q;
+                v[k][i] = (h < H && w < W) ? *reinterpret_cast<const float4*>(s + (int64_t)h * W + w) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    // the column-major directions go through shared memory: direction 1 from tile 0, direction 3 from tile 1 (one_by_one) or 0
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        if (t == 0 || p.obo) {
+            const int k = p.obo ? 1 + 2 * t : 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float* row = &tile[t][r + 16 * i][4 * q];
+                row[0] = v[k][i].x; row[1] = v[k][i].y; row[2] = v[k][i].z; row[3] = v[k][i].w;
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; k += 2) {   // row-major directions straight from registers
+        const int ks = p.obo ? k : 0;
+        float* d = dst + (((int64_t)b * 4 + k) * p.C + c) * L;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int h = h0 + r + 16 * i, w = w0 + 4 * q;
+            if (h < H && w < W) {
+                const int64_t pos = (int64_t)h * W + w;
+                if (k == 0) *reinterpret_cast<float4*>(d + pos) = v[ks][i];
+                else *reinterpret_cast<float4*>(d + (L - 4 - pos)) = csm_rev4(v[ks][i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 1; k < 4; k += 2) {
+        const int t = (p.obo && k == 3) ? 1 : 0;
+        float* d = dst + (((int64_t)b * 4 + k) * p.C + c) * L;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int wl = r + 16 * i, hl = 4 * q;
+            const int w = w0 + wl, h = h0 + hl;
+            if (h < H && w < W) {
+                const float4 o = make_float4(tile[t][hl][wl], tile[t][hl + 1][wl], tile[t][hl + 2][wl], tile[t][hl + 3][wl]);
+                const int64_t pos = (int64_t)w * H + h;
+                if (k == 1) *reinterpret_cast<float4*>(d + pos) = o;
+                else *reinterpret_cast<float4*>(d + (L - 4 - pos)) = csm_rev4(o);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) csm_merge_tiled4(const CsmArgs p) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float tile[2][CSM_T][CSM_LD];
+    const int H = p.H, W = p.W;
+    const int64_t L = (int64_t)H * W;
+    const int tilesW = (W + CSM_T - 1) / CSM_T;
+    const int h0 = (blockIdx.x / tilesW) * CSM_T, w0 = (blockIdx.x % tilesW) * CSM_T;
+    const int c = blockIdx.y, b = blockIdx.z;
+    const int q = threadIdx.x & 15, r = threadIdx.x >> 4;
+    const float* src = reinterpret_cast<const float*>(p.src);
+    float* dst = reinterpret_cast<float*>(p.dst);
+    float4 v[4][4];   // all 16 loads of a thread in flight before the one barrier
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float* s = src + (((int64_t)b * 4 + k) * p.C + c) * L;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if ((k & 1) == 0) {
+                const int h = h0 + r + 16 * i, w = w0 + 4 * q;
+                const int64_t pos = (int64_t)h * W + w;
+                if (h < H && w < W) v[k][i] = k == 0 ? *reinterpret_cast<const float4*>(s + pos) : csm_rev4(*reinterpret_cast<const float4*>(s + (L - 4 - pos)));
+                else v[k][i] = zero;
+            } else {
+                const int w = w0 + r + 16 * i, h = h0 + 4 * q;
+                const int64_t pos = (int64_t)w * H + h;
+                if (h < H && w < W) v[k][i] = k == 1 ? *reinterpret_cast<const float4*>(s + pos) : csm_rev4(*reinterpret_cast<const float4*>(s + (L - 4 - pos)));
+                else v[k][i] = zero;
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {   // element j of the float4 is pixel (h = 4q + j, w = r + 16 i)
+            const int wl = r + 16 * i, hl = 4 * q;
+            const float4 o = v[1 + 2 * t][i];
+            tile[t][hl][wl] = o.x; tile[t][hl + 1][wl] = o.y; tile[t][hl + 2][wl] = o.z; tile[t][hl + 3][wl] = o.w;
+        }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int hl = r + 16 * i, wl = 4 * q;
+        const int h = h0 + hl, w = w0 + wl;
+        if (h < H && w < W) {
+            const float4 a1 = make_float4(tile[0][hl][wl], tile[0][hl][wl + 1], tile[0][hl][wl + 2], tile[0][hl][wl + 3]);
+            const float4 a3 = make_float4(tile[1][hl][wl], tile[1][hl][wl + 1], tile[1][hl][wl + 2], tile[1][hl][wl + 3]);
+            const int64_t pos = (int64_t)h * W + w;
+            if (p.obo) {
+                *reinterpret_cast<float4*>(dst + (((int64_t)b * 4 + 0) * p.C + c) * L + pos) = v[0][i];
+                *reinterpret_cast<float4*>(dst + (((int64_t)b * 4 + 1) * p.C + c) * L + pos) = a1;
+                *reinterpret_cast<float4*>(dst + (((int64_t)b * 4 + 2) * p.C + c) * L + pos) = v[2][i];
+                *reinterpret_cast<float4*>(dst + (((int64_t)b * 4 + 3) * p.C + c) * L + pos) = a3;
+            } else {   // (y0 + y2) + (y1 + y3), csm_triton.py:60-62
+                const float4 a0 = v[0][i], a2 = v[2][i];
+                *reinterpret_cast<float4*>(dst + ((int64_t)b * p.C + c) * L + pos) =
+                    make_float4((a0.x + a2.x) + (a1.x + a3.x), (a0.y + a2.y) + (a1.y + a3.y), (a0.z + a2.z) + (a1.z + a3.z),
+                                (a0.w + a2.w) + (a1.w + a3.w));
+            }
+        }
+    }
+}
+
 template <typename T>
 static int csm_launch(const CsmArgs& a, bool merge, cudaStream_t stream) {
     const bool tiled = a.img_cf && a.seq_cf && a.scans == 0 && a.C <= 65535 && a.B <= 65535;
-    if (tiled) {
+    const bool vec4 = tiled && sizeof(T) == 4 && a.H % 4 == 0 && a.W % 4 == 0 &&
+                      ((reinterpret_cast<uintptr_t>(a.src) | reinterpret_cast<uintptr_t>(a.dst)) & 15) == 0;
+    if (vec4) {
+        dim3 grid(((a.W + CSM_T - 1) / CSM_T) * ((a.H + CSM_T - 1) / CSM_T), a.C, a.B);
+        if (merge) launch_pdl(csm_merge_tiled4, grid, dim3(256), 0, stream, a);
+        else launch_pdl(csm_scan_tiled4, grid, dim3(256), 0, stream, a);
+    } else if (tiled) {
         dim3 grid(((a.W + 31) / 32) * ((a.H + 31) / 32), a.C, a.B), block(32, 8);
         if (merge) launch_pdl(csm_merge_tiled<T>, dim3(grid), dim3(block), 0, stream, a);
         else launch_pdl(csm_scan_tiled<T>, dim3(grid), dim3(block), 0, stream, a);

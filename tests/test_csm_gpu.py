@@ -44,9 +44,10 @@ def test_golden_reference_vectors(golden_csm, scans, icf, ocf, obo):
 
 
 @pytest.mark.parametrize("scans,icf,ocf,obo", list(_layouts()))
-@pytest.mark.parametrize("shape", [(2, 5, 56, 57), (1, 3, 1, 9), (1, 2, 33, 31)])
+@pytest.mark.parametrize("shape", [(2, 5, 56, 57), (1, 3, 1, 9), (1, 2, 33, 31), (2, 3, 56, 60), (1, 2, 132, 72), (1, 2, 64, 128)])
 def test_against_oracle_all_layouts(shape, scans, icf, ocf, obo):
-    """non-square, non-multiple-of-32 shapes like the reference's own check (csm_triton.py:514: 56 x 57)"""
+    """non-square, non-multiple-of-32 shapes like the reference's own check (csm_triton.py:514: 56 x 57); the shapes with H and W
+    multiples of 4 take the 16-byte tiled kernels (partial, multiple and exact 64 x 64 tiles)"""
     import bem_b200
     Bt, Cc, H, W = shape
     rng = np.random.RandomState(0)
