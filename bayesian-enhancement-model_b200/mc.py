@@ -87,13 +87,15 @@ class MCArena:
         base = self.buffer.data_ptr()
         rows, blocks = [], []
         self._ptrs = []
+        self.views = {}    # id(layer) -> {"weight": view, "bias": view} into self.buffer (several arenas may serve one network)
         for e, (L, which, mu, rho, sid, off) in enumerate(tensors):
             n = mu.numel()
             rows.append([mu.data_ptr(), rho.data_ptr(), base + 4 * off, n, sid])
             self._ptrs.append((mu, rho, mu.data_ptr(), rho.data_ptr()))
             for b0 in range(0, (n + 3) // 4, 256):
                 blocks.append([e, b0])
-            L.__dict__.setdefault("_arena_views", {})[which] = self.buffer[off:off + n].view(mu.shape)
+            self.views.setdefault(id(L), {})[which] = self.buffer[off:off + n].view(mu.shape)
+            L.__dict__["_arena_views"] = self.views[id(L)]      # the most recent arena's views (introspection, tests)
         self.entries = torch.tensor(rows, dtype=torch.int64).to(self.device)
         self.blocks = torch.tensor(blocks, dtype=torch.int32).to(self.device)
         self.n_blocks = len(blocks)
@@ -105,7 +107,7 @@ class MCArena:
 
     def attach(self, on: bool = True):
         for L in self.layers:
-            L._arena = L.__dict__.get("_arena_views") if on else None
+            L._arena = self.views[id(L)] if on else None
 
     def draw(self, sample_id: Optional[int] = None, plan=None):
         """fill the arena for global sample `sample_id`; None = read the index from the device word `self.sample0`.
@@ -136,6 +138,17 @@ class MCArena:
             return fn()
 
 
+class _Lane:
+    """One in-flight sample of an MCSampler: its own weight arena, captured graphs and streams. The library's scratch buffers
+    are per stream, so the graphs of two lanes replay concurrently without sharing anything but the (read-only) parameters."""
+
+    def __init__(self):
+        self.arena = None
+        self.graphs = {}
+        self.capture_stream = None
+        self.stream = None
+
+
 class MCSampler:
     """Draws Monte-Carlo predictions of a Bayesian network for one input.
 
@@ -146,10 +159,12 @@ class MCSampler:
     arena      : draw all layers' weights with one launch per sample (philox source, batch 1); same numbers as without
     graph      : capture the forward of one sample as a CUDA graph per input shape and replay it (needs `arena`); the
                  reference's ~700 launches per sample are otherwise bound by the host
+    lanes      : samples in flight at once (needs `graph`): each lane replays its own graph on its own stream, so the ramp
+                 and tail of one sample's kernels (148 per sample, 5-100 us each) fill with the other's. Same numbers.
     """
 
     def __init__(self, net, seed: int = 287128, batch: int = 1, eps_source: str = "philox", out_index: int = -1,
-                 post: Optional[Callable] = None, arena: bool = True, graph: bool = False):
+                 post: Optional[Callable] = None, arena: bool = True, graph: bool = False, lanes: int = 1):
         self.net = net
         self.seed = seed
         self.batch = max(1, int(batch))
@@ -158,27 +173,37 @@ class MCSampler:
         self.post = post or (lambda y: torch.clamp(y, 0, 1))   # eval.py:201
         self.use_arena = bool(arena) and eps_source == "philox" and self.batch == 1
         self.use_graph = bool(graph) and self.use_arena
-        self._arena = None
-        self._graphs = {}
+        self._lanes = [_Lane() for _ in range(max(1, int(lanes)) if self.use_graph else 1)]
         bayesian.set_prediction_type(net, deterministic=False)
 
+    @property
+    def _arena(self):
+        return self._lanes[0].arena
+
+    @property
+    def _graphs(self):
+        return self._lanes[0].graphs
+
     # ------------------------------------------------------------------------------------------------
-    def _get_arena(self):
-        if self._arena is None or not self._arena.valid():
-            self._arena = MCArena(self.net, self.seed)
-            self._graphs = {}
-        return self._arena
+    def _get_arena(self, lane=None):
+        lane = lane or self._lanes[0]
+        if lane.arena is None or not lane.arena.valid():
+            lane.arena = MCArena(self.net, self.seed)
+            lane.graphs = {}
+        return lane.arena
 
     def _forward_one(self, x):
         y = self.net(x)
         y = y[self.out_index] if isinstance(y, (list, tuple)) else y
         return self.post(y)
 
-    def _graph_for(self, x):
+    def _graph_for(self, x, lane=None):
+        """(graph, static input, static output) of `lane` for inputs like x; captured with the lane's arena attached"""
+        lane = lane or self._lanes[0]
         key = (tuple(x.shape), x.dtype, x.device)
-        rec = self._graphs.get(key)
+        rec = lane.graphs.get(key)
         if rec is None:
-            arena = self._get_arena()
+            arena = self._get_arena(lane)
             static_x = x.clone()
             side = torch.cuda.Stream(device=x.device)
             side.wait_stream(torch.cuda.current_stream(x.device))
@@ -187,11 +212,59 @@ class MCSampler:
                     arena.forward_planned(key, None, lambda: self._forward_one(static_x))
             torch.cuda.current_stream(x.device).wait_stream(side)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            if lane.capture_stream is None:
+                lane.capture_stream = torch.cuda.Stream(device=x.device)
+            with torch.cuda.graph(g, stream=lane.capture_stream):
                 static_y = arena.forward_planned(key, None, lambda: self._forward_one(static_x))
             rec = (g, static_x, static_y)
-            self._graphs[key] = rec
+            lane.graphs[key] = rec
         return rec
+
+    def _lane_graphs(self, x, n):
+        """the first min(lanes, n) lanes with their graphs for inputs like x (captured on first use)"""
+        lanes = self._lanes[: max(1, min(len(self._lanes), n))]
+        bayesian.set_mc_config(self.net, mc_samples=1, eps_source="philox", seed=self.seed, sample0=0)
+        recs = []
+        for lane in lanes:
+            arena = self._get_arena(lane)
+            key = (tuple(x.shape), x.dtype, x.device)
+            if key not in lane.graphs:
+                arena.attach(True)
+                try:
+                    self._graph_for(x, lane)
+                finally:
+                    arena.attach(False)
+            recs.append(lane.graphs[key])
+            if lane.stream is None:
+                lane.stream = torch.cuda.Stream(device=x.device)
+        return lanes, recs
+
+    @torch.no_grad()
+    def samples_to_host(self, x_host: torch.Tensor, out_host: torch.Tensor, sample_ids: Sequence[int]):
+        """len(sample_ids) predictions of one (pinned) host image into the rows of a (pinned) host buffer, the lanes working
+        side by side: per sample the image goes H2D into the lane's graph input and the prediction D2H from its output.
+        Returns after everything has landed."""
+        ids = list(sample_ids)
+        if not (self.use_graph and x_host.shape[0] == 1 and len(self._lanes) > 1 and len(ids) > 1):
+            for i, sid in enumerate(ids):
+                self.sample_to_host(x_host, out_host[i:i + 1], sid)
+            return out_host
+        dev = next(self.net.parameters()).device
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream(dev)
+            lanes, recs = self._lane_graphs(torch.empty(x_host.shape, dtype=x_host.dtype, device=dev), len(ids))
+            for lane in lanes:
+                lane.stream.wait_stream(cur)
+            for i, sid in enumerate(ids):
+                lane, (g, static_x, static_y) = lanes[i % len(lanes)], recs[i % len(lanes)]
+                with torch.cuda.stream(lane.stream):
+                    static_x.copy_(x_host, non_blocking=True)
+                    lane.arena.sample0.fill_(int(sid))
+                    g.replay()
+                    out_host[i].copy_(static_y[0], non_blocking=True)
+            for lane in lanes:
+                lane.stream.synchronize()
+        return out_host
 
     @torch.no_grad()
     def sample_to_host(self, x_host: torch.Tensor, out_host: torch.Tensor, sample_id: int):
@@ -228,6 +301,25 @@ class MCSampler:
         outs = []
         ids = list(sample_ids)
         if self.use_arena and ids and x.is_cuda and x.shape[0] == 1:
+            if self.use_graph and len(self._lanes) > 1 and len(ids) > 1:
+                cur = torch.cuda.current_stream(x.device)
+                lanes, recs = self._lane_graphs(x, len(ids))
+                for lane, (g, static_x, static_y) in zip(lanes, recs):
+                    lane.stream.wait_stream(cur)
+                    with torch.cuda.stream(lane.stream):
+                        static_x.copy_(x)
+                outs = [None] * len(ids)
+                for i, sid in enumerate(ids):
+                    lane, (g, static_x, static_y) = lanes[i % len(lanes)], recs[i % len(lanes)]
+                    with torch.cuda.stream(lane.stream):
+                        lane.arena.sample0.fill_(int(sid))
+                        g.replay()
+                        outs[i] = static_y.clone()
+                for lane in lanes:
+                    cur.wait_stream(lane.stream)
+                for o in outs:
+                    o.record_stream(cur)
+                return torch.cat(outs, dim=0)
             arena = self._get_arena()
             bayesian.set_mc_config(self.net, mc_samples=1, eps_source="philox", seed=self.seed, sample0=0)
             arena.attach(True)

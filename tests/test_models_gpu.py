@@ -179,6 +179,28 @@ def test_pack_plan_batches_the_pack_steps_without_changing_a_bit():
     assert planned_launches == plain_launches - len(plan.entries) + 1
 
 
+def test_mc_sampler_lanes_give_the_same_predictions_bit_for_bit():
+    """two samples in flight (own arena, graph, streams and scratch per lane) == one lane, for device and host-buffer calls"""
+    from bem_b200 import mc, network
+    torch.manual_seed(0)
+    net = network.build_bayesian_model().cuda().eval()
+    x = torch.rand(1, 3, 32, 48, device="cuda")
+    ids = [0, 3, 4, 11, 12]
+    one = mc.MCSampler(net, seed=7, arena=True, graph=True, lanes=1).sample(x, ids)
+    two_sampler = mc.MCSampler(net, seed=7, arena=True, graph=True, lanes=2)
+    two = two_sampler.sample(x, ids)
+    again = two_sampler.sample(x, ids[::-1])
+    assert torch.equal(one, two)
+    assert torch.equal(again.flip(0), two)
+    xh = x.cpu().pin_memory()
+    oh = torch.empty(len(ids), 3, 32, 48).pin_memory()
+    two_sampler.samples_to_host(xh, oh, ids)
+    assert torch.equal(oh, one.cpu())
+    res = mc.mc_infer(two_sampler, x, 7)
+    ref = mc.mc_infer(mc.MCSampler(net, seed=7, arena=True, graph=True), x, 7)
+    assert res["index"] == ref["index"] and torch.equal(res["best"], ref["best"]) and torch.equal(res["scores"], ref["scores"])
+
+
 def test_mc_sampler_host_buffer_call_matches_device_call():
     """sample_to_host (pinned image in, pinned prediction out; the bench's e2e call) == sample on device, graph and eager"""
     from bem_b200 import mc, network
