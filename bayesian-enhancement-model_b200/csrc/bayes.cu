@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(512) bayes_depthwise3_smem_kernel(const BemBay
 // resolution, UNet_arch.py:423-431): register-tiled direct convolution. One thread = 4 output columns of one row x COT
 // output channels; the weights of the CTA's output-channel tile sit in shared memory as [ci][tap][COT] (broadcast LDS.128),
 // input rows are read as one float4 + two clamped / masked halo scalars. The library path splits these shapes into five
-// kernels and takes 90 / 430 us at 600x400; this takes ~15 us each.
+// kernels and takes 90 / 430 us at 600x400; this takes 26 us (3 -> 40) and 55 us (40 -> 3, load-latency bound).
 // ------------------------------------------------------------------------------------------------
 template <int COT, bool VEC>
 __global__ void __launch_bounds__(256) conv3x3_direct_kernel(const BemConv3x3Params p) {

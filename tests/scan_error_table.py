@@ -1,5 +1,6 @@
-"""Diagnostic (GPU box): normalised max error of the sm_100a scan vs the fp64 oracle, next to the error of the
-reference-order fp32 oracle, for a list of shapes. Not part of the product; reads only this repo."""
+"""Diagnostic (GPU box; `python tests/scan_error_table.py`): normalised max error of the sm_100a scan vs the fp64 oracle, next to
+the error of the reference-order fp32 oracle, for a list of shapes. Test infrastructure (it uses the oracle), not part of the
+product; reads only this repo. Not collected by pytest (no test_ prefix)."""
 import os
 import sys
 
@@ -8,7 +9,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import bem_b200  # noqa: E402
 import oracle  # noqa: E402
 from conftest import nmax_err  # noqa: E402
