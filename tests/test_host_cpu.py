@@ -42,6 +42,74 @@ def test_size_queries_without_gpu(bem):
     assert lib.bem_scan_workspace_bytes(0, 160, 100, 1, 0) == 0
 
 
+def test_pack_table_is_built_on_the_host(bem):
+    """bem_bayes_pointwise_pack_table (no GPU work): tiling, block ranges and workspace carving of every entry"""
+    import ctypes as C
+    L = bem._lib
+    n = 3
+    shapes = [(40, 320, 240000), (160, 40, 240000), (640, 160, 15000)]      # (cin, cout, P)
+    arr = (L.BemBayesPointwiseParams * n)()
+    need = []
+    for e, (cin, cout, P) in zip(arr, shapes):
+        nb = L.lib.bem_bayes_pointwise_workspace_bytes(1, cin, cout)
+        need.append(nb)
+        e.n_samples, e.batch, e.cin, e.cout, e.P = 1, 1, cin, cout, P
+        e.x, e.w, e.out = 0x10000, 0x20000, 0x30000           # never dereferenced on the host
+        e.workspace, e.workspace_bytes = 0x7000000 + 0x1000000 * len(need), nb
+    nbytes = L.lib.bem_bayes_pointwise_pack_table_bytes(n)
+    assert nbytes > 0 and nbytes % n == 0
+
+    class Entry(C.Structure):
+        _fields_ = [("p", L.BemBayesPointwiseParams), ("pack", C.c_void_p), ("vec", C.c_void_p)] + [
+            (k, C.c_int32) for k in ("NT", "ntiles", "nk", "fold_ln", "block0", "nblocks")]
+    assert C.sizeof(Entry) == nbytes // n
+    tab = (Entry * n)()
+    total = C.c_int32(0)
+    assert L.lib.bem_bayes_pointwise_pack_table(arr, n, C.cast(tab, C.c_void_p), C.byref(total)) == 0
+    blocks = 0
+    for t, (cin, cout, P), nb in zip(tab, shapes, need):
+        assert t.block0 == blocks and t.nblocks > 0
+        assert t.nk == (cin + 15) // 16 and t.NT % 16 == 0 and t.NT * t.ntiles >= cout and t.NT <= 192
+        assert t.fold_ln == 1                                                # aligned input -> persistent kernel layout
+        assert t.nblocks == t.ntiles * t.nk + (cout + 7) // 8
+        assert t.pack == t.p.workspace and t.pack < t.vec <= t.p.workspace + nb - 8 * t.NT * t.ntiles
+        blocks += t.nblocks
+    assert total.value == blocks
+    arr[1].workspace_bytes = 16                                              # too small -> workspace error, nothing written past
+    assert L.lib.bem_bayes_pointwise_pack_table(arr, n, C.cast(tab, C.c_void_p), C.byref(total)) == 10002
+    assert L.lib.bem_bayes_pointwise_pack_table(None, n, C.cast(tab, C.c_void_p), C.byref(total)) == 10001
+    assert L.lib.bem_bayes_pointwise_pack_run(None, 1, 1, None) == 10001
+
+
+def test_pack_plan_matches_calls_by_position_and_signature(bem):
+    """functional.PackPlan host logic: only tensors inside the drawn buffer are eligible; a call out of step (or with another
+    signature) makes this and every later call pack for itself"""
+    BF = bem.bayesian.functional
+    buf = torch.zeros(64)
+    lo = buf.data_ptr()
+    plan = BF.PackPlan((lo, lo + 4 * buf.numel()))
+    inside, outside = buf[8:24], torch.zeros(16)
+    assert plan.eligible(inside, None) and plan.eligible(inside, buf[30:32])
+    assert not plan.eligible(outside, None) and not plan.eligible(inside, outside) and not plan.eligible(None, None)
+    with plan.recording():
+        assert BF._ACTIVE_PLAN is plan and plan.mode == "record"
+        plan.entries.append((("a",), None, "ws_a", ()))
+        plan.entries.append((("b",), None, "ws_b", ()))
+    assert BF._ACTIVE_PLAN is None and plan.mode is None
+    with plan.playing():
+        assert plan._lookup(("a",)) is None            # no device table yet: nothing is prepacked
+    plan.table = object()
+    with plan.playing():
+        assert plan._lookup(("a",)) == "ws_a" and plan._lookup(("b",)) == "ws_b" and plan._lookup(("c",)) is None
+    misses = plan.misses
+    with plan.playing():
+        assert plan._lookup(("b",)) is None            # out of step
+        assert plan._lookup(("a",)) is None            # ... stays out of step for the rest of the forward
+    assert plan.misses == misses + 2
+    with plan.playing():                               # the next forward starts over
+        assert plan._lookup(("a",)) == "ws_a"
+
+
 def test_no_cpu_fallback(bem):
     u = torch.randn(1, 4, 16)
     with pytest.raises(RuntimeError):
