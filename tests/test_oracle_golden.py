@@ -155,3 +155,30 @@ def test_network_oracle_matches_reference_model(golden_models):
     eps = _sd(golden_models, "net/eps")
     y = onet.network_forward(sd, x, eps=eps)
     assert nmax_err(y.numpy(), golden_models["net/out_mc"]) < 1e-5
+
+
+@pytest.mark.parametrize("C,hidden,H,W,th,tw,pairs", [(8, 12, 11, 37, 4, 16, 5), (4, 8, 3, 5, 4, 128, 16), (6, 16, 9, 33, 2, 8, 16),
+                                                      (5, 7, 1, 9, 4, 4, 3)])
+def test_tiled_gdmlp_schedule_equals_the_plain_one(C, hidden, H, W, th, tw, pairs):
+    """oracle/gdmlp_tiled.py: the fused single-pass schedule planned for x + gdMlp(norm2(x)) (spatial tiles with halo, gate-pair
+    groups, K-split project_out) is the same function as the reference's op sequence (vmamba.py:128-133, 1331-1333), which in turn
+    is checked against torch's own ops here — ragged tiles, tiles wider than the image, a one-row image"""
+    import torch
+    import torch.nn.functional as F
+    from oracle import gdmlp_tiled as G
+    rng = np.random.default_rng(C * 100 + H)
+    x = rng.standard_normal((C, H, W))
+    gamma, beta = rng.standard_normal(C), rng.standard_normal(C)
+    w1, b1 = rng.standard_normal((2 * hidden, C)), rng.standard_normal(2 * hidden)
+    wd, bd = rng.standard_normal((2 * hidden, 3, 3)), rng.standard_normal(2 * hidden)
+    w2, b2 = rng.standard_normal((C, hidden)), rng.standard_normal(C)
+    plain = G.gdmlp_plain(x, gamma, beta, 1e-5, w1, b1, wd, bd, w2, b2)
+    t = lambda a: torch.from_numpy(np.asarray(a))
+    xn = F.layer_norm(t(x).permute(1, 2, 0), (C,), t(gamma), t(beta), 1e-5).permute(2, 0, 1)[None]
+    y = F.conv2d(xn, t(w1)[:, :, None, None], t(b1))
+    x1, x2 = F.conv2d(y, t(wd)[:, None], t(bd), padding=1, groups=2 * hidden).chunk(2, dim=1)
+    ref = t(x)[None] + F.conv2d(F.gelu(x1) * x2, t(w2)[:, :, None, None], t(b2))
+    assert nmax_err(plain, ref[0].numpy()) < 1e-12
+    tiled, stats = G.gdmlp_tiled(x, gamma, beta, 1e-5, w1, b1, wd, bd, w2, b2, tile_h=th, tile_w=tw, pairs=pairs)
+    assert nmax_err(tiled, plain) < 1e-12
+    assert 1.0 <= stats["fc1_recompute"] <= (th + 2) * (tw + 2) / float(th * tw) + 1e-9
