@@ -182,3 +182,32 @@ def test_tiled_gdmlp_schedule_equals_the_plain_one(C, hidden, H, W, th, tw, pair
     tiled, stats = G.gdmlp_tiled(x, gamma, beta, 1e-5, w1, b1, wd, bd, w2, b2, tile_h=th, tile_w=tw, pairs=pairs)
     assert nmax_err(tiled, plain) < 1e-12
     assert 1.0 <= stats["fc1_recompute"] <= (th + 2) * (tw + 2) / float(th * tw) + 1e-9
+
+
+@pytest.mark.parametrize("D,H,W,N,R", [(3, 5, 7, 1, 2), (2, 4, 4, 3, 1), (4, 1, 9, 1, 3), (2, 6, 2, 2, 2)])
+def test_traversal_aware_ss2d_equals_the_cross_scan_form(D, H, W, N, R):
+    """oracle/ss2d_traversal.py: the SS2D core computed from the image and its transpose only (directions 2 / 3 as backward scans,
+    nothing flipped, merge = (y0 + y2) + T(y1 + y3)) is the reference's cross_scan -> scan -> cross_merge; that form in turn is
+    held against the pinned pieces (cross_scan_oracle, selective_scan_oracle, cross_merge_oracle)"""
+    from oracle import ss2d_traversal as T
+    rng = np.random.default_rng(D * 1000 + H * 10 + W)
+    K = 4
+    x = rng.standard_normal((D, H, W))
+    xw = rng.standard_normal((K, R + 2 * N, D)) * 0.5
+    dtw = rng.standard_normal((K, D, R)) * 0.5
+    dtb = rng.standard_normal((K, D)) * 0.5
+    A = -np.exp(rng.standard_normal((K, D, N)) * 0.3)
+    Dv = rng.standard_normal((K, D))
+    a = T.ss2d_cross_scan_form(x, xw, dtw, dtb, A, Dv)
+    b = T.ss2d_traversal_aware(x, xw, dtw, dtb, A, Dv)
+    assert nmax_err(b, a) < 1e-12
+    # the cross-scan form against the pinned oracle pieces (fp32 scan)
+    L = H * W
+    xs = oracle.cross_scan_oracle(x[None].astype(np.float32))                                  # (1, 4, D, L)
+    x_dbl = np.einsum("kcd,kdl->kcl", xw.astype(np.float32), xs[0])
+    dts = np.einsum("kdr,krl->kdl", dtw.astype(np.float32), x_dbl[:, :R])
+    ys = oracle.selective_scan_oracle(xs.reshape(1, K * D, L), dts.reshape(1, K * D, L), A.reshape(K * D, N).astype(np.float32),
+                                      np.ascontiguousarray(x_dbl[None, :, R:R + N]), np.ascontiguousarray(x_dbl[None, :, R + N:]),
+                                      Dv.reshape(-1).astype(np.float32), None, dtb.reshape(-1).astype(np.float32), True)
+    y = oracle.cross_merge_oracle(np.asarray(ys).reshape(1, K, D, L), H, W)
+    assert nmax_err(np.asarray(y).reshape(D, H, W), a) < 2e-5
