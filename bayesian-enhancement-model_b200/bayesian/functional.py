@@ -78,7 +78,9 @@ class PackPlan:
     matched by position and checked against the recorded signature (weight / bias / LayerNorm pointers, shape, alignment
     class of x) — a call that does not match simply packs for itself as before. Only calls whose weight (and bias) live
     inside `stable` = (first, last) byte address of the buffer the draw fills are eligible: anything computed during the
-    forward is not there yet when run() packs."""
+    forward is not there yet when run() packs.
+    The active plan is process-global state (like torch's grad mode is per thread, this is per process): one planned forward at a
+    time; the lanes of an MCSampler record and capture one after the other and only REPLAY concurrently, which involves no plan."""
 
     def __init__(self, stable):
         self.stable = (int(stable[0]), int(stable[1]))
