@@ -3,6 +3,7 @@
     import bem_b200
     bem_b200.patch.install()            # patches whatever reference modules are already in sys.modules
     bem_b200.patch.install(vmamba=mod)  # or pass modules explicitly
+    bem_b200.patch.uninstall()          # restores what install() replaced
 
 What gets replaced:
   * `csms6s.selective_scan_fn` and the name imported into vmamba.py (basicsr/vmamba/models/vmamba.py:27-30)
@@ -14,6 +15,32 @@ What gets replaced:
 from __future__ import annotations
 
 import sys
+
+_MISSING = object()
+_undo: list = []   # (object, attribute, previous value) of the last install(), newest last
+
+
+def _set(obj, name, value):
+    _undo.append((obj, name, vars(obj).get(name, _MISSING) if isinstance(obj, type) else getattr(obj, name, _MISSING)))
+    setattr(obj, name, value)
+
+
+def uninstall():
+    """put back everything install() replaced (module attributes, SS2D.forward_corev2, sys.modules entries)"""
+    while _undo:
+        obj, name, old = _undo.pop()
+        if obj is sys.modules:
+            if old is _MISSING:
+                sys.modules.pop(name, None)
+            else:
+                sys.modules[name] = old
+        elif old is _MISSING:
+            try:
+                delattr(obj, name)
+            except AttributeError:
+                pass
+        else:
+            setattr(obj, name, old)
 
 
 def install(vmamba=None, csms6s=None, csm_triton=None, replace_bayesian=True):
@@ -29,26 +56,31 @@ def install(vmamba=None, csms6s=None, csm_triton=None, replace_bayesian=True):
             continue
         base = name.rsplit(".", 1)[-1]
         if (csms6s is None and base == "csms6s") or mod is csms6s:
-            mod.selective_scan_fn = selective_scan_fn
-            mod.SelectiveScanCuda = SelectiveScanCuda
-            mod.selective_scan_cuda_oflex = selective_scan_cuda_oflex
-            mod.WITH_SELECTIVESCAN_OFLEX = True
+            _set(mod, "selective_scan_fn", selective_scan_fn)
+            _set(mod, "SelectiveScanCuda", SelectiveScanCuda)
+            _set(mod, "selective_scan_cuda_oflex", selective_scan_cuda_oflex)
+            _set(mod, "WITH_SELECTIVESCAN_OFLEX", True)
             patched.append(name)
         if (csm_triton is None and base == "csm_triton") or mod is csm_triton:
-            mod.cross_scan_fn = cross_scan_fn
-            mod.cross_merge_fn = cross_merge_fn
+            _set(mod, "cross_scan_fn", cross_scan_fn)
+            _set(mod, "cross_merge_fn", cross_merge_fn)
             patched.append(name)
         if (vmamba is None and base == "vmamba" and hasattr(mod, "SS2D")) or mod is vmamba:
-            mod.selective_scan_fn = selective_scan_fn
-            mod.cross_scan_fn = cross_scan_fn
-            mod.cross_merge_fn = cross_merge_fn
+            _set(mod, "selective_scan_fn", selective_scan_fn)
+            _set(mod, "cross_scan_fn", cross_scan_fn)
+            _set(mod, "cross_merge_fn", cross_merge_fn)
             for cls_name in ("SS2Dv2", "SS2D"):
                 cls = getattr(mod, cls_name, None)
                 if cls is not None and "forward_corev2" in vars(cls):
-                    cls.forward_corev2 = forward_corev2_patched
+                    _set(cls, "forward_corev2", forward_corev2_patched)
             patched.append(name)
+
+    def set_module(name, value):
+        _undo.append((sys.modules, name, sys.modules.get(name, _MISSING)))
+        sys.modules[name] = value
     if replace_bayesian:
-        sys.modules["bayesian"] = _bayes
+        set_module("bayesian", _bayes)
         patched.append("bayesian")
-    sys.modules.setdefault("selective_scan_cuda_oflex", selective_scan_cuda_oflex)
+    if "selective_scan_cuda_oflex" not in sys.modules:
+        set_module("selective_scan_cuda_oflex", selective_scan_cuda_oflex)
     return patched

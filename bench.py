@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """bench.py — BASELINE.json's metric on its config.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config mc|c1|hd|train]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+--config mc (default) is the headline below; c1 / hd / train are BASELINE configs[0] / [3] / [4] (bench_configs.py).
 
 metric   : MC-sample images/s of the stage-1 Bayesian condition generator on a synthetic 600x400 image
            (BASELINE.json configs[1]; N > 1 ranks = configs[2]: samples sharded over ranks, weak scaling in samples)
@@ -10,9 +12,12 @@ step     : every rank draws ONE Monte-Carlo sample (one stochastic forward of th
 value    : samples/s summed over ranks, image resident in HBM
 e2e      : the same through the public API with HOST buffers: per step a pinned-host image is copied to the device,
            sampled, and the prediction is read back to the host
-roofline : the dominant kernel of the hot path, the level-0 selective scan forward (B1 KD160 N1 L240000 fp32), timed with
-           CUDA events inside the timed region; algorithmic bytes per SURVEY 8(d)
-cpu_baseline / --impl reference : the CPU restatement of the reference network (oracle/network.py) on the host cores
+roofline : the dominant kernel of the hot path, the level-0 selective scan forward (B1 KD160 N1 L240000 fp32), timed live in
+           this run with CUDA events in a separate pass after the timed region (8 launches per graph replay); bytes per SURVEY 8(d)
+reference_gpu : the reference's own GPU path on the same box (oflex extension recompiled for sm_100a, Triton cross scan / merge,
+           eager Bayesian layers), per kernel and as a whole network — the kernels to beat
+cpu_baseline / --impl reference : the UNMODIFIED reference network (staged under oracle/_ref) on the host cores, pure PyTorch
+           (selective_scan_torch loop); falls back to the CPU restatement oracle/network.py (kind "port") only if it is not staged
 """
 import argparse
 import json
@@ -41,6 +46,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying the CUDA graph")
     ap.add_argument("--lanes", type=int, default=2, help="MC samples in flight per GPU (sampler lanes, each its own graph and stream)")
     ap.add_argument("--job", type=int, default=100, help="samples of the MC job timed after the steps (0 = skip)")
+    ap.add_argument("--config", default="mc", choices=["mc", "c1", "hd", "train"],
+                    help="mc = BASELINE configs[1]/[2] (headline); c1 / hd / train = configs[0] / [3] / [4]")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference-on-GPU columns")
     return ap.parse_args()
 
 
@@ -138,22 +146,30 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------------------------------
 def cpu_reference_run(steps, warmup, budget_s=120.0):
-    """The reference's CPU path for the same workload, restated in oracle/network.py (kind "port": the reference itself is
-    Python and cannot travel to the GPU box). Each step = one MC sample on a top crop of the 600x400 image sized so that
+    """The reference's CPU path for the headline workload. Preferred: the UNMODIFIED reference network staged under
+    oracle/_ref (kind "reference", bench_configs.cpu_reference_network). Fallback when it is not staged: the CPU restatement
+    oracle/network.py (kind "port"; its scan is the C loop, faster than the reference's Python loop)."""
+    import bench_configs as bc
+    if bc._ref().available():
+        return bc.cpu_reference_network(steps, warmup, budget_s, H_IMG, W_IMG)
+    return cpu_port_run(steps, warmup, budget_s)
+
+
+def cpu_port_run(steps, warmup, budget_s=120.0):
+    """oracle/network.py on all host cores: each step = one MC sample on a top crop of the 600x400 image sized so that
     warmup + steps fit the time budget; throughput is scaled to whole images by the pixel fraction."""
     import torch
     import oracle
     from oracle import network as onet
-    import bem_b200
     oracle.build()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
+    import bem_b200   # fallback only (reference not staged): the mirror modules just initialise a reference-format state_dict
     net = bem_b200.network.build_bayesian_model()
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
     img = torch.rand(1, 3, H_IMG, W_IMG)
     gen = torch.Generator().manual_seed(1)
-    # probe: 64 rows
     t0 = time.perf_counter()
     onet.network_forward(sd, img[:, :, :64], generator=gen)
     per_row = (time.perf_counter() - t0) / 64
@@ -176,6 +192,13 @@ def cpu_reference_run(steps, warmup, budget_s=120.0):
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.config in ("c1", "hd"):
+        import bench_configs as bc
+        print(json.dumps(bc.run_scan_config_reference(args.config, args)), flush=True)
+        return
+    if args.config == "train":
+        print(json.dumps({"impl": "reference", "unavailable": "config train: the reference's CPU backward through the Python scan loop is O(L^2) (254 s for one config-1 scan, BASELINE.md section 3); see cpu_baseline of --config train"}), flush=True)
         return
     steps = max(1, min(args.steps, 8))
     r = cpu_reference_run(steps, min(args.warmup, 1), budget_s=150.0)
@@ -271,6 +294,19 @@ def main_ours(args):
     torch.backends.cudnn.allow_tf32 = False          # fp32 everywhere: the metric is quoted in the reference's precision
     torch.backends.cuda.matmul.allow_tf32 = False
 
+    if args.config != "mc":
+        import bench_configs as bc
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        line = bc.run_train_config(args, rank, world, dev) if args.config == "train" else bc.run_scan_config(args.config, args, rank, world, dev)
+        if rank == 0:
+            line["clocks"] = clocks.stop()
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     torch.manual_seed(0)                              # same random-init weights on every rank
     net = network.build_bayesian_model().to(dev).eval()
     # product path: one-launch weight arena + the forward of one sample captured as a CUDA graph and replayed
@@ -298,12 +334,22 @@ def main_ours(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    steps(args.warmup, args.steps)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    # the timed region = EXACTLY K steps between barrier + synchronize; it is repeated (each region bracketed the same way) until
+    # >= 1 s has been measured and the MEDIAN region is reported: one 20-step region is 80 ms, where host jitter of 8 processes shows
+    region_ms = []
+    while True:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        steps(args.warmup + len(region_ms) * args.steps, args.steps)
+        e1.record()
+        barrier()
+        region_ms.append(e0.elapsed_time(e1))
+        done = torch.tensor([1.0 if (sum(region_ms) >= 1000.0 or len(region_ms) >= 25) else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(done, op=dist.ReduceOp.MAX)
+        if float(done[0]) > 0:
+            break
+    ms = statistics.median(region_ms)
     clk = clocks.stop() if rank == 0 else None
 
     # per-kernel pass, outside the timed region: the same samples run eagerly, every C-ABI call bracketed by CUDA events
@@ -320,10 +366,13 @@ def main_ours(args):
     # end to end through the public API with host buffers
     steps_e2e(0, max(2, min(args.steps, 2 * args.lanes)))
     barrier()
-    t0 = time.perf_counter()
-    steps_e2e(0, args.steps)
-    barrier()
-    ms_e2e = 1e3 * (time.perf_counter() - t0)
+    e2e_ms = []
+    for _ in range(len(region_ms)):
+        t0 = time.perf_counter()
+        steps_e2e(0, args.steps)
+        barrier()
+        e2e_ms.append(1e3 * (time.perf_counter() - t0))
+    ms_e2e = statistics.median(e2e_ms)
 
     # the BASELINE configs[2] job: `--job` samples of one image sharded over ranks + selection exchange
     job = None
@@ -377,14 +426,29 @@ def main_ours(args):
                        "eps": "philox (seed, layer, sample)", "samples_sharding": "sample i -> rank i % n_gpus",
                        "execution": "eager launches" if args.no_graph else f"CUDA graph replay of one sample's forward, {args.lanes} samples in flight per GPU (sampler lanes)"},
             "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": img_host.numel() * 4,
-                    "d2h_bytes_per_step": out_host.numel() * 4},
+                    "d2h_bytes_per_step": out_host[0].numel() * 4},
+            "regions": {"timed": len(region_ms), "ms": region_ms, "reported": "median"},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_scan_bwd": roof_bwd, "roofline_pointwise": roof_pw, "kernels": shares, "job": job}
+    if not args.no_reference_gpu:
+        try:   # the reference's own GPU path on this box, after everything of ours has been measured
+            import bench_configs as bc
+            rg = bc.reference_gpu_kernels(dev, H_IMG, W_IMG)
+            if "unavailable" not in rg:
+                rg["network"] = bc.reference_gpu_network(dev, steps=5, H=H_IMG, W=W_IMG)
+                ours = {"scan_fwd_L0": roof["ms_per_launch"], "scan_bwd_L0": roof_bwd["ms_per_launch"],
+                        "bayes_1x1_40_320_ln_L0": roof_pw["ms_per_launch"]}
+                for k, v in ours.items():
+                    rg[k]["ours_ms"] = v
+                rg["network"]["ours_images_per_s"] = line["value"] / world
+            line["reference_gpu"] = rg
+        except Exception as ex:
+            line["reference_gpu"] = {"unavailable": f"failed: {type(ex).__name__}: {ex}"}
     if not args.no_cpu_baseline and world == 1:
         try:
             r = cpu_reference_run(2, 0, budget_s=25.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as ex:   # the baseline must never take the GPU number down with it
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
