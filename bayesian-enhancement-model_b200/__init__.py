@@ -6,12 +6,15 @@
     Bayesian layers     bem_b200.bayesian.{Conv2d,Linear2d,Linear}Reparameterization, convert2bnn*, set_prediction_type, ...
     MC inference        bem_b200.mc.{MCSampler, mc_infer, select_best}
     stage-1 network     bem_b200.network.{Network, build_model, build_bayesian_model}
-    reference patching  bem_b200.patch.install(...)
+    reference patching  bem_b200.patch.install(...) / uninstall()
+    after `.data` writes  bem_b200.invalidate_caches()  (derived-weight caches and captured graphs key on tensor versions,
+                        which in-place writes through `.data` — e.g. an EMA update — do not advance)
 
 All operators call libbem_b200.so (include/bem_b200.h) through ctypes; importing this package without the built library
 raises ImportError — there is no fallback path.
 """
 from . import _lib  # noqa: F401  (loads libbem_b200.so, raises if it is missing)
+from ._lib import invalidate_caches  # noqa: F401
 from . import bayesian, mc, network, patch  # noqa: F401
 from .csm import CrossMergeF, CrossScanF, cross_merge_fn, cross_scan_fn  # noqa: F401
 from .selective_scan import (SelectiveScanCuda, build_selective_scan_fn, chunk_len, selective_scan_cuda_oflex,  # noqa: F401

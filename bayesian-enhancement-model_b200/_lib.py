@@ -135,6 +135,44 @@ def require_cuda(*tensors):
             raise RuntimeError("bem_b200 operators run on CUDA tensors only (sm_100a kernels; there is no CPU fallback)")
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# cache generation. The inference paths cache tensors derived from parameters (sigma = log1p(exp(rho)), packed weight tiles
+# of constant-weight 1x1 layers, -exp(A_logs), split fusion weights) and CUDA graphs with those addresses baked in. Their
+# keys hold (data_ptr, tensor._version) of the sources — but writes through `.data` (the reference's EMA update,
+# basicsr/models/base_model.py:84 `p.data.mul_(decay).add_(...)`, init_parameters(), tools.py `.data.copy_`) do NOT bump
+# `_version`. Every key therefore also holds this process-wide generation, which module.train() / .eval(),
+# load_state_dict and .to() / .cuda() (nn.Module._apply) of this package's modules advance, and which callers who write
+# parameters through `.data` must advance themselves: bem_b200.invalidate_caches().
+# ---------------------------------------------------------------------------------------------------------------------
+_cache_generation = [0]
+
+
+def invalidate_caches():
+    """drop every derived-weight cache and captured graph of this package at its next use (call after writing parameters
+    through `.data`, e.g. an EMA update)"""
+    _cache_generation[0] += 1
+
+
+def cache_generation() -> int:
+    return _cache_generation[0]
+
+
+class InvalidatesCaches:
+    """mixin for nn.Modules whose parameters feed the caches above"""
+
+    def train(self, mode: bool = True):
+        invalidate_caches()
+        return super().train(mode)
+
+    def _apply(self, fn, *args, **kwargs):
+        invalidate_caches()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        invalidate_caches()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+
 _workspaces: dict = {}
 
 
@@ -147,6 +185,12 @@ def workspace(device: torch.device, nbytes: int, kind: str = "scan") -> torch.Te
         ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)   # scan kernels need a zero-filled first use
         _workspaces[key] = ws
     return ws
+
+
+def release_workspaces(stream_handle: int):
+    """drop the scratch buffers cached for a stream that is no longer used (e.g. a warm-up side stream)"""
+    for key in [k for k in _workspaces if k[2] == stream_handle]:
+        del _workspaces[key]
 
 
 def scan_error_word(device: torch.device) -> int:

@@ -8,9 +8,10 @@ import torch
 import torch.nn as nn
 
 from . import functional as BF
+from .. import _lib
 
 
-class BaseLayer_(nn.Module):
+class BaseLayer_(_lib.InvalidatesCaches, nn.Module):
     # --- Monte-Carlo controls (extensions; defaults reproduce the reference exactly) ------------------------------
     eps_source = "torch"   # "torch": eps_*.normal_() from torch's global generator, weight then bias (conv.py:107,110)
     #                        "philox": counter-based stream generated inside the sample kernel, keyed (mc_seed, layer_id, sample)
@@ -97,10 +98,11 @@ class BaseLayer_(nn.Module):
         return torch.log1p(torch.exp(self.rho_bias))
 
     def _sigma_cached(self, which="weight"):
-        """detached log1p(exp(rho)) for the inference kernels, recomputed only when rho changes (optimizer steps and
-        load_state_dict bump the tensor version)"""
+        """detached log1p(exp(rho)) for the inference kernels, recomputed only when rho changes: optimizer steps bump the
+        tensor version; train() / load_state_dict / .to() and explicit bem_b200.invalidate_caches() (needed after writes
+        through `.data`, which leave the version alone) advance the package's cache generation"""
         rho = getattr(self, "rho_" + which)
-        key = (rho._version, rho.data_ptr(), rho.device)
+        key = (rho._version, rho.data_ptr(), rho.device, _lib.cache_generation())
         cache = self.__dict__.setdefault("_sigma_cache", {})
         hit = cache.get(which)
         if hit is None or hit[0] != key:

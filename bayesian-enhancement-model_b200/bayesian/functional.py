@@ -196,14 +196,24 @@ def _pointwise_raw(x, w=None, bias=None, mu=None, sigma=None, eps=None, n_sample
     if pack_cache is not None and not force_simt:
         # constant weights (deterministic layers): the packed tiles live in the layer's own buffer and are rebuilt only when
         # a participating tensor changes (in-place updates bump ._version) or x changes alignment class
+        # One buffer PER key, never rewritten for another key: a captured CUDA graph has `prepacked = 1` and the buffer's
+        # address baked in, so a later eager call with another alignment class (another image size) must not repack the
+        # tiles the graph reads. A new cache generation (weights written through .data, load_state_dict, ...) clears the lot;
+        # graphs are re-captured on the same signal (mc.MCArena.valid).
+        gen = _lib.cache_generation()
+        if pack_cache.get("gen") != gen:
+            pack_cache.clear()
+            pack_cache["gen"] = gen
         key = tuple((t.data_ptr(), t._version) for t in (w, bias, g, b) if t is not None) + (n_samples, P % 4 == 0, int(img_stride) % 4 == 0,
-                                                                                              x.data_ptr() % 16 == 0, float(ln_eps))
-        ws = pack_cache.get("ws")
-        if ws is None or ws.numel() < need or ws.device != x.device:
+                                                                                              x.data_ptr() % 16 == 0, float(ln_eps), x.device.index)
+        packs = pack_cache.setdefault("packs", {})
+        ws = packs.get(key)
+        prepacked = int(ws is not None)
+        if ws is None:
+            if len(packs) >= 8:      # stale tensor versions (optimizer steps between evaluations): keep the dict small
+                packs.clear()
             ws = torch.empty(need, dtype=torch.uint8, device=x.device)
-            pack_cache["ws"], pack_cache["key"] = ws, None
-        prepacked = int(pack_cache.get("key") == key)
-        pack_cache["key"] = key
+            packs[key] = ws
     else:
         ws = None
         plan = _ACTIVE_PLAN

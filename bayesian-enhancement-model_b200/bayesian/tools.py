@@ -103,3 +103,46 @@ def set_mc_config(model, mc_samples=None, eps_source=None, seed=None, sample0=No
             layer.mc_seed = int(seed)
         if sample0 is not None:
             layer.mc_sample0 = int(sample0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# extension: the resume gap of the reference. `prior_mu_* / prior_rho_*` are NON-persistent buffers and `step`,
+# `prior_sigma_*` plain attributes (conv.py:39-52, linear.py:26-39), so they are absent from every checkpoint: a run resumed
+# from `{'params': state_dict}` (basicsr/models/base_model.py:255-263) restarts the prior EMA from the freshly initialised
+# prior and step 0, which changes the KL term of the first thousands of iterations. The state_dict itself must stay
+# key-for-key the reference's (released checkpoints load with strict=True), so the missing state travels in a side dict.
+# ---------------------------------------------------------------------------------------------------------------------
+def prior_state_dict(model):
+    """{'<layer name>.prior_mu_weight': tensor, ..., '<layer name>.step': int}: what the checkpoint does not hold"""
+    out = {}
+    for name, layer in model.named_modules():
+        if not (hasattr(layer, "deterministic") and hasattr(layer, "prior_mu_weight")):
+            continue
+        for k in ("prior_mu_weight", "prior_rho_weight", "prior_mu_bias", "prior_rho_bias"):
+            t = getattr(layer, k, None)
+            if t is not None:
+                out[f"{name}.{k}"] = t.detach().clone()
+        out[f"{name}.step"] = int(getattr(layer, "step", 0))
+    return out
+
+
+def load_prior_state_dict(model, state):
+    """inverse of prior_state_dict: restores the prior EMA tensors, `step`, and `prior_sigma_*` = log1p(exp(prior_rho_*))
+    (what the next training forward would otherwise recompute from a reset prior). Returns the restored layer names."""
+    import torch
+    done = []
+    for name, layer in model.named_modules():
+        if f"{name}.step" not in state:
+            continue
+        for k in ("prior_mu_weight", "prior_rho_weight", "prior_mu_bias", "prior_rho_bias"):
+            key = f"{name}.{k}"
+            if key in state and getattr(layer, k, None) is not None:
+                with torch.no_grad():
+                    getattr(layer, k).copy_(state[key].to(getattr(layer, k).device))
+        layer.step = int(state[f"{name}.step"])
+        with torch.no_grad():
+            layer.prior_sigma_weight = torch.log1p(torch.exp(layer.prior_rho_weight))
+            if getattr(layer, "bias", False):
+                layer.prior_sigma_bias = torch.log1p(torch.exp(layer.prior_rho_bias))
+        done.append(name)
+    return done

@@ -129,12 +129,25 @@ __device__ __forceinline__ void decay_step(float e, float b, float& P, float& V)
     P = fmaf(e, P, P);
 }
 
-// softplus(x) = max(x,0) + log1p(exp(-|x|)); identical to the reference's `x <= 20 ? log1pf(expf(x)) : x`
-// (cusoflex/selective_scan_fwd_kernel_oflex.cuh:124-126, F.softplus threshold 20) to < 2e-7 absolute: beyond 20 the
-// correction term is below 2.1e-9.
+// softplus(x) = max(x,0) + log1p(exp(-|x|)); matches the reference's `x <= 20 ? log1pf(expf(x)) : x`
+// (cusoflex/selective_scan_fwd_kernel_oflex.cuh:124-126, F.softplus threshold 20): beyond 20 the correction term is below
+// 2.1e-9. log1p(z) must keep its RELATIVE accuracy for small z: x = delta + bias is very negative for channels whose dt
+// sits near dt_init_floor (z ~ 1e-4), and forming 1.f + z rounds z to 6e-8 absolute = 6e-4 of such a delta, which the
+// backward pass multiplies into ddelta and dA. Below z = 2^-4 the alternating series is used instead; at and above it the
+// rounding of 1 + z costs at most 2^-24 / 2^-4 = 1e-6 relative.
+__device__ __forceinline__ float log1p_small(float z) {
+    // z in [0, 2^-4): z * (1 - z/2 + z^2/3 - z^3/4 + z^4/5 - z^5/6), truncation < z^6/7 < 9e-9 relative
+    float p = fmaf(z, -1.f / 6.f, 0.2f);
+    p = fmaf(z, p, -0.25f);
+    p = fmaf(z, p, 1.f / 3.f);
+    p = fmaf(z, p, -0.5f);
+    p = fmaf(z, p, 1.f);
+    return z * p;
+}
 __device__ __forceinline__ float softplus_f(float x) {
     const float z = ex2_approx(-fabsf(x) * kLog2e);
-    return fmaxf(x, 0.f) + kLn2 * lg2_approx(1.f + z);
+    const float big = kLn2 * lg2_approx(1.f + z);          // z >= 2^-4: rounding of 1 + z costs <= 1e-6 relative
+    return fmaxf(x, 0.f) + (z < 0.0625f ? log1p_small(z) : big);
 }
 // d softplus / dx = sigmoid(x); the reference switches to 1 above the threshold
 // (cusoflex/selective_scan_bwd_kernel_oflex.cuh:250-255)

@@ -100,10 +100,22 @@ class MCArena:
         self.blocks = torch.tensor(blocks, dtype=torch.int32).to(self.device)
         self.n_blocks = len(blocks)
         self.sample0 = torch.zeros((), dtype=torch.int64, device=self.device)   # device-side sample index (graph replay)
+        self._net = net
+        self._stamp = self._net_stamp()
         self.plans = {}   # input shape -> functional.PackPlan: the pack steps of all Bayesian 1x1 layers in one launch per draw
 
+    def _net_stamp(self):
+        """(address, version) of every parameter and buffer of the network + the package's cache generation: what a captured
+        graph of the forward depends on besides its input (packed constant weights, -exp(A_logs), split fusion weights are
+        baked in by address and were derived from these tensors)"""
+        ts = list(self._net.parameters()) + list(self._net.buffers())
+        return (_lib.cache_generation(), tuple((t.data_ptr(), t._version) for t in ts))
+
     def valid(self) -> bool:
-        return all(mu.data_ptr() == pm and rho.data_ptr() == pr for mu, rho, pm, pr in self._ptrs)
+        """False once any weight of the network was replaced or modified (optimizer step, load_state_dict, .to(), or a `.data`
+        write followed by bem_b200.invalidate_caches()): the arena's tables, pack plans and graphs are then rebuilt"""
+        return (all(mu.data_ptr() == pm and rho.data_ptr() == pr for mu, rho, pm, pr in self._ptrs)
+                and self._stamp == self._net_stamp())
 
     def attach(self, on: bool = True):
         for L in self.layers:
@@ -136,6 +148,30 @@ class MCArena:
         self.draw(sample_id, plan)
         with plan.playing():
             return fn()
+
+
+class _McConfigScope:
+    """The Monte-Carlo controls live on the (shared) layers; a sampler sets them for its forwards and puts back what it found,
+    so a direct `net(x)` afterwards — e.g. the training step that follows an in-loop validation — draws fresh eps again exactly
+    as before (the reference always does `eps.normal_()`, conv.py:107)."""
+    KEYS = ("eps_source", "mc_seed", "mc_sample0", "mc_samples")
+
+    def __init__(self, net):
+        from .bayesian.base_layer import BaseLayer_
+        self.layers = [m for m in net.modules() if isinstance(m, BaseLayer_)]
+
+    def __enter__(self):
+        self.saved = [{k: m.__dict__[k] for k in self.KEYS if k in m.__dict__} for m in self.layers]
+        return self
+
+    def __exit__(self, *exc):
+        for m, sv in zip(self.layers, self.saved):
+            for k in self.KEYS:
+                if k in sv:
+                    setattr(m, k, sv[k])
+                else:
+                    m.__dict__.pop(k, None)      # back to the class default
+        return False
 
 
 class _Lane:
@@ -205,15 +241,15 @@ class MCSampler:
         if rec is None:
             arena = self._get_arena(lane)
             static_x = x.clone()
-            side = torch.cuda.Stream(device=x.device)
-            side.wait_stream(torch.cuda.current_stream(x.device))
-            with torch.cuda.stream(side):            # warm-up off the capture: lazy initialisation, workspace growth
+            if lane.capture_stream is None:
+                lane.capture_stream = torch.cuda.Stream(device=x.device)
+            side = lane.capture_stream           # warm up on the stream that captures: the library's scratch buffers are per
+            side.wait_stream(torch.cuda.current_stream(x.device))   # stream, so they are created (and zero-filled) here, not as graph nodes
+            with torch.cuda.stream(side):
                 for _ in range(2):               # the first of them records the pack plan of this shape
                     arena.forward_planned(key, None, lambda: self._forward_one(static_x))
             torch.cuda.current_stream(x.device).wait_stream(side)
             g = torch.cuda.CUDAGraph()
-            if lane.capture_stream is None:
-                lane.capture_stream = torch.cuda.Stream(device=x.device)
             with torch.cuda.graph(g, stream=lane.capture_stream):
                 static_y = arena.forward_planned(key, None, lambda: self._forward_one(static_x))
             rec = (g, static_x, static_y)
@@ -358,11 +394,13 @@ class MCSampler:
 
 @torch.no_grad()
 def mc_infer(sampler: MCSampler, x: torch.Tensor, num_samples: int, score_fn: Callable = default_score,
-             take_min: bool = False, monte_carlo_mean: bool = False, group=None):
+             take_min: bool = False, monte_carlo_mean: bool = False, group=None, select_fn: Callable = None):
     """Distributed MC inference for one image. Every rank calls this with the same x / num_samples.
 
     Returns dict(best=(C,H,W) tensor on every rank, index=int, scores=(num_samples,) tensor[, mean=(C,H,W)]).
     Single process (no initialised process group) = all samples local.
+    select_fn(scores, take_min) -> (index, value): the selection operator, bem_select_best by default (CUDA only — the
+    host-logic tests inject a stand-in; there is no CPU selection in this package).
     """
     distributed = dist.is_available() and dist.is_initialized()
     rank = dist.get_rank(group) if distributed else 0
@@ -381,12 +419,8 @@ def mc_infer(sampler: MCSampler, x: torch.Tensor, num_samples: int, score_fn: Ca
         table = torch.stack(gathered, dim=1).reshape(-1)[:num_samples]   # [j, r] -> sample j * world + r
     else:
         table = padded[:num_samples]
-    if x.is_cuda:
-        idx_t, _ = select_best(table, take_min)
-        index = int(idx_t.item())
-    else:   # host-logic tests on CPU (gloo): same semantics as bem_select_best
-        lst = table.tolist()
-        index = lst.index(min(lst) if take_min else max(lst))
+    idx_t, _ = (select_fn or select_best)(table, take_min)
+    index = int(idx_t)
     owner = owner_of(index, world)
     if owner == rank:
         best = preds[mine.index(index)].clone()

@@ -16,12 +16,12 @@ from functools import partial
 import torch
 import torch.nn as nn
 
-from . import bayesian
+from . import _lib, bayesian
 from .bayesian import functional as BF
 from .ss2d import SS2D, LayerNorm2d, apply_1x1, apply_residual, fuses_act
 
 
-class Conv2d(nn.Conv2d):
+class Conv2d(_lib.InvalidatesCaches, nn.Conv2d):
     """nn.Conv2d (same name, parameters and state_dict) whose small-channel 3x3 stems run on bem_conv3x3 and whose deterministic 1x1 case — PatchMerging.reduction, the
     DualUpSample projections, the decoder fusion convs (UNet_arch.py:88-135, 161-163) — runs on the same tcgen05 pointwise
     kernel as the Bayesian 1x1 layers (one weight set, no sampling) when no gradient is needed; everything else is the
@@ -63,7 +63,7 @@ def conv1x1_of_cat(conv, a, b):
         return conv(torch.cat([a, b], dim=1))
     ca = a.shape[1]
     cache = conv.__dict__.setdefault("_split_cache", {})
-    key = (conv.weight.data_ptr(), conv.weight._version, ca)
+    key = (conv.weight.data_ptr(), conv.weight._version, ca, _lib.cache_generation())
     if cache.get("key") != key:
         w = conv.weight.detach().view(conv.out_channels, -1)
         cache.update(key=key, wa=w[:, :ca].contiguous().unsqueeze(0), wb=w[:, ca:].contiguous().unsqueeze(0), pa={}, pb={})

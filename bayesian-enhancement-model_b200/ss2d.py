@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib
 from .bayesian import functional as BF
 from .csm import cross_merge_fn, cross_scan_fn
 from .selective_scan import fused_dt_rank_ok, selective_scan_fn
@@ -22,7 +23,6 @@ _SCAN_MODES = dict(cross2d=0, unidi=1, bidi=2)
 
 def ss2d_fwd(x, z, dt_weight, A, Dskip, delta_bias, dstate=1, delta_softplus=True):
     """bem_ss2d_fwd: x (B, D, H, W), z = x_proj output in image order (B, 4*(R+2N), H*W) -> y (B, D, H*W), fp32."""
-    from . import _lib
     from ._lib import lib
     _lib.require_cuda(x, z, dt_weight, A)
     B, D, H, W = x.shape
@@ -106,7 +106,7 @@ def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_pr
             # everything after x_proj in ONE C-ABI call (bem_ss2d_fwd): cross_scan(x), per-direction traversal of z,
             # selective scan with dt_proj fused (the (B, K*D, L) delta tensor is neither written nor read), cross_merge
             As = None if pack_cache is None else pack_cache.get("As")
-            akey = (A_logs.data_ptr(), A_logs._version)
+            akey = (A_logs.data_ptr(), A_logs._version, _lib.cache_generation())
             if As is None or pack_cache.get("As_key") != akey:     # -exp(A_logs) once per parameter version, not per call
                 As = -A_logs.detach().to(torch.float).exp()
                 if pack_cache is not None:
@@ -179,7 +179,7 @@ def _dt_init(dt_rank, d_inner, dt_scale=1.0, dt_init="random", dt_min=0.001, dt_
     return dt_proj
 
 
-class SS2D(nn.Module):
+class SS2D(_lib.InvalidatesCaches, nn.Module):
     """The SS2D configuration every BEM arch instantiates: forward_type "v05_noz", channel_first, ssm_init "v0"
     (vmamba.py:438-545 __initv2__, :700-716 forwardv2). Other forward types are out of scope and raise."""
 

@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--config", default="mc", choices=["mc", "c1", "hd", "train"],
                     help="mc = BASELINE configs[1]/[2] (headline); c1 / hd / train = configs[0] / [3] / [4]")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference-on-GPU columns")
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds of host work of the --impl reference arm")
     return ap.parse_args()
 
 
@@ -201,7 +202,7 @@ def main_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "config train: the reference's CPU backward through the Python scan loop is O(L^2) (254 s for one config-1 scan, BASELINE.md section 3); see cpu_baseline of --config train"}), flush=True)
         return
     steps = max(1, min(args.steps, 8))
-    r = cpu_reference_run(steps, min(args.warmup, 1), budget_s=150.0)
+    r = cpu_reference_run(steps, min(args.warmup, 1), budget_s=args.cpu_budget)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -444,8 +445,11 @@ def main_ours(args):
         except Exception as ex:
             line["reference_gpu"] = {"unavailable": f"failed: {type(ex).__name__}: {ex}"}
     if not args.no_cpu_baseline and world == 1:
-        try:
-            r = cpu_reference_run(2, 0, budget_s=25.0)
+        try:   # own process: the reference's modules must be imported WITHOUT its CUDA extension for the pure-PyTorch scan
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "0",
+                                  "--cpu-budget", "25"], capture_output=True, text=True, timeout=600,
+                                 env={**os.environ, "CUDA_VISIBLE_DEVICES": "", "RANK": "0", "WORLD_SIZE": "1"})
+            r = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])["cpu_baseline"]
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as ex:   # the baseline must never take the GPU number down with it
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}

@@ -359,3 +359,16 @@ def test_classic_schedule_still_matches_the_deferred_one():
         ref = torch.load(f + ".out")
     assert nmax_err(out.cpu().numpy(), ref["o"].numpy()) < 2e-6
     assert nmax_err(x.cpu().numpy(), ref["x"].numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("lo,hi", [(-14.0, -6.0), (-9.5, -2.0)])
+def test_softplus_keeps_relative_accuracy_near_the_dt_floor(lo, hi):
+    """delta + bias in [-14, -6]: dt = softplus(.) between 8e-7 and 2.5e-3, the dt_init_floor regime of mamba_init.dt_init
+    (vmamba.py:224-249). log1p(exp(x)) must stay accurate RELATIVE to dt (a `1 + z` formulation loses up to 1 % there);
+    out, ddelta and dA scale with dt, so all of them are held to the fp32 bar against the fp64 oracle."""
+    inp = make_inputs(2, 16, 1, 2, 1500, torch.float32, seed=11)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    inp["delta"] = (lo + (hi - lo) * torch.rand(2, 16, 1500, generator=g)).cuda()
+    inp["delta_bias"] = torch.zeros(16).cuda()
+    inp["A"] = -(1.0 + 50.0 * torch.rand(16, 1, generator=g)).cuda()     # delta * A still moves the state at dt ~ 1e-4
+    run_case(inp, True, FP32_TOL)
