@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libbem_b200.so")
 
 BEM_F32, BEM_F16, BEM_BF16 = 0, 1, 2
 BEM_OK, BEM_ERR_BAD_ARG, BEM_ERR_WORKSPACE, BEM_ERR_UNSUPPORTED = 0, 10001, 10002, 10003
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 i32, i64, u64, vp = C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
 
@@ -80,6 +80,7 @@ SYMBOLS = {
     "bem_scan_bwd": (C.c_int, [C.POINTER(BemScanBwdParams), vp]),
     "bem_cross_scan": (C.c_int, [C.POINTER(BemCsmParams), vp]),
     "bem_cross_merge": (C.c_int, [C.POINTER(BemCsmParams), vp]),
+    "bem_ss2d_supported": (C.c_int, [C.c_int] * 2),
     "bem_ss2d_workspace_bytes": (i64, [C.c_int] * 6),
     "bem_ss2d_fwd": (C.c_int, [C.POINTER(BemSs2dFwdParams), vp]),
     "bem_bayes_sample": (C.c_int, [C.POINTER(BemBayesSampleParams), vp]),

@@ -114,6 +114,24 @@ struct ScanBwdArgs {
     unsigned int* err;
 };
 
+// traversal-aware SS2D core (ss2d_fused.cu)
+struct Ss2dFusedArgs {
+    const float* x;      // (B, D, H, W)
+    const float* xdbl;   // (B, 4, R + 2, H, W): x_proj output in image order, [dt rows | B | C] per direction
+    const float* dt_w;   // (4 * D, R)
+    const float* A;      // (4 * D) (dstate 1)
+    const float* Ds;     // (4 * D) or nullptr
+    const float* bias;   // (4 * D) or nullptr
+    float* y;            // (B, D, H, W)
+    float2* agg;         // segment maps (P, V)
+    float* hin;          // state entering each segment
+    int B, D, H, W, R, softplus;
+    int NTH, NTW;        // tiles along H / W
+};
+bool ss2d_fused_supported(int dstate, int dt_rank);
+int64_t ss2d_fused_workspace(int B, int D, int H, int W);
+int ss2d_fused_dispatch(Ss2dFusedArgs a, void* workspace, cudaStream_t stream);
+
 int scan_fwd_dispatch(const ScanFwdArgs& a, int dtype, int out_dtype, int sm_count, cudaStream_t stream);
 int scan_fwd_deferred_dispatch(const ScanFwdArgs& a, int sm_count, cudaStream_t stream);   // fp32, N = 1: deferred-finish schedule
 int scan_bwd_dispatch(ScanBwdArgs& a, int dtype, int dout_dtype, int sm_count, cudaStream_t stream);

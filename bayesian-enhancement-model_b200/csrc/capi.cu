@@ -145,21 +145,39 @@ int bem_scan_bwd(const BemScanBwdParams* q, void* stream_) {
     return scan_bwd_dispatch(a, q->dtype, q->dout_dtype, sms, stream);
 }
 
-// SS2D core in one call: cross_scan(x), cross_scan(xdbl, one_by_one), scan with dt_proj fused, cross_merge — the launch
-// sequence of bem_b200/ss2d.py behind a single entry point, intermediates in the caller's workspace.
+// SS2D core in one call. Default: the traversal-aware scan of ss2d_fused.cu (three launches, no materialised traversal).
+// Composed form (BEM_SS2D_COMPOSED=1, or a dt_rank the fused kernels are not instantiated for): cross_scan(x),
+// cross_scan(xdbl, one_by_one), scan with dt_proj fused, cross_merge — four launches with intermediates in the workspace.
 static int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
+static bool ss2d_use_fused(int dstate, int dt_rank) {
+    static const bool composed = [] {
+        const char* v = getenv("BEM_SS2D_COMPOSED");
+        return v && atoi(v) != 0;
+    }();
+    return !composed && ss2d_fused_supported(dstate, dt_rank);
+}
 struct Ss2dLayout {
-    int64_t scan_ws, xs, xdbl_s, ys, total;
+    int64_t scan_ws, xs, xdbl_s, ys, fused, total;
 };
 static Ss2dLayout ss2d_layout(int batch, int d_inner, int H, int W, int dstate, int dt_rank) {
     const int64_t L = (int64_t)H * W, Cx = dt_rank + 2 * dstate;
     Ss2dLayout l;
     l.scan_ws = 0;
+    if (ss2d_use_fused(dstate, dt_rank)) {
+        l.xs = l.xdbl_s = l.ys = l.fused = 256;          // header kept (and left zero) so both forms may share one buffer
+        l.total = l.fused + align256(ss2d_fused_workspace(batch, d_inner, H, W));
+        return l;
+    }
     l.xs = align256(bem_scan_workspace_bytes(batch, 4 * d_inner, (int)L, dstate, BEM_F32));
     l.xdbl_s = l.xs + align256((int64_t)batch * 4 * d_inner * L * 4);
     l.ys = l.xdbl_s + align256((int64_t)batch * 4 * Cx * L * 4);
-    l.total = l.ys + align256((int64_t)batch * 4 * d_inner * L * 4);
+    l.fused = l.total = l.ys + align256((int64_t)batch * 4 * d_inner * L * 4);
     return l;
+}
+int bem_ss2d_supported(int dstate, int dt_rank) {
+    if (dstate != 1 || dt_rank <= 0) return 0;
+    if (ss2d_use_fused(dstate, dt_rank)) return 2;
+    return dt_rank <= kMaxDtRank ? 1 : 0;
 }
 int64_t bem_ss2d_workspace_bytes(int batch, int d_inner, int H, int W, int dstate, int dt_rank) {
     if (batch <= 0 || d_inner <= 0 || H <= 0 || W <= 0 || dstate <= 0 || dt_rank <= 0) return 0;
@@ -168,10 +186,17 @@ int64_t bem_ss2d_workspace_bytes(int batch, int d_inner, int H, int W, int dstat
 int bem_ss2d_fwd(const BemSs2dFwdParams* p, void* stream) {
     if (!p || !p->x || !p->xdbl || !p->dt_weight || !p->A || !p->y) return BEM_ERR_BAD_ARG;
     if (p->batch <= 0 || p->d_inner <= 0 || p->H <= 0 || p->W <= 0 || p->dstate <= 0 || p->dt_rank <= 0) return BEM_ERR_BAD_ARG;
-    if (p->dstate != 1 || p->dt_rank > kMaxDtRank) return BEM_ERR_UNSUPPORTED;
+    const bool fused = ss2d_use_fused(p->dstate, p->dt_rank);
+    if (p->dstate != 1 || (!fused && p->dt_rank > kMaxDtRank)) return BEM_ERR_UNSUPPORTED;
     const Ss2dLayout l = ss2d_layout(p->batch, p->d_inner, p->H, p->W, p->dstate, p->dt_rank);
     if (!p->workspace || p->workspace_bytes < l.total || (reinterpret_cast<uintptr_t>(p->workspace) & 255)) return BEM_ERR_WORKSPACE;
     unsigned char* ws = reinterpret_cast<unsigned char*>(p->workspace);
+    if (fused) {
+        Ss2dFusedArgs a{};
+        a.x = p->x; a.xdbl = p->xdbl; a.dt_w = p->dt_weight; a.A = p->A; a.Ds = p->Dskip; a.bias = p->delta_bias; a.y = p->y;
+        a.B = p->batch; a.D = p->d_inner; a.H = p->H; a.W = p->W; a.R = p->dt_rank; a.softplus = p->delta_softplus ? 1 : 0;
+        return ss2d_fused_dispatch(a, ws + l.fused, (cudaStream_t)stream);
+    }
     float* xs = reinterpret_cast<float*>(ws + l.xs);
     float* xdbl_s = reinterpret_cast<float*>(ws + l.xdbl_s);
     float* ys = reinterpret_cast<float*>(ws + l.ys);

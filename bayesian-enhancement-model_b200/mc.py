@@ -275,15 +275,29 @@ class MCSampler:
                 lane.stream = torch.cuda.Stream(device=x.device)
         return lanes, recs
 
+    def samples_to_host(self, x_host, out_host, sample_ids):
+        with _McConfigScope(self.net):
+            return self._samples_to_host(x_host, out_host, sample_ids)
+
+    def sample_to_host(self, x_host, out_host, sample_id):
+        with _McConfigScope(self.net):
+            return self._sample_to_host(x_host, out_host, sample_id)
+
+    def sample(self, x, sample_ids):
+        """x: (1, C, H, W) -> (len(sample_ids), C_out, H, W), one prediction per global sample index. The layers' Monte-Carlo
+        controls are put back afterwards (see _McConfigScope)."""
+        with _McConfigScope(self.net):
+            return self._sample(x, sample_ids)
+
     @torch.no_grad()
-    def samples_to_host(self, x_host: torch.Tensor, out_host: torch.Tensor, sample_ids: Sequence[int]):
+    def _samples_to_host(self, x_host: torch.Tensor, out_host: torch.Tensor, sample_ids: Sequence[int]):
         """len(sample_ids) predictions of one (pinned) host image into the rows of a (pinned) host buffer, the lanes working
         side by side: per sample the image goes H2D into the lane's graph input and the prediction D2H from its output.
         Returns after everything has landed."""
         ids = list(sample_ids)
         if not (self.use_graph and x_host.shape[0] == 1 and len(self._lanes) > 1 and len(ids) > 1):
             for i, sid in enumerate(ids):
-                self.sample_to_host(x_host, out_host[i:i + 1], sid)
+                self._sample_to_host(x_host, out_host[i:i + 1], sid)
             return out_host
         dev = next(self.net.parameters()).device
         with torch.cuda.device(dev):
@@ -303,7 +317,7 @@ class MCSampler:
         return out_host
 
     @torch.no_grad()
-    def sample_to_host(self, x_host: torch.Tensor, out_host: torch.Tensor, sample_id: int):
+    def _sample_to_host(self, x_host: torch.Tensor, out_host: torch.Tensor, sample_id: int):
         """One prediction from a (pinned) host image into a (pinned) host buffer, on the current stream and without
         intermediate device copies when the graph path is active: H2D straight into the graph's input, replay, D2H straight
         from the graph's output. Returns after the result has landed in `out_host`."""
@@ -326,14 +340,13 @@ class MCSampler:
             out_host.copy_(static_y[0] if out_host.dim() == static_y.dim() - 1 else static_y, non_blocking=True)
         else:
             dev = next(self.net.parameters()).device
-            y = self.sample(x_host.to(dev, non_blocking=True), [sample_id])
+            y = self._sample(x_host.to(dev, non_blocking=True), [sample_id])
             out_host.copy_(y[0] if out_host.dim() == y.dim() - 1 else y, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return out_host
 
     @torch.no_grad()
-    def sample(self, x: torch.Tensor, sample_ids: Sequence[int]) -> torch.Tensor:
-        """x: (1, C, H, W) -> (len(sample_ids), C_out, H, W), one prediction per global sample index."""
+    def _sample(self, x: torch.Tensor, sample_ids: Sequence[int]) -> torch.Tensor:
         outs = []
         ids = list(sample_ids)
         if self.use_arena and ids and x.is_cuda and x.shape[0] == 1:

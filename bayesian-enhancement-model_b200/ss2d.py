@@ -38,8 +38,11 @@ def ss2d_fwd(x, z, dt_weight, A, Dskip, delta_bias, dstate=1, delta_softplus=Tru
                               Dskip=_lib.ptr(Dskip), delta_bias=_lib.ptr(delta_bias), y=_lib.ptr(y), workspace=_lib.ptr(ws),
                               workspace_bytes=ws.numel())
     L = H * W
-    _lib.launch("ss2d_fwd", lib.bem_ss2d_fwd, p, x.device, key=(B, D, H, W, R),
-                nbytes=4 * B * L * (D + 4 * (R + 2 * dstate)) * 2 + 4 * B * L * 4 * D * 4 + 4 * B * L * D, kernels=4)
+    fused = lib.bem_ss2d_supported(dstate, R) == 2
+    # algorithmic bytes, SURVEY 8(d) fused-SS2D form with x_proj outside: x in, xdbl in, y out (the traversal-aware kernels
+    # read x / xdbl twice; the composed form moves ~18 D*L units through four launches)
+    nbytes = 4 * B * L * (D + 4 * (R + 2 * dstate) + D)
+    _lib.launch("ss2d_fwd", lib.bem_ss2d_fwd, p, x.device, key=(B, D, H, W, R), nbytes=nbytes, kernels=3 if fused else 4)
     return y
 
 
@@ -102,7 +105,7 @@ def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_pr
         Cx = x_proj_weight.shape[1]
         z = BF.pointwise_conv(x.reshape(B, D, L), x_proj_weight.reshape(1, K * Cx, D),
                               None if x_proj_bias is None else x_proj_bias.reshape(1, K * Cx), 1, pack_cache=pack_cache)
-        if scans == 0 and fused_dt_rank_ok(R, N, x.dtype) and not force_fp32:
+        if scans == 0 and x.dtype == torch.float32 and _lib.lib.bem_ss2d_supported(N, R) > 0 and not force_fp32:
             # everything after x_proj in ONE C-ABI call (bem_ss2d_fwd): cross_scan(x), per-direction traversal of z,
             # selective scan with dt_proj fused (the (B, K*D, L) delta tensor is neither written nor read), cross_merge
             As = None if pack_cache is None else pack_cache.get("As")

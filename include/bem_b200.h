@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define BEM_ABI_VERSION 11
+#define BEM_ABI_VERSION 12
 
 /* element types of u/delta/B/C/x-activations */
 enum { BEM_F32 = 0, BEM_F16 = 1, BEM_BF16 = 2 };
@@ -164,16 +164,21 @@ int bem_cross_merge(const BemCsmParams* p, void* stream);
  * "cross2d", `no_einsum`): split dt/B/C -> dt_proj -> cross_scan -> selective scan -> cross_merge.
  * x_proj is pointwise in l and commutes with the traversal, so its output is taken in IMAGE order, one
  * (dt_rank + 2*dstate)-channel block per direction — produced by ONE bem_bayes_pointwise call on x with the concatenated
- * x_proj weights (bem_b200/ss2d.py). This entry point then runs
- *     bem_cross_scan(x)  ->  bem_cross_scan(xdbl, one_by_one)  ->  bem_scan_fwd (dt_proj fused, dt_rank > 0)  ->  bem_cross_merge
- * on the caller's stream with intermediates in `workspace`.
+ * x_proj weights (bem_b200/ss2d.py). This entry point then runs the traversal-aware scan (csrc/ss2d_fused.cu): the cross-scan
+ * gather and the cross-merge scatter are part of the scan itself — every direction reads x and xdbl where they lie (k0 / k2
+ * walk image rows forward / backward, k1 / k3 image columns), the four results of a pixel are summed on chip in the
+ * reference's association (y0 + y2) + (y1 + y3) (csm_triton.py:60-62) and y is written once. No (B, 4, D, L) tensor exists.
+ * Three launches (tile maps, carry scan, tile outputs) on the caller's stream, 12 bytes of workspace per 32-pixel segment.
  *   x         : (B, D, H, W)                         fp32
  *   xdbl      : (B, 4, dt_rank + 2*dstate, H, W)     fp32, channel order [dt | B | C] per direction
  *   dt_weight : (4*D, dt_rank) fp32; A : (4*D, dstate) fp32; Dskip, delta_bias : (4*D) fp32 or NULL
  *   y         : (B, D, H*W)  fp32 = sum over the 4 directions, un-traversed (before out_norm)
- * fp32, dstate = 1, dt_rank <= 8 (BEM_ERR_UNSUPPORTED otherwise: compose the entry points with a separate dt_proj).
- * workspace : bem_ss2d_workspace_bytes() bytes, 256-byte aligned, ZERO-FILLED BY THE CALLER BEFORE ITS FIRST USE (it starts
- *             with the scan look-back workspace, see bem_scan_fwd), then owned by the calls of one stream.
+ * fp32, dstate = 1. bem_ss2d_supported(dstate, dt_rank) tells whether the call is built for a configuration: dt_rank 3 / 5 / 10
+ * (the BEM levels) run the traversal-aware kernels; other ranks <= 8 (and everything under BEM_SS2D_COMPOSED=1, the A/B knob)
+ * run the composed form bem_cross_scan x2 -> bem_scan_fwd (dt_proj fused) -> bem_cross_merge with intermediates in `workspace`;
+ * anything else returns BEM_ERR_UNSUPPORTED (compose the entry points with a separate dt_proj).
+ * workspace : bem_ss2d_workspace_bytes() bytes, 256-byte aligned, ZERO-FILLED BY THE CALLER BEFORE ITS FIRST USE (the composed
+ *             form starts with the scan look-back workspace, see bem_scan_fwd), then owned by the calls of one stream.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct BemSs2dFwdParams {
     int32_t batch, d_inner, H, W, dstate, dt_rank;
@@ -188,6 +193,7 @@ typedef struct BemSs2dFwdParams {
     void* workspace;
     int64_t workspace_bytes;
 } BemSs2dFwdParams;
+int bem_ss2d_supported(int dstate, int dt_rank);   /* 0: not built; 1: composed form; 2: traversal-aware kernels */
 int64_t bem_ss2d_workspace_bytes(int batch, int d_inner, int H, int W, int dstate, int dt_rank);
 int bem_ss2d_fwd(const BemSs2dFwdParams* p, void* stream);
 
@@ -326,7 +332,8 @@ int bem_conv3x3(const BemConv3x3Params* p, void* stream);
 /* ------------------------------------------------------------------------------------------------
  * Monte-Carlo best-sample selection.
  * Replaces `_idx = one_clip_list.index(max(one_clip_list))` (Enhancement/eval.py:270-271; NIQE uses min, :273-274):
- * first index attaining the extremum; NaN scores are never selected unless all are NaN (then index 0).
+ * first index attaining the extremum with Python's comparison semantics: every comparison with NaN is false, so a NaN at
+ * index 0 stays selected (`max([nan, 1, 2])` is nan -> index 0) while a NaN anywhere else is never selected.
  *   scores : (n) fp32;  out_index : int32[1];  out_value : fp32[1] or NULL
  * ---------------------------------------------------------------------------------------------- */
 int bem_select_best(const float* scores, int32_t n, int32_t take_min, int32_t* out_index, float* out_value, void* stream);

@@ -218,7 +218,10 @@ def test_mc_sampler_host_buffer_call_matches_device_call():
             assert nmax_err(oh.numpy(), ref.cpu().numpy()) < 5e-5
 
 
-@pytest.mark.parametrize("B,D,H,W,R", [(1, 40, 20, 28, 3), (2, 16, 9, 13, 1), (1, 80, 8, 12, 5), (1, 24, 7, 5, 8)])
+@pytest.mark.parametrize("B,D,H,W,R", [(1, 40, 20, 28, 3), (2, 16, 9, 13, 1), (1, 80, 8, 12, 5), (1, 24, 7, 5, 8),
+                                       # traversal-aware kernels (dt_rank 3 / 5 / 10): several tiles per direction, ragged edges,
+                                       # channel counts that are no multiple of the 8-channel CTA, batch > 1
+                                       (1, 40, 70, 45, 3), (2, 12, 33, 65, 5), (1, 20, 64, 64, 10), (1, 9, 100, 37, 3), (1, 8, 32, 32, 5)])
 def test_ss2d_fwd_entry_point_matches_reference_chain(B, D, H, W, R):
     """bem_ss2d_fwd (x_proj on the un-scanned x, then one C-ABI call: traversals + scan with dt_proj fused + merge) against the
     reference's own op sequence (vmamba.py:656-684) evaluated in fp64 with torch ops"""
