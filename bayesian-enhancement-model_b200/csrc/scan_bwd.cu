@@ -380,7 +380,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                             dD_acc = fmaf(dyi, ui, dD_acc);
                             // d softplus = sigmoid(raw) = 1 - exp(-softplus(raw)); equals the reference's switch to 1
                             // above raw = 20 (bwd_kernel_oflex.cuh:250-255) to 2e-9
-                            if (p.softplus) ddl *= 1.f - ex2_approx(-x * kLog2e);
+                            if (p.softplus) ddl *= -decay_m1<true>(-x);   // expm1 form: 1 - exp(-x) cancels for the tiny deltas of slow channels
                             if (!valid) ddl = 0.f;
                             dbias_acc += ddl;
                             ddv[k] = ddl;

@@ -70,8 +70,8 @@ __device__ __forceinline__ TileGeom tile_geom(const Ss2dFusedArgs& p) {
 
 // One 32 x 32 tile x 8 channels. APPLY = false: segment maps; APPLY = true: outputs.
 // Row walks: warp = channel, lane = image row of the tile; column walks: warp = channel, lane = image column.
-template <int R, bool APPLY>
-__global__ void __launch_bounds__(THREADS, 2) ss2d_tile_kernel(const Ss2dFusedArgs p) {
+template <int R, bool APPLY, bool SOFTPLUS>
+__global__ void __launch_bounds__(THREADS, APPLY ? 2 : 3) ss2d_tile_kernel(const Ss2dFusedArgs p) {
     pdl_trigger();
     pdl_wait();
     constexpr int CX = R + 2;                       // [dt rows | B | C] of one direction (dstate 1)
@@ -85,34 +85,62 @@ __global__ void __launch_bounds__(THREADS, 2) ss2d_tile_kernel(const Ss2dFusedAr
     const bool dval = d < p.D;
     const int64_t HW = (int64_t)p.H * p.W;
 
-    // ---- u tile: warp `warp` loads its channel, one image row per instruction (coalesced 128 B) ----
-    {
-        const float* src = p.x + ((int64_t)g.b * p.D + (dval ? d : 0)) * HW + (int64_t)g.h0 * p.W + g.w0 + lane;
-        float* dst = xs + warp * TS * PITCH + lane;
-        const bool cv = dval && lane < g.tw;
-#pragma unroll 8
-        for (int h = 0; h < TS; ++h) dst[h * PITCH] = (cv && h < g.th) ? src[(int64_t)h * p.W] : 0.f;
-    }
-    // projected channels of directions pp, pp + 2: 2 * CX * TS rows of 32 pixels, spread over the 8 warps
-    auto load_xd = [&](int pp) {
-        for (int row = warp; row < 2 * CX * TS; row += DB) {
-            const int q = row / (CX * TS), rem = row - q * (CX * TS);
-            const int c = rem / TS, h = rem - c * TS;
-            const int k = pp + 2 * q;
-            const float* src = p.xdbl + (((int64_t)g.b * 4 + k) * CX + c) * HW + (int64_t)(g.h0 + h) * p.W + g.w0 + lane;
-            xd[(q * CX + c) * TS * PITCH + h * PITCH + lane] = (h < g.th && lane < g.tw) ? *src : 0.f;
+    // Tile loads are 4-byte cp.async copies (zero-filled outside the image): a warp issues one image row of 32 pixels per
+    // instruction (coalesced 128 B) and all of a thread's copies are in flight together (a load -> store loop serialises ~40
+    // DRAM round trips per warp).
+    auto cp4 = [](float* dst, const float* src, bool valid) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(valid ? 4u : 0u) : "memory");
+    };
+    // Addresses advance by pointer increments and an out-of-image copy reads zero bytes from the (clamped, always valid) address
+    // of the tile's first pixel column / row, so a copy costs ~4 instructions; the loads are ~15 % of the kernel's instructions.
+    const int lane_c = min(lane, g.tw - 1);
+    const uint32_t col_ok = lane < g.tw ? 4u : 0u;
+    auto cp_rows = [&](float* dst, const float* src, int row0, int row_step, int n_rows) {
+        // rows row0, row0 + row_step, ... of a (TS x TS) tile plane whose pixel (0, lane_c) is at `src`; dst likewise
+        uint32_t sdst = smem_u32(dst) + (uint32_t)(row0 * PITCH + lane) * 4u;
+        const float* gsrc = src + (int64_t)min(row0, g.th - 1) * p.W;
+        const int64_t gstep = (int64_t)row_step * p.W;
+        int h = row0;
+#pragma unroll 4
+        for (int i = 0; i < n_rows; ++i) {
+            const bool ok = h < g.th;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sdst), "l"(gsrc), "r"(ok ? col_ok : 0u) : "memory");
+            sdst += (uint32_t)(row_step * PITCH) * 4u;
+            h += row_step;
+            if (h < g.th) gsrc += gstep;          // stays inside the image
         }
+    };
+    // ---- u tile: warp `warp` loads its channel ----
+    cp_rows(xs + warp * TS * PITCH, p.x + ((int64_t)g.b * p.D + (dval ? d : 0)) * HW + (int64_t)g.h0 * p.W + g.w0 + lane_c, 0, 1,
+            dval ? TS : 0);
+    if (!dval) {   // a channel slot past D: zeros, so that its lanes compute on defined data
+        for (int i = lane; i < TS * PITCH; i += 32) xs[warp * TS * PITCH + i] = 0.f;
+    }
+    // projected channels of directions pp, pp + 2: 2 * CX planes of TS rows, four rows per warp and plane
+    auto load_xd = [&](int pp) {
+        const float* plane = p.xdbl + ((int64_t)g.b * 4 + pp) * CX * HW + (int64_t)g.h0 * p.W + g.w0 + lane_c;
+#pragma unroll 1
+        for (int qc = 0; qc < 2 * CX; ++qc) {
+            cp_rows(xd + qc * TS * PITCH, plane, warp, DB, TS / DB);
+            plane += (qc == CX - 1) ? (int64_t)(CX + 1) * HW : HW;      // direction pp + 2 starts 2 * CX planes after direction pp
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     };
     load_xd(0);
     __syncthreads();
 
     const int64_t NSr = (int64_t)p.H * p.NTW, NSc = (int64_t)p.W * p.NTH;     // segments per (b, d) sequence: rows / columns
     const int64_t bd = (int64_t)g.b * p.D + d;
+    constexpr int PL = TS * PITCH;                                            // one shared plane
 
-    float yreg[TS];
     // ------------------------------------------------------------------------------------------------------------------
-    // One direction of one pair. ROWS: this lane owns image row `lane` of the tile and walks its 32 pixels; else it owns image
-    // column `lane` and walks down / up. q = 0 forward (k0 / k1), q = 1 backward (k2 / k3).
+    // One direction of one pair. ROWS: this lane owns image row `lane` of the tile and walks its pixels; else it owns image
+    // column `lane` and walks down / up. q = 0 forward (k0 / k1), q = 1 backward (k2 / k3). The walks are ROLLED loops (4 steps
+    // per iteration): fully unrolled they are 130 KB of straight-line code that every CTA executes exactly once — the first
+    // version spent its time in instruction-cache misses (a constant ~200 us whatever the image size).
+    // Where the partial sums live: k0 writes y0 to `acc`, k2 adds y2 (acc = y0 + y2); k1 parks y1 in the output buffer itself
+    // (same thread writes and re-reads it, L2-resident), k3 forms (y0 + y2) + (y1 + y3) and stores the final value.
     // ------------------------------------------------------------------------------------------------------------------
     auto walk = [&](auto rows_tag, auto q_tag) {
         constexpr bool ROWS = decltype(rows_tag)::value;
@@ -126,7 +154,7 @@ __global__ void __launch_bounds__(THREADS, 2) ss2d_tile_kernel(const Ss2dFusedAr
 #pragma unroll
         for (int r = 0; r < R; ++r) wdt[r] = p.dt_w[(int64_t)kd * R + r];
         const int n_own = ROWS ? g.th : g.tw;           // lanes that own a real row / column
-        const int n_step = ROWS ? g.tw : g.th;          // real pixels along the walk
+        const int n_step = ROWS ? g.tw : g.th;          // real pixels along the walk (the rest of the tile is outside the image)
         const bool own = dval && lane < n_own;
         // segment index of this lane's row / column segment in its sequence (memory order)
         const int64_t seg = ROWS ? ((int64_t)(g.h0 + lane) * p.NTW + g.tj) : ((int64_t)(g.w0 + lane) * p.NTH + g.ti);
@@ -134,65 +162,115 @@ __global__ void __launch_bounds__(THREADS, 2) ss2d_tile_kernel(const Ss2dFusedAr
         const int64_t slot = seg_offset(p, k) + bd * NS + seg;
         float h = 0.f, P = 1.f;
         if (APPLY && own) h = p.hin[slot];
-        const float* us = ROWS ? xs + (warp * TS + lane) * PITCH : xs + warp * TS * PITCH + lane;
-        const float* xq = ROWS ? xd + q * CX * TS * PITCH + lane * PITCH : xd + q * CX * TS * PITCH + lane;
         constexpr int ustep = ROWS ? 1 : PITCH;
-#pragma unroll
-        for (int s = 0; s < TS; ++s) {
-            const int i = q == 0 ? s : TS - 1 - s;          // position along the walk, in image coordinates
-            const float u = us[i * ustep];
+        // APPLY walks in flow order. The map pass walks AGAINST the flow: with T = sum of the deltas between a pixel and the
+        // segment's flow end, V = sum_t exp(A T_t) b_t and P = exp(A T_total) — no recurrence, one ex2 per pixel and no expm1
+        // polynomial (an ex2.approx error enters V additively, 2.4e-7 relative, instead of compounding through a product of decays;
+        // P comes from ONE accurate expm1 of the exact sum). 31 instead of ~50 instructions per pixel.
+        constexpr bool ASC = APPLY ? (q == 0) : (q == 1);
+        constexpr int step = ASC ? ustep : -ustep;
+        const int first = ASC ? 0 : (n_step - 1);                       // first visited pixel along the walk
+        const int lane_off = ROWS ? lane * PITCH : lane;
+        const float* us = xs + warp * PL + lane_off + first * ustep;
+        const float* xq = xd + q * CX * PL + lane_off + first * ustep;
+        float* ac = acc + warp * PL + lane_off + first * ustep;
+        // column walks: this lane's pixel column in the output image
+        float* gy = p.y + ((int64_t)g.b * p.D + (dval ? d : 0)) * HW + (int64_t)(g.h0 + first) * p.W + g.w0 + lane;
+        const int64_t gstep = ASC ? p.W : -(int64_t)p.W;
+        const float A2 = A1 * kLog2e;
+        float T = 0.f;
+        (void)ac;
+        (void)gy;
+        (void)gstep;
+        (void)Dv;
+        (void)P;
+        (void)A2;
+        (void)T;
+        (void)gstep;
+        // one pixel; y1v: the parked y1 of this pixel (k3 only)
+        auto pixel = [&](float y1v) {
+            const float u = us[0];
             float dl = bias;
 #pragma unroll
-            for (int r = 0; r < R; ++r) dl = fmaf(wdt[r], xq[r * TS * PITCH + i * ustep], dl);
-            const float Bv = xq[R * TS * PITCH + i * ustep];
-            if (p.softplus) dl = softplus_f(dl);
-            if (i >= n_step) dl = 0.f;                      // outside the image: identity map (e = 0, b = 0)
-            const float e = decay_m1<true>(dl * A1);
+            for (int r = 0; r < R; ++r) dl = fmaf(wdt[r], xq[r * PL], dl);
+            const float Bv = xq[R * PL];
+            if constexpr (SOFTPLUS) dl = softplus_f(dl);
             const float bb = dl * u * Bv;
-            h = fmaf(e, h, h) + bb;
             if constexpr (APPLY) {
-                const float Cv = xq[(R + 1) * TS * PITCH + i * ustep];
-                const float yv = fmaf(Cv, h, Dv * u);
-                yreg[i] = q == 0 ? yv : yreg[i] + yv;       // (y0 + y2) resp. (y1 + y3)
+                const float e = decay_m1<true>(dl * A1);
+                h = fmaf(e, h, h) + bb;
+                const float yv = fmaf(xq[(R + 1) * PL], h, Dv * u);
+                if constexpr (ROWS) {
+                    ac[0] = q == 0 ? yv : ac[0] + yv;                       // y0, then y0 + y2
+                } else if constexpr (q == 0) {
+                    if (own) gy[0] = yv;                                    // y1 parked where the result will go
+                } else {
+                    if (own) gy[0] = ac[0] + (y1v + yv);                    // (y0 + y2) + (y1 + y3)
+                }
+                gy += gstep;
+                ac += step;
             } else {
-                P = fmaf(e, P, P);
+                h = fmaf(ex2_approx(A2 * T), bb, h);                        // h doubles as V
+                T += dl;
             }
+            us += step;
+            xq += step;
+        };
+        constexpr bool K3 = APPLY && !ROWS && q == 1;
+        constexpr int CH = APPLY ? 8 : 4;                                   // pixels per loop iteration
+        // k3 re-reads the y1 values k1 parked in global memory: the loads of the NEXT chunk are issued before this chunk's
+        // arithmetic (the compiler cannot hoist them itself across the chunk's stores to the same array)
+        float ynext[CH];
+        auto fetch = [&](int s0) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) ynext[j] = (K3 && own && s0 + j < n_step) ? gy[(int64_t)j * gstep] : 0.f;
+        };
+        if constexpr (K3) fetch(0);
+        int s = 0;
+        for (; s + CH <= n_step; s += CH) {
+            float ycur[CH];
+#pragma unroll
+            for (int j = 0; j < CH; ++j) ycur[j] = ynext[j];
+            if constexpr (K3) {
+                const float* keep = gy;
+                gy += (int64_t)CH * gstep;
+                fetch(s + CH);
+                gy = const_cast<float*>(keep);
+            }
+#pragma unroll
+            for (int j = 0; j < CH; ++j) pixel(ycur[j]);
+        }
+        for (int j = 0; s < n_step; ++s, ++j) {                             // ragged end of an edge tile
+            float y1v = 0.f;
+            if constexpr (K3) y1v = own ? gy[0] : 0.f;
+            pixel(y1v);
         }
         if constexpr (!APPLY) {
-            if (own) p.agg[slot] = make_float2(P, h);
+            if (own) p.agg[slot] = make_float2(1.f + decay_m1<true>(A1 * T), h);
         }
     };
 
     // ---- directions 0 / 2: along image rows ----
     walk(std::true_type{}, std::integral_constant<int, 0>{});
     walk(std::true_type{}, std::integral_constant<int, 1>{});
-    if constexpr (APPLY) {
-        float* a = acc + (warp * TS + lane) * PITCH;
-#pragma unroll
-        for (int i = 0; i < TS; ++i) a[i] = yreg[i];
-    }
-    __syncthreads();            // everyone is done with the pair-0 channels
+    __syncthreads();            // everyone is done with the pair-0 channels (acc is written and read by the same warp)
     load_xd(1);
     __syncthreads();
     // ---- directions 1 / 3: along image columns ----
     walk(std::false_type{}, std::integral_constant<int, 0>{});
     walk(std::false_type{}, std::integral_constant<int, 1>{});
-    if constexpr (APPLY) {
-        if (dval && lane < g.tw) {
-            float* dst = p.y + ((int64_t)g.b * p.D + d) * HW + (int64_t)g.h0 * p.W + g.w0 + lane;
-            const float* a = acc + warp * TS * PITCH + lane;
-#pragma unroll
-            for (int i = 0; i < TS; ++i)
-                if (i < g.th) dst[(int64_t)i * p.W] = a[i * PITCH] + yreg[i];      // (y0 + y2) + (y1 + y3)
-        }
-    }
 }
 
 // Exclusive scan of one sequence's segment maps in flow order -> the state entering each segment.
-// grid (B * D, 4): blockIdx.y = direction; 256 threads walk the NS segments 256 at a time (coalesced), carrying the running map.
+// grid (B * D, 4): blockIdx.y = direction. A round handles 256 x CPT consecutive flow positions: coalesced loads of CPT maps
+// per thread all in flight, transposed through shared memory so that each thread composes CPT CONSECUTIVE maps in registers,
+// one block-level scan of the 256 thread totals, then the CPT incoming states go back the same way. (The first version walked
+// 256 segments per round with two barriers and a dependent load each: 30 serial rounds = 33 us for the level-0 image.)
+constexpr int CPT = 16;
 __global__ void __launch_bounds__(256) ss2d_carry_kernel(const Ss2dFusedArgs p) {
     pdl_trigger();
     pdl_wait();
+    __shared__ float2 buf[256 * CPT + 256 * CPT / 16];      // padded: index i lives at i + i / 16
     __shared__ float2 wtot[8];
     const int k = blockIdx.y;
     const int64_t bd = blockIdx.x;
@@ -202,38 +280,66 @@ __global__ void __launch_bounds__(256) ss2d_carry_kernel(const Ss2dFusedArgs p) 
     const float2* agg = p.agg + dir_off + bd * NS;
     float* hin = p.hin + dir_off + bd * NS;
     const bool rev = k >= 2;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float carry = 0.f;                                   // state entering the current block of 256 segments
-    for (int64_t f0 = 0; f0 < NS; f0 += 256) {
-        const int64_t f = f0 + threadIdx.x;              // flow index
-        const int64_t s = rev ? NS - 1 - f : f;          // memory index
-        float P = 1.f, V = 0.f;
-        if (f < NS) {
-            const float2 a = agg[s];
-            P = a.x;
-            V = a.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float carry = 0.f;                                   // state entering the current round
+    for (int64_t f0 = 0; f0 < NS; f0 += 256 * CPT) {
+        float2 m[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {                  // coalesced: thread t takes flow positions f0 + j * 256 + t
+            const int64_t f = f0 + j * 256 + tid;
+            m[j] = f < NS ? agg[rev ? NS - 1 - f : f] : make_float2(1.f, 0.f);
         }
-        warp_scan_fwd(P, V, lane);                       // inclusive over the warp, flow order = lane order
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int i = j * 256 + tid;
+            buf[i + (i >> 4)] = m[j];
+        }
+        __syncthreads();
+        float P = 1.f, V = 0.f;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {                  // this thread's CPT consecutive maps, flow order
+            const int i = tid * CPT + j;
+            m[j] = buf[i + (i >> 4)];
+            V = fmaf(m[j].x, V, m[j].y);
+            P *= m[j].x;
+        }
+        warp_scan_fwd(P, V, lane);
         if (lane == 31) wtot[warp] = make_float2(P, V);
         __syncthreads();
-        // state entering this warp's first segment: carry pushed through the preceding warps of the block
-        float hw = carry;
-        for (int w2 = 0; w2 < warp; ++w2) hw = fmaf(wtot[w2].x, hw, wtot[w2].y);
-        // exclusive value of this lane: map of lanes 0 .. lane-1 applied to hw
+        float hw = carry, c = carry;
+        for (int w2 = 0; w2 < 8; ++w2) {
+            const float2 t = wtot[w2];
+            if (w2 < warp) hw = fmaf(t.x, hw, t.y);
+            c = fmaf(t.x, c, t.y);
+        }
         float Pe = __shfl_up_sync(FULL, P, 1), Ve = __shfl_up_sync(FULL, V, 1);
         if (lane == 0) {
             Pe = 1.f;
             Ve = 0.f;
         }
-        if (f < NS) hin[s] = fmaf(Pe, hw, Ve);
-        float c = carry;
-        for (int w2 = 0; w2 < 8; ++w2) c = fmaf(wtot[w2].x, c, wtot[w2].y);
+        float hcur = fmaf(Pe, hw, Ve);                   // state entering this thread's first segment
+        float* hbuf = reinterpret_cast<float*>(buf);
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int i = tid * CPT + j;
+            const float2 mj = m[j];
+            __syncwarp();
+            hbuf[2 * (i + (i >> 4))] = hcur;             // reuse the slot of map i (x component)
+            hcur = fmaf(mj.x, hcur, mj.y);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int i = j * 256 + tid;
+            const int64_t f = f0 + i;
+            if (f < NS) hin[rev ? NS - 1 - f : f] = hbuf[2 * (i + (i >> 4))];
+        }
         carry = c;
         __syncthreads();
     }
 }
 
-template <int R>
+template <int R, bool SP>
 static int launch_fused(const Ss2dFusedArgs& a, cudaStream_t stream) {
     constexpr int CX = R + 2;
     const size_t sm1 = (size_t)(DB * TS * PITCH + 2 * CX * TS * PITCH) * 4;
@@ -243,22 +349,22 @@ static int launch_fused(const Ss2dFusedArgs& a, cudaStream_t stream) {
     cudaGetDevice(&dev);
     dev &= 63;
     if (!attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(ss2d_tile_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+        cudaError_t e = cudaFuncSetAttribute(ss2d_tile_kernel<R, false, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(ss2d_tile_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3);
+        e = cudaFuncSetAttribute(ss2d_tile_kernel<R, true, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3);
         if (e != cudaSuccess) return (int)e;
         attr_done[dev] = true;
     }
     const int nDb = (a.D + DB - 1) / DB;
     const dim3 grid(a.NTW, a.NTH, a.B * nDb);
     if ((int64_t)a.B * nDb > 65535 || a.NTH > 65535) return BEM_ERR_UNSUPPORTED;
-    launch_pdl(ss2d_tile_kernel<R, false>, grid, dim3(THREADS), sm1, stream, a);
+    launch_pdl(ss2d_tile_kernel<R, false, SP>, grid, dim3(THREADS), sm1, stream, a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     launch_pdl(ss2d_carry_kernel, dim3(a.B * a.D, 4), dim3(256), 0, stream, a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    launch_pdl(ss2d_tile_kernel<R, true>, grid, dim3(THREADS), sm3, stream, a);
+    launch_pdl(ss2d_tile_kernel<R, true, SP>, grid, dim3(THREADS), sm3, stream, a);
     return (int)cudaGetLastError();
 }
 
@@ -277,9 +383,9 @@ int ss2d_fused_dispatch(Ss2dFusedArgs a, void* workspace, cudaStream_t stream) {
     a.agg = reinterpret_cast<float2*>(workspace);
     a.hin = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + (nseg * 8 + 255) / 256 * 256);
     switch (a.R) {
-        case 3: return launch_fused<3>(a, stream);
-        case 5: return launch_fused<5>(a, stream);
-        case 10: return launch_fused<10>(a, stream);
+        case 3: return a.softplus ? launch_fused<3, true>(a, stream) : launch_fused<3, false>(a, stream);
+        case 5: return a.softplus ? launch_fused<5, true>(a, stream) : launch_fused<5, false>(a, stream);
+        case 10: return a.softplus ? launch_fused<10, true>(a, stream) : launch_fused<10, false>(a, stream);
         default: return BEM_ERR_UNSUPPORTED;
     }
 }

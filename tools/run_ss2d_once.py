@@ -13,7 +13,7 @@ from bem_b200 import ss2d  # noqa: E402
 from bem_b200.bayesian import functional as BF  # noqa: E402
 
 dev = torch.device("cuda")
-LEVELS = [(40, 400, 600, 3), (80, 200, 300, 5), (160, 100, 150, 10)]
+LEVELS = [(40, 400, 600, 3), (80, 200, 300, 5)] + ([] if os.environ.get("BEM_SS2D_COMPOSED") else [(160, 100, 150, 10)])
 
 
 def chain(x, z, dtw, A, Ds, bias, R):
