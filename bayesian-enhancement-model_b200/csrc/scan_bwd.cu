@@ -20,10 +20,12 @@
 
 namespace bem {
 
-template <typename T, typename DT, int ITEMS, int NW, bool N1>
+// SP: delta_softplus at compile time (1 / 0; fp32 dstate-1 instantiations) or -1 = read from the arguments (see scan_fwd_deferred.cu)
+template <typename T, typename DT, int ITEMS, int NW, bool N1, int SP = -1>
 __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1) scan_bwd_kernel(const ScanBwdArgs p) {
     pdl_trigger();
     pdl_wait();
+    const bool softplus_on = SP >= 0 ? SP == 1 : p.softplus != 0;
     constexpr int CL = 32 * ITEMS;
     constexpr bool kAcc = sizeof(T) == 4;   // fp32 inputs: full-precision decay rate (scan_common.cuh decay_m1)
     constexpr int ROW_SLOT = 2 * CL * (int)sizeof(T) + CL * (int)sizeof(DT);   // [u | delta | dout]
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                         for (int k = 0; k < VT; ++k) {
                             const int i = v * VT + k;
                             float x = dl[k] + bias;
-                            if (p.softplus) x = softplus_f(x);
+                            if (softplus_on) x = softplus_f(x);
                             float ei = decay_m1<kAcc>(x * Av);
                             float bi = x * uv[k] * Bv[k];
                             if (PART && e0 + i >= len) {
@@ -364,7 +366,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                                 x = dl[k];
                             } else {
                                 const float raw = valid ? dl[k] + bias : 0.f;   // stale smem beyond the end may hold NaN patterns
-                                x = p.softplus ? softplus_f(raw) : raw;
+                                x = softplus_on ? softplus_f(raw) : raw;
                             }
                             const float ui = valid ? uv[k] : 0.f;
                             const float dyi = valid ? dy[k] : 0.f;
@@ -380,7 +382,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                             dD_acc = fmaf(dyi, ui, dD_acc);
                             // d softplus = sigmoid(raw) = 1 - exp(-softplus(raw)); equals the reference's switch to 1
                             // above raw = 20 (bwd_kernel_oflex.cuh:250-255) to 2e-9
-                            if (p.softplus) ddl *= -decay_m1<true>(-x);   // expm1 form: 1 - exp(-x) cancels for the tiny deltas of slow channels
+                            if (softplus_on) ddl *= -decay_m1<true>(-x);   // expm1 form: 1 - exp(-x) cancels for the tiny deltas of slow channels
                             if (!valid) ddl = 0.f;
                             dbias_acc += ddl;
                             ddv[k] = ddl;
@@ -653,7 +655,9 @@ template <typename T, typename DT, int ITEMS, bool N1>
 static int launch_bwd(ScanBwdArgs& a, int sm_count, cudaStream_t stream) {
     constexpr int NW = kScanWarps;
     constexpr int CL = 32 * ITEMS;
-    auto kernel = scan_bwd_kernel<T, DT, ITEMS, NW, N1>;
+    auto kernel = scan_bwd_kernel<T, DT, ITEMS, NW, N1, -1>;
+    if constexpr (N1 && sizeof(T) == 4 && sizeof(DT) == 4)      // the BEM configuration: softplus resolved at compile time
+        kernel = a.softplus ? scan_bwd_kernel<T, DT, ITEMS, NW, N1, 1> : scan_bwd_kernel<T, DT, ITEMS, NW, N1, 0>;
     const int hdr_bytes = 128 + ((NW * (2 * a.N + 2) * 4 + 127) / 128) * 128;
     const int stage_bytes = hdr_bytes + NW * (2 * CL * (int)sizeof(T) + CL * (int)sizeof(DT)) + 2 * a.N * CL * (int)sizeof(T);
     const int red_bytes = N1 ? 2 * NW * CL * (int)sizeof(float) : 0;

@@ -52,7 +52,9 @@ struct Pending {   // what a lane keeps of a tile between pass 1 and its finish
 }  // namespace
 
 // RANK: fused dt_proj rank. 0 = delta per channel row; > 0 compile-time rank; -1 = rank from the arguments (<= kMaxDtRank).
-template <int RANK, bool TRACE = false>
+// SP: delta_softplus as a compile-time constant (1 / 0) for the plain kernel, -1 = read from the arguments: a (uniform) branch
+// around softplus_f in every element fences the unrolled elements off from each other in the instruction schedule.
+template <int RANK, int SP = -1, bool TRACE = false>
 __global__ void __launch_bounds__(D_THREADS, 2) scan_fwd_deferred_kernel(const ScanFwdArgs p) {
     pdl_trigger();
     pdl_wait();
@@ -378,7 +380,11 @@ __global__ void __launch_bounds__(D_THREADS, 2) scan_fwd_deferred_kernel(const S
 #pragma unroll
                 for (int k = 0; k < V; ++k) {
                     float xd = dl[k] + bias;
-                    if (p.softplus) xd = softplus_f(xd);
+                    if constexpr (SP >= 0) {
+                        if constexpr (SP == 1) xd = softplus_f(xd);
+                    } else {
+                        if (p.softplus) xd = softplus_f(xd);
+                    }
                     float e = decay_m1<true>(xd * A1);
                     float b = xd * uv[k] * Bv[k];
                     if (PART && e0 + v * V + k >= tc.len) {   // identity padding so the carried state stays exact
@@ -433,7 +439,9 @@ static int launch_deferred(ScanFwdArgs a, int sm_count, cudaStream_t stream) {
     if (stages < 3) return BEM_ERR_UNSUPPORTED;
     a.stages = stages;
     const int smem_bytes = stages * stage_bytes + stages * 3 * 8 + 64;
-    auto kernel = (RANK == 0 && a.trace) ? scan_fwd_deferred_kernel<RANK == 0 ? 0 : RANK, RANK == 0> : scan_fwd_deferred_kernel<RANK, false>;
+    auto kernel = scan_fwd_deferred_kernel<RANK, -1, false>;
+    if (RANK == 0) kernel = a.trace ? scan_fwd_deferred_kernel<0, -1, true>
+                                    : (a.softplus ? scan_fwd_deferred_kernel<0, 1, false> : scan_fwd_deferred_kernel<0, 0, false>);
     static int cached_smem[64] = {0}, cached_per_sm[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);

@@ -372,3 +372,28 @@ def test_softplus_keeps_relative_accuracy_near_the_dt_floor(lo, hi):
     inp["delta_bias"] = torch.zeros(16).cuda()
     inp["A"] = -(1.0 + 50.0 * torch.rand(16, 1, generator=g)).cuda()     # delta * A still moves the state at dt ~ 1e-4
     run_case(inp, True, FP32_TOL)
+
+
+@pytest.mark.parametrize("shape", ["BEM-I-L0", "BEM-I-L1"])
+def test_full_size_backward_bem_inference_levels(shape):
+    """BEM-I level 0 / 1 (B1 KD160 L240000, KD320 L60000: the 600x400 workload's own scans): forward AND every gradient
+    against the fp64 oracle at full size (round 1 held the level-0 shape forward-only)"""
+    cfg = {"BEM-I-L0": (1, 160, 1, 4, 240000), "BEM-I-L1": (1, 320, 1, 4, 60000)}[shape]
+    inp = make_inputs(*cfg, torch.float32, seed=4)
+    run_case(inp, True, FP32_TOL)
+
+
+@pytest.mark.parametrize("cfg", [(1, 640, 1, 4, 129600), (1, 384, 16, 4, 129600)], ids=["HD-KD640-N1", "HD-KD384-N16"])
+def test_full_size_hd_bf16_forward(cfg):
+    """BASELINE configs[3]: the 1920x1080 long-sequence scans (L = 129600 per direction) with bf16 inputs, fp32 'oflex' output,
+    against the fp64 oracle evaluated on the same bf16-rounded inputs; bar 1e-2 (north_star), measured ~1e-5"""
+    bem = _bem()
+    inp = make_inputs(*cfg, torch.bfloat16, seed=6)
+    out = bem.selective_scan_fn(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["delta_bias"], True, True)
+    assert out.dtype == torch.float32 and bem._lib.scan_error_word(out.device) == 0
+    o = oracle.selective_scan_oracle_f64(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["delta_bias"], True)
+    err = nmax_err(out.cpu().numpy(), o["out"])
+    assert err < LOW_TOL, err
+    assert err < 1e-4, err      # the inputs are bf16, the arithmetic is fp32: far inside the bf16 bar
+    out_b = bem.selective_scan_fn(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["delta_bias"], True, False)
+    assert out_b.dtype == torch.bfloat16 and nmax_err(out_b.float().cpu().numpy(), o["out"]) < LOW_TOL
