@@ -78,8 +78,23 @@ class Linear2dReparameterization(_LinearBase):
 
 class LinearReparameterization(_LinearBase):
     """F.linear on the last axis with a sampled weight (linear.py:106-203). No shipped arch instantiates it
-    (channel_first=True everywhere): the sample step runs on bem_bayes_sample, the contraction is the
-    library GEMM."""
+    (channel_first=True everywhere). At inference it runs on the same tcgen05 1x1 kernel as Linear2d: the rows of
+    the (.., in_features) input are the kernel's pixels, so the input is presented channel-major (one transposing copy each
+    way — the layer's natural layout is the transpose of the kernel's); with a gradient the contraction is the library GEMM
+    on the weights sampled by bem_bayes_sample."""
+
+    def _contract(self, input, w, b, S):
+        """w: (S, out, in), b: (S, out) | None"""
+        needs_grad = torch.is_grad_enabled() and (input.requires_grad or w.requires_grad)
+        if input.is_cuda and input.dtype == torch.float32 and not needs_grad and input.numel() > 0:
+            xs = input.reshape(S, -1, self.in_features).transpose(1, 2).contiguous()        # (S, in, rows)
+            out = BF.pointwise_conv(xs, w, b, S)                                             # (S, out, rows)
+            return out.transpose(1, 2).reshape(*input.shape[:-1], self.out_features)
+        if S == 1:
+            return F.linear(input, w[0], None if b is None else b[0])
+        xs = input.reshape(S, -1, self.in_features)
+        out = torch.baddbmm(b.unsqueeze(1), xs, w.transpose(1, 2)) if b is not None else torch.bmm(xs, w.transpose(1, 2))
+        return out.reshape(*input.shape[:-1], self.out_features)
 
     def _forward_uncertain(self, input, eps_weight=None, eps_bias=None):
         if self.training:
@@ -87,11 +102,7 @@ class LinearReparameterization(_LinearBase):
         S = self.mc_samples
         w, _ = self._sample("weight", eps_weight)
         b = self._sample("bias", eps_bias)[0] if self.bias else None
-        if S == 1:
-            return F.linear(input, w[0], None if b is None else b[0])
-        xs = input.reshape(S, -1, self.in_features)
-        out = torch.baddbmm(b.unsqueeze(1), xs, w.transpose(1, 2)) if b is not None else torch.bmm(xs, w.transpose(1, 2))
-        return out.reshape(*input.shape[:-1], self.out_features)
+        return self._contract(input, w, b, S)
 
     def _forward_det(self, input):
-        return F.linear(input, self.mu_weight, self.mu_bias if self.bias else None)
+        return self._contract(input, self.mu_weight.unsqueeze(0), self.mu_bias.unsqueeze(0) if self.bias else None, 1)

@@ -675,7 +675,8 @@ static int launch_bwd(ScanBwdArgs& a, int sm_count, cudaStream_t stream) {
     }
     a.stages = stages;
     const int smem_bytes = stages * stage_bytes + red_bytes + stages * 2 * 8 + 64;
-    static int cached_smem[64] = {0};
+    static int cached_smem_v[2][64] = {{0}};      // per kernel function: [softplus variant][device]
+    int* cached_smem = cached_smem_v[a.softplus ? 1 : 0];
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;

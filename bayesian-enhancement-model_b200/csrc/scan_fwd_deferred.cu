@@ -442,7 +442,11 @@ static int launch_deferred(ScanFwdArgs a, int sm_count, cudaStream_t stream) {
     auto kernel = scan_fwd_deferred_kernel<RANK, -1, false>;
     if (RANK == 0) kernel = a.trace ? scan_fwd_deferred_kernel<0, -1, true>
                                     : (a.softplus ? scan_fwd_deferred_kernel<0, 1, false> : scan_fwd_deferred_kernel<0, 0, false>);
-    static int cached_smem[64] = {0}, cached_per_sm[64] = {0};
+    // the attribute belongs to a kernel FUNCTION: one cache slot per variant this launcher may pick
+    const int variant = RANK != 0 ? 0 : (a.trace ? 3 : (a.softplus ? 1 : 2));
+    static int cached_smem_v[4][64] = {{0}}, cached_per_sm_v[4][64] = {{0}};
+    int* cached_smem = cached_smem_v[variant];
+    int* cached_per_sm = cached_per_sm_v[variant];
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;

@@ -297,3 +297,89 @@ def test_patch_install_on_the_reference_network_end_to_end():
     finally:
         bem_b200.patch.uninstall()
     assert sys.modules["bayesian"] is refb and vm.selective_scan_fn is not bem_b200.selective_scan_fn
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# no-reference scorer and LinearReparameterization on the 1x1 kernel (a14)
+# ---------------------------------------------------------------------------------------------------------------------
+def _textured(seed, H=400, W=600):
+    g = torch.Generator().manual_seed(seed)
+    base = torch.rand(1, 3, H // 8 + 2, W // 8 + 2, generator=g)
+    up = torch.nn.functional.interpolate(base, size=(H, W), mode="bicubic", align_corners=False)
+    return (up + 0.03 * torch.randn(1, 3, H, W, generator=g)).clamp(0, 1)[0]
+
+
+def test_niqe_scorer_vs_reference_numpy_niqe_and_selection():
+    """bem_b200.NiqeScorer (float64 on the device, batched) against basicsr/metrics/niqe.py::calculate_niqe called exactly as
+    Enhancement/eval.py:250 calls it (`calculate_niqe(pred*255, crop_border=0)` on the (H, W, 3) float prediction), on textured
+    600x400 images and on a 300x200 one; then the selection of eval.py:272-275 (`index(min(...))`) on the device scores."""
+    import bem_b200
+    niqe_ref = R.niqe_module().calculate_niqe
+    scorer = bem_b200.NiqeScorer(os.path.join(R.ROOT, "basicsr/metrics/niqe_pris_params.npz"))
+    preds = torch.stack([_textured(s) for s in range(8)])
+    ref = [niqe_ref(p.permute(1, 2, 0).numpy() * 255, crop_border=0) for p in preds]
+    ours = scorer(preds.cuda())
+    assert ours.dtype == torch.float32 and ours.shape == (8,)
+    rel = np.abs(ours.cpu().numpy().astype(np.float64) - np.array(ref)) / np.array(ref)
+    assert rel.max() < 1e-3, rel
+    idx, val = bem_b200.mc.select_best(ours, take_min=True)
+    assert int(idx) == ref.index(min(ref))
+    small = torch.stack([_textured(20 + s, 200, 300) for s in range(3)])
+    ref_s = [niqe_ref(p.permute(1, 2, 0).numpy() * 255, crop_border=0) for p in small]
+    rel = np.abs(scorer(small.cuda()).cpu().numpy().astype(np.float64) - np.array(ref_s)) / np.array(ref_s)
+    assert rel.max() < 1e-3, rel
+    with pytest.raises(RuntimeError):
+        scorer(preds)                              # CUDA only, like every operator of the package
+
+
+def test_mc_infer_with_the_niqe_scorer_selects_the_reference_minimum():
+    """the MC loop end to end on the device: MCSampler predictions of a small Bayesian network, scored by NiqeScorer, selected by
+    bem_select_best (take_min) — same index as the reference's numpy NIQE over the same predictions"""
+    import bem_b200
+    from bem_b200 import mc, network
+    torch.manual_seed(0)
+    net = network.build_bayesian_model().cuda().eval()
+    x = torch.rand(1, 3, 192, 288, device="cuda")
+    scorer = bem_b200.NiqeScorer(os.path.join(R.ROOT, "basicsr/metrics/niqe_pris_params.npz"))
+    sampler = mc.MCSampler(net, seed=5, arena=True, graph=False)
+    res = mc.mc_infer(sampler, x, 6, score_fn=scorer, take_min=True)
+    preds = sampler.sample(x, list(range(6)))
+    niqe_ref = R.niqe_module().calculate_niqe
+    ref = [niqe_ref(p.permute(1, 2, 0).cpu().numpy() * 255, crop_border=0) for p in preds]
+    assert res["index"] == ref.index(min(ref))
+    assert torch.equal(res["best"], preds[res["index"]])
+    assert np.allclose(res["scores"].cpu().numpy(), np.array(ref), rtol=1e-3)
+
+
+@pytest.mark.parametrize("S", [1, 3])
+def test_linear_reparameterization_on_the_pointwise_kernel_vs_reference(S):
+    """LinearReparameterization (linear.py:106-203): the reference layer on the GPU and ours with the same eps; ours runs the
+    contraction on bem_bayes_pointwise (rows as pixels), also with S weight samples per call"""
+    refb = R.bayesian()
+    import bem_b200
+    from bem_b200 import bayesian as ours
+    torch.manual_seed(3)
+    r = refb.LinearReparameterization(40, 24, bias=True).cuda().eval()
+    with torch.no_grad():
+        r.mu_bias.normal_()
+    o = ours.LinearReparameterization(40, 24, bias=True)
+    o.load_state_dict(r.state_dict(), strict=True)
+    o = o.cuda().eval()
+    x = torch.randn(S, 6, 10, 40, device="cuda")
+    outs, epsw, epsb = [], [], []
+    with torch.no_grad(), torch.backends.cuda.sdp_kernel() if False else torch.no_grad():
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            for s in range(S):
+                outs.append(r(x[s]))
+                epsw.append(r.eps_weight.clone())
+                epsb.append(r.eps_bias.clone())
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        bem_b200._lib.profile.reset()
+        ours.set_mc_config(o, mc_samples=S)
+        y = o(x.reshape(S * 6, 10, 40), eps_weight=torch.stack(epsw), eps_bias=torch.stack(epsb))
+        ours.set_mc_config(o, mc_samples=1)
+    assert bem_b200._lib.profile.launches >= 2            # sample kernel(s) + the pointwise kernel
+    assert nmax_err(y.reshape(S, 6, 10, 24).cpu().numpy(), torch.stack(outs).cpu().numpy()) < 1e-5
