@@ -378,13 +378,21 @@ def main_ours(args):
     # the BASELINE configs[2] job: `--job` samples of one image sharded over ranks + selection exchange
     job = None
     if args.job > 0:
-        mc.mc_infer(sampler, img, args.job)          # untimed: collective set-up, allocator growth for the gathered predictions
+        # scorer of the job: device-resident NIQE (Enhancement/eval.py --no_ref niqe: lower is better) when the reference's
+        # pristine-model parameters are at hand (BEM_NIQE_PARAMS, or the staged copy of basicsr/metrics/niqe_pris_params.npz),
+        # else the luminance-contrast stand-in
+        npz = os.environ.get("BEM_NIQE_PARAMS") or os.path.join(ROOT, "oracle", "_ref", "reference", "basicsr", "metrics", "niqe_pris_params.npz")
+        if os.path.exists(npz):
+            score_fn, take_min, scorer_name = bem_b200.NiqeScorer(npz), True, "niqe (bem_b200.NiqeScorer, float64 on the device)"
+        else:
+            score_fn, take_min, scorer_name = mc.default_score, False, "luminance contrast stand-in (NIQE parameters not found)"
+        mc.mc_infer(sampler, img, args.job, score_fn=score_fn, take_min=take_min)   # untimed: collective set-up, allocator growth
         barrier()
         t0 = time.perf_counter()
-        res = mc.mc_infer(sampler, img, args.job)
+        res = mc.mc_infer(sampler, img, args.job, score_fn=score_fn, take_min=take_min)
         barrier()
         job_s = time.perf_counter() - t0
-        job = {"samples": args.job, "seconds": job_s, "images_per_s": args.job / job_s, "best_index": res["index"]}
+        job = {"samples": args.job, "seconds": job_s, "images_per_s": args.job / job_s, "best_index": res["index"], "scorer": scorer_name}
 
     if world > 1:
         t = torch.tensor([ms, ms_e2e, job["seconds"] if job else 0.0], device=dev, dtype=torch.float64)

@@ -367,7 +367,7 @@ def test_linear_reparameterization_on_the_pointwise_kernel_vs_reference(S):
     o = o.cuda().eval()
     x = torch.randn(S, 6, 10, 40, device="cuda")
     outs, epsw, epsb = [], [], []
-    with torch.no_grad(), torch.backends.cuda.sdp_kernel() if False else torch.no_grad():
+    with torch.no_grad():
         prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = False
         try:
