@@ -149,6 +149,70 @@ __device__ __forceinline__ float softplus_f(float x) {
     const float big = kLn2 * lg2_approx(1.f + z);          // z >= 2^-4: rounding of 1 + z costs <= 1e-6 relative
     return fmaxf(x, 0.f) + (z < 0.0625f ? log1p_small(z) : big);
 }
+// ------------------------------------------------------------------------------------------------
+// Packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 execute two fp32 operations per issued instruction). The scan kernels are
+// bound by instruction issue, and two thirds of their instructions are fp32 arithmetic on independent elements, so the element
+// math is evaluated for TWO positions at a time. Every packed operation is the same IEEE operation as its scalar twin
+// (fma.rn / mul.rn / add.rn per half), and the helpers below mirror softplus_f / decay_m1 operation for operation: results
+// are bit-identical to the scalar forms.
+// ------------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 r, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r)); }
+__device__ __forceinline__ f32x2 splat2(float v) { return pk2(v, v); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// softplus_f of two values (same operations per half)
+__device__ __forceinline__ f32x2 softplus2(float x0, float x1) {
+    const float z0 = ex2_approx(-fabsf(x0) * kLog2e), z1 = ex2_approx(-fabsf(x1) * kLog2e);
+    const f32x2 z = pk2(z0, z1);
+    float u0, u1;
+    upk2(add2(splat2(1.f), z), u0, u1);
+    const f32x2 big = mul2(splat2(kLn2), pk2(lg2_approx(u0), lg2_approx(u1)));
+    f32x2 p = fma2(z, splat2(-1.f / 6.f), splat2(0.2f));
+    p = fma2(z, p, splat2(-0.25f));
+    p = fma2(z, p, splat2(1.f / 3.f));
+    p = fma2(z, p, splat2(-0.5f));
+    p = fma2(z, p, splat2(1.f));
+    const f32x2 sm = mul2(z, p);
+    float s0, s1, b0, b1;
+    upk2(sm, s0, s1);
+    upk2(big, b0, b1);
+    return add2(pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)), pk2(z0 < 0.0625f ? s0 : b0, z1 < 0.0625f ? s1 : b1));
+}
+// decay_m1<true> of two values
+__device__ __forceinline__ f32x2 decay_m1_2(f32x2 y) {
+    float y0, y1, t0, t1;
+    upk2(y, y0, y1);
+    upk2(mul2(y, splat2(kLog2e)), t0, t1);
+    const f32x2 fast = add2(pk2(ex2_approx(t0), ex2_approx(t1)), splat2(-1.f));
+    f32x2 p = fma2(y, splat2(1.f / 120.f), splat2(1.f / 24.f));
+    p = fma2(y, p, splat2(1.f / 6.f));
+    p = fma2(y, p, splat2(0.5f));
+    const f32x2 e = fma2(mul2(y, y), p, y);
+    float e0, e1, f0, f1;
+    upk2(e, e0, e1);
+    upk2(fast, f0, f1);
+    return pk2(y0 > -0.125f ? e0 : f0, y1 > -0.125f ? e1 : f1);
+}
+
 // d softplus / dx = sigmoid(x); the reference switches to 1 above the threshold
 // (cusoflex/selective_scan_bwd_kernel_oflex.cuh:250-255)
 __device__ __forceinline__ float softplus_grad_f(float x) {

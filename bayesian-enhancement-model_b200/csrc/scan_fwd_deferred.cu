@@ -377,23 +377,34 @@ __global__ void __launch_bounds__(D_THREADS, 2) scan_fwd_deferred_kernel(const S
                 }
                 lds_items<float, V>(sB + v * V, Bv);
                 lds_items<float, V>(sC + v * V, Cv);
+                // the element math that does not depend on the recurrence (softplus, decay, b, D u) runs two positions at a
+                // time on the packed fp32 pipe (scan_common.cuh); the recurrence and alpha / beta stay scalar
 #pragma unroll
-                for (int k = 0; k < V; ++k) {
-                    float xd = dl[k] + bias;
-                    if constexpr (SP >= 0) {
-                        if constexpr (SP == 1) xd = softplus_f(xd);
-                    } else {
-                        if (p.softplus) xd = softplus_f(xd);
+                for (int k = 0; k < V; k += 2) {
+                    f32x2 xd = add2(pk2(dl[k], dl[k + 1]), splat2(bias));
+                    const bool sp_on = SP >= 0 ? SP == 1 : p.softplus != 0;
+                    if (sp_on) {
+                        float x0, x1;
+                        upk2(xd, x0, x1);
+                        xd = softplus2(x0, x1);
                     }
-                    float e = decay_m1<true>(xd * A1);
-                    float b = xd * uv[k] * Bv[k];
-                    if (PART && e0 + v * V + k >= tc.len) {   // identity padding so the carried state stays exact
-                        e = 0.f;
-                        b = 0.f;
+                    f32x2 e2 = decay_m1_2(mul2(xd, splat2(A1)));
+                    f32x2 b2 = mul2(mul2(xd, pk2(uv[k], uv[k + 1])), pk2(Bv[k], Bv[k + 1]));
+                    const f32x2 du2 = mul2(splat2(Dv), pk2(uv[k], uv[k + 1]));
+                    float ee[2], bb[2], du[2];
+                    upk2(e2, ee[0], ee[1]);
+                    upk2(b2, bb[0], bb[1]);
+                    upk2(du2, du[0], du[1]);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        if (PART && e0 + v * V + k + j >= tc.len) {   // identity padding so the carried state stays exact
+                            ee[j] = 0.f;
+                            bb[j] = 0.f;
+                        }
+                        decay_step(ee[j], bb[j], P, Vv);
+                        al[k + j] = Cv[k + j] * P;
+                        be[k + j] = fmaf(Cv[k + j], Vv, du[j]);
                     }
-                    decay_step(e, b, P, Vv);
-                    al[k] = Cv[k] * P;
-                    be[k] = fmaf(Cv[k], Vv, Dv * uv[k]);
                 }
                 sts_items<float, V>(su + v * V, al);
                 sts_items<float, V>(su + CL + v * V, be);

@@ -216,6 +216,50 @@ __global__ void __launch_bounds__(THREADS, APPLY ? 2 : 3) ss2d_tile_kernel(const
             us += step;
             xq += step;
         };
+        // two consecutive pixels of the walk: everything that does not depend on the recurrence (dt_proj, softplus, decay, b,
+        // D u) on the packed fp32 pipe (scan_common.cuh: FFMA2 / FMUL2 / FADD2, bit-identical to the scalar forms), then
+        // the two recurrence steps
+        auto pixel_pair = [&](float y1a, float y1b) {
+            const f32x2 u2 = pk2(us[0], us[step]);
+            f32x2 dl2 = splat2(bias);
+#pragma unroll
+            for (int r = 0; r < R; ++r) dl2 = fma2(splat2(wdt[r]), pk2(xq[r * PL], xq[r * PL + step]), dl2);
+            const f32x2 B2 = pk2(xq[R * PL], xq[R * PL + step]);
+            float d0, d1;
+            upk2(dl2, d0, d1);
+            if constexpr (SOFTPLUS) {
+                dl2 = softplus2(d0, d1);
+                upk2(dl2, d0, d1);
+            }
+            float bb[2];
+            upk2(mul2(mul2(dl2, u2), B2), bb[0], bb[1]);
+            if constexpr (APPLY) {
+                float e[2], du[2];
+                upk2(decay_m1_2(mul2(dl2, splat2(A1))), e[0], e[1]);
+                upk2(mul2(splat2(Dv), u2), du[0], du[1]);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    h = fmaf(e[j], h, h) + bb[j];
+                    const float yv = fmaf(xq[(R + 1) * PL + j * step], h, du[j]);
+                    if constexpr (ROWS) {
+                        ac[0] = q == 0 ? yv : ac[0] + yv;
+                    } else if constexpr (q == 0) {
+                        if (own) gy[0] = yv;
+                    } else {
+                        if (own) gy[0] = ac[0] + ((j == 0 ? y1a : y1b) + yv);
+                    }
+                    gy += gstep;
+                    ac += step;
+                }
+            } else {
+                h = fmaf(ex2_approx(A2 * T), bb[0], h);
+                T += d0;
+                h = fmaf(ex2_approx(A2 * T), bb[1], h);
+                T += d1;
+            }
+            us += 2 * step;
+            xq += 2 * step;
+        };
         constexpr bool K3 = APPLY && !ROWS && q == 1;
         constexpr int CH = APPLY ? 8 : 4;                                   // pixels per loop iteration
         // k3 re-reads the y1 values k1 parked in global memory: the loads of the NEXT chunk are issued before this chunk's
@@ -238,7 +282,7 @@ __global__ void __launch_bounds__(THREADS, APPLY ? 2 : 3) ss2d_tile_kernel(const
                 gy = const_cast<float*>(keep);
             }
 #pragma unroll
-            for (int j = 0; j < CH; ++j) pixel(ycur[j]);
+            for (int j = 0; j < CH; j += 2) pixel_pair(ycur[j], ycur[j + 1]);
         }
         for (int j = 0; s < n_step; ++s, ++j) {                             // ragged end of an edge tile
             float y1v = 0.f;
