@@ -15,7 +15,8 @@ Follows basicsr/metrics/niqe.py step by step (the numbers in brackets are its li
   * [126-139] multivariate-Gaussian fit of the 36-d block features (nanmean, covariance of the NaN-free rows), distance to the
     pristine model: sqrt(d^T pinv((cov_p + cov_d) / 2) d).
 All arithmetic after the luma conversion is float64 on the device (the reference is float64 numpy), batched over images;
-nothing synchronises with the host. The pristine parameters are the reference's own file (basicsr/metrics/niqe_pris_params.npz),
+nothing synchronises with the host. The per-pixel work (local statistics, normalisation, the block moments of the five maps)
+runs in two hand-written kernels (csrc/niqe.cu); what remains per image is a few kilobytes of moment algebra in torch. The pristine parameters are the reference's own file (basicsr/metrics/niqe_pris_params.npz),
 read from a path the caller gives — they are not part of this repository.
 """
 from __future__ import annotations
@@ -96,7 +97,7 @@ class NiqeScorer:
             gam = t(self._gam)
             rg = 1.0 / gam
             r_gam = torch.exp(2 * torch.lgamma(rg * 2) - torch.lgamma(rg) - torch.lgamma(rg * 3))   # niqe.py:26
-            c = dict(mu=t(self._mu), cov=t(self._cov), win=t(self._win)[None, None], gam=gam, r_gam=r_gam)
+            c = dict(mu=t(self._mu), cov=t(self._cov), win=t(self._win).contiguous(), gam=gam, r_gam=r_gam.contiguous())
             self._dev[device] = c
         return c
 
@@ -110,37 +111,46 @@ class NiqeScorer:
         return m
 
     @staticmethod
-    def _aggd(x, c):
-        """x: (..., n) -> alpha, beta_l, beta_r (niqe.py:13-38)"""
-        neg, pos = x < 0, x > 0
-        x2 = x * x
-        left = torch.sqrt((x2 * neg).sum(-1) / neg.sum(-1))          # mean over an empty set -> nan, like numpy
-        right = torch.sqrt((x2 * pos).sum(-1) / pos.sum(-1))
+    def _aggd_from_moments(m, n, c):
+        """m: (..., 6) = [sum_{v<0} v^2, #{v<0}, sum_{v>0} v^2, #{v>0}, sum |v|, sum v^2] over n values -> alpha, beta_l, beta_r
+        (niqe.py:13-38). The table of r(gamma) is strictly increasing, so `argmin((r_gam - rhatnorm)**2)` is a binary search plus
+        one comparison of the two neighbours (ties -> the lower index, as argmin); a NaN statistic selects index 0 like numpy."""
+        left = torch.sqrt(m[..., 0] / m[..., 1])              # mean over an empty set -> nan, like numpy
+        right = torch.sqrt(m[..., 2] / m[..., 3])
         gh = left / right
-        rhat = x.abs().mean(-1) ** 2 / x2.mean(-1)
+        rhat = (m[..., 4] / n) ** 2 / (m[..., 5] / n)
         rn = rhat * (gh ** 3 + 1) * (gh + 1) / (gh ** 2 + 1) ** 2
-        d = (c["r_gam"] - rn.unsqueeze(-1)) ** 2
-        d = torch.where(torch.isnan(d), torch.full_like(d, -1.0), d)   # np.argmin returns the first NaN: index 0
-        alpha = c["gam"][torch.argmin(d, dim=-1)]
+        rg = c["r_gam"]
+        hi = torch.searchsorted(rg, rn.contiguous()).clamp(1, rg.numel() - 1)
+        lo = hi - 1
+        pick_hi = (rg[hi] - rn) ** 2 < (rg[lo] - rn) ** 2
+        idx = torch.where(pick_hi, hi, lo)
+        idx = torch.where(torch.isnan(rn), torch.zeros_like(idx), idx)
+        alpha = c["gam"][idx]
         s = torch.exp(0.5 * (torch.lgamma(1 / alpha) - torch.lgamma(3 / alpha)))
         return alpha, left * s, right * s
 
     def _features(self, img, c, bs):
-        """img: (S, H, W) float64, H / W multiples of bs -> (S, blocks, 18)   (niqe.py:104-116, 41-60)"""
+        """img: (S, H, W) float32, H / W multiples of bs -> (S, blocks, 18) float64   (niqe.py:104-116, 41-60): the per-pixel
+        work runs in csrc/niqe.cu (bem_niqe_mscn, bem_niqe_block_stats), the 18 features per block come from the moments"""
+        from . import _lib
+        from ._lib import lib
         S, H, W = img.shape
-        pad = torch.nn.functional.pad(img[:, None], (3, 3, 3, 3), mode="replicate")
-        mu = torch.nn.functional.conv2d(pad, c["win"])[:, 0]
-        pad2 = torch.nn.functional.pad((img * img)[:, None], (3, 3, 3, 3), mode="replicate")
-        sigma = torch.sqrt(torch.abs(torch.nn.functional.conv2d(pad2, c["win"])[:, 0] - mu * mu))
-        nrm = (img - mu) / (sigma + 1)
-        blk = nrm.view(S, H // bs, bs, W // bs, bs).permute(0, 1, 3, 2, 4).reshape(S, -1, bs, bs)
-        feats = []
-        a, bl, br = self._aggd(blk.flatten(-2), c)
-        feats += [a, (bl + br) / 2]
-        for sh in ((0, 1), (1, 0), (1, 1), (1, -1)):
-            a, bl, br = self._aggd((blk * torch.roll(blk, shifts=sh, dims=(-2, -1))).flatten(-2), c)
-            mean = (br - bl) * torch.exp(torch.lgamma(2 / a) - torch.lgamma(1 / a))
-            feats += [a, mean, bl, br]
+        img = img.contiguous()
+        dev = img.device
+        nrm = torch.empty((S, H, W), dtype=torch.float64, device=dev)
+        nb = (H // bs) * (W // bs)
+        mom = torch.empty((S, nb, 5, 6), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            _lib.check(lib.bem_niqe_mscn(_lib.ptr(img), _lib.ptr(c["win"]), _lib.ptr(nrm), S, H, W, st), "niqe_mscn")
+            _lib.check(lib.bem_niqe_block_stats(_lib.ptr(nrm), _lib.ptr(mom), S, H, W, bs, st), "niqe_block_stats")
+        _lib.profile.launches += 2
+        a, bl, br = self._aggd_from_moments(mom, float(bs * bs), c)          # (S, nb, 5) each
+        g21 = torch.exp(torch.lgamma(2 / a) - torch.lgamma(1 / a))
+        feats = [a[..., 0], (bl[..., 0] + br[..., 0]) / 2]
+        for k in range(1, 5):
+            feats += [a[..., k], (br[..., k] - bl[..., k]) * g21[..., k], bl[..., k], br[..., k]]
         return torch.stack(feats, dim=-1)
 
     @torch.no_grad()
@@ -154,7 +164,7 @@ class NiqeScorer:
         p = p / 255.0                                                      # to_y_channel (metric_util.py:45)
         y = (p[:, 0].double() * 24.966 + p[:, 1].double() * 128.553 + p[:, 2].double() * 65.481 + 16.0)   # bgr2ycbcr y_only
         y = ((y / 255.0).float() * 255.0)                                  # float32 round trips of the reference (:52, _convert_output_type_range)
-        img = torch.round(y).double()
+        img = torch.round(y)                                               # float32, integer-valued
         bs = self.BLOCK
         S, H, W = img.shape
         nh, nw = H // bs, W // bs
@@ -163,7 +173,7 @@ class NiqeScorer:
         img = img[:, :nh * bs, :nw * bs]
         f1 = self._features(img, c, bs)
         Mh, Mw = self._resize_mats(nh * bs, nw * bs, pred.device)
-        small = (Mh @ (img / 255.0).float().double() @ Mw.t()).float().double() * 255.0   # imresize works in float32
+        small = (Mh @ (img / 255.0).double() @ Mw.t()).float() * 255.0     # imresize works in float32
         f2 = self._features(small, c, bs // 2)
         dist = torch.cat([f1, f2], dim=-1)                                 # (S, blocks, 36)
         mu_d = torch.nanmean(dist, dim=1)

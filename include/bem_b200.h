@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define BEM_ABI_VERSION 12
+#define BEM_ABI_VERSION 13
 
 /* element types of u/delta/B/C/x-activations */
 enum { BEM_F32 = 0, BEM_F16 = 1, BEM_BF16 = 2 };
@@ -337,6 +337,22 @@ int bem_conv3x3(const BemConv3x3Params* p, void* stream);
  *   scores : (n) fp32;  out_index : int32[1];  out_value : fp32[1] or NULL
  * ---------------------------------------------------------------------------------------------- */
 int bem_select_best(const float* scores, int32_t n, int32_t take_min, int32_t* out_index, float* out_value, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * No-reference scorer of the Monte-Carlo predictions: the per-pixel part of NIQE, batched over images, fp64.
+ * Replaces the inner loops of basicsr/metrics/niqe.py (called per prediction by Enhancement/eval.py:249-250):
+ * bem_niqe_mscn        : mean / deviation with the 7x7 Gaussian window (scipy.ndimage.convolve, mode 'nearest') and the
+ *                        normalised image (img - mu) / (sigma + 1)                                   (niqe.py:104-108)
+ *     img : (n, H, W) fp32 (the rounded luma, or the half-scale image); window7x7 : 49 doubles; out : (n, H, W) fp64
+ * bem_niqe_block_stats : per (block x block) tile of the normalised image, for the tile and its products with the four
+ *                        circular shifts (0,1), (1,0), (1,1), (1,-1) of niqe.py:55-57, the moments the AGGD fit of
+ *                        niqe.py:13-38 needs: sum_{v<0} v^2, #{v<0}, sum_{v>0} v^2, #{v>0}, sum |v|, sum v^2
+ *     normalized : (n, H, W) fp64, H and W multiples of `block`; out : (n, (H/block)*(W/block), 5, 6) fp64, tiles row-major
+ * The gamma-table matching, the 36-d Gaussian fit and the pseudo-inverse (niqe.py:126-139) are host-language code over
+ * these few kilobytes (bem_b200/niqe.py).
+ * ---------------------------------------------------------------------------------------------- */
+int bem_niqe_mscn(const float* img, const double* window7x7, double* out, int32_t n_images, int32_t H, int32_t W, void* stream);
+int bem_niqe_block_stats(const double* normalized, double* out, int32_t n_images, int32_t H, int32_t W, int32_t block, void* stream);
 
 #ifdef __cplusplus
 }
