@@ -183,7 +183,11 @@ class NiqeScorer:
         m = z.sum(dim=1, keepdim=True) / n.unsqueeze(-1)
         zc = torch.where(ok.unsqueeze(-1), dist - m, torch.zeros_like(dist))
         cov_d = zc.transpose(1, 2) @ zc / (n.unsqueeze(-1) - 1)
-        inv = torch.linalg.pinv((c["cov"] + cov_d) / 2, rtol=1e-15, hermitian=False)
-        d = (c["mu"] - mu_d).unsqueeze(1)
-        q = torch.sqrt((d @ inv @ d.transpose(1, 2)).reshape(S))
+        # niqe.py:132-134: d pinv(M) d^T with M = (cov_p + cov_d) / 2. M is symmetric positive definite (the pristine
+        # covariance has full rank), where the pseudo-inverse is the inverse: one batched LU solve instead of S SVDs (the SVD
+        # path of torch.linalg.pinv costs ~1.4 ms per image). solve_ex neither raises nor synchronises; a singular M (only
+        # possible with NaN features) yields NaN, which selection treats like the reference does.
+        d = (c["mu"] - mu_d).unsqueeze(-1)                                 # (S, 36, 1)
+        sol = torch.linalg.solve_ex((c["cov"] + cov_d) / 2, d)[0]
+        q = torch.sqrt((d * sol).sum(dim=(1, 2)))
         return q.float()
