@@ -146,9 +146,9 @@ class BaseLayer_(_lib.InvalidatesCaches, nn.Module):
         """-> (w, eps_used) with w: (S, *shape). stream ids: 2*layer_id for weights, 2*layer_id + 1 for biases."""
         mu, rho = getattr(self, "mu_" + which), getattr(self, "rho_" + which)
         arena = getattr(self, "_arena", None)
-        if (arena is not None and given is None and self.eps_source == "philox" and self.mc_samples == 1
+        if (arena is not None and given is None and self.eps_source == "philox" and self.mc_samples == arena[which].shape[0]
                 and not (torch.is_grad_enabled() and mu.requires_grad)):
-            return arena[which].unsqueeze(0), None   # drawn for the whole network by MCArena.draw (one launch)
+            return arena[which], None   # (S, *shape), drawn for the whole network by MCArena.draw (one launch per sample set)
         eps = self._draw_eps(which, given)
         sid = 2 * int(self.layer_id) + (1 if which == "bias" else 0)
         w, used = BF.sample_weights(mu, rho, eps, self.mc_samples, self.mc_seed, sid, self.mc_sample0)

@@ -876,7 +876,8 @@ static int tc_plan(const BemBayesPointwiseParams& p, TcPlan& t) {
     const bool aligned = (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && p.P % 4 == 0 && p.x_img_stride % 4 == 0;
     tc_tiling(p.cin, p.cout, P3_NMAX, t.ntiles, t.NT, t.nk);
     // the persistent kernel keeps the epilogue vectors of every (sample, tile) in shared memory
-    t.persistent = aligned && !force_v2 && (int64_t)p.n_samples * t.ntiles * t.NT * 8 <= 16 * 1024;
+    // (S-batched Monte-Carlo forwards: S weight sets x up to 1280 output channels = 40 KB at S = 4; the raw-stage count shrinks to fit)
+    t.persistent = aligned && !force_v2 && (int64_t)p.n_samples * t.ntiles * t.NT * 8 <= 64 * 1024;
     if (!t.persistent) tc_tiling(p.cin, p.cout, TC_NMAX, t.ntiles, t.NT, t.nk);
     t.vec = t.pack + tc_pack_floats(p.n_samples, p.cin, p.cout, t.persistent ? P3_NMAX : TC_NMAX);
     t.pack_blocks = p.n_samples * t.ntiles * t.nk;

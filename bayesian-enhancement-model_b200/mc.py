@@ -63,13 +63,14 @@ class MCArena:
     every layer exactly the numbers its per-layer Philox path would. The sample index can be read from a device word,
     which is what lets a captured CUDA graph of the forward be replayed for any sample."""
 
-    def __init__(self, net, seed: int):
+    def __init__(self, net, seed: int, n_sets: int = 1):
         from .bayesian.base_layer import BaseLayer_
         bayesian.set_mc_config(net)                       # assigns layer ids (= Philox stream ids) in module order
         self.layers = [m for m in net.modules() if isinstance(m, BaseLayer_)]
         if not self.layers:
             raise RuntimeError("MCArena: the network has no bem_b200.bayesian layers")
         self.seed = int(seed)
+        self.S = S = max(1, int(n_sets))                  # weight sets per draw: the S Monte-Carlo samples of one batched forward
         self.device = self.layers[0].mu_weight.device
         _lib.require_cuda(self.layers[0].mu_weight)
         tensors = []   # (layer, which, mu, rho, stream_id, offset)
@@ -82,24 +83,28 @@ class MCArena:
                 if mu.dtype != torch.float32 or not mu.is_contiguous() or not rho.is_contiguous():
                     raise RuntimeError("MCArena: parameters must be contiguous float32")
                 tensors.append((L, which, mu, rho, 2 * int(L.layer_id) + (1 if which == "bias" else 0), total))
-                total += (mu.numel() + 3) // 4 * 4          # keep every view 16-byte aligned
+                total += ((mu.numel() + 3) // 4 * 4) * S    # the S sets of a tensor lie back to back: the view (S, *shape) is contiguous
         self.buffer = torch.empty(total, dtype=torch.float32, device=self.device)
         base = self.buffer.data_ptr()
-        rows, blocks = [], []
+        rows, blocks = [[] for _ in range(S)], []
         self._ptrs = []
         self.views = {}    # id(layer) -> {"weight": view, "bias": view} into self.buffer (several arenas may serve one network)
         for e, (L, which, mu, rho, sid, off) in enumerate(tensors):
             n = mu.numel()
-            rows.append([mu.data_ptr(), rho.data_ptr(), base + 4 * off, n, sid])
+            pad = (n + 3) // 4 * 4
+            for sset in range(S):
+                rows[sset].append([mu.data_ptr(), rho.data_ptr(), base + 4 * (off + sset * pad), n, sid])
             self._ptrs.append((mu, rho, mu.data_ptr(), rho.data_ptr()))
             for b0 in range(0, (n + 3) // 4, 256):
                 blocks.append([e, b0])
-            self.views.setdefault(id(L), {})[which] = self.buffer[off:off + n].view(mu.shape)
+            # true view of the S sets of this tensor, (S, *shape); contiguous whenever numel is a multiple of 4 (every BEM tensor)
+            view = torch.as_strided(self.buffer, (S,) + tuple(mu.shape), (pad,) + tuple(mu.stride()), off)
+            self.views.setdefault(id(L), {})[which] = view
             L.__dict__["_arena_views"] = self.views[id(L)]      # the most recent arena's views (introspection, tests)
-        self.entries = torch.tensor(rows, dtype=torch.int64).to(self.device)
+        self.entries = [torch.tensor(r, dtype=torch.int64).to(self.device) for r in rows]   # one table per weight set
         self.blocks = torch.tensor(blocks, dtype=torch.int32).to(self.device)
         self.n_blocks = len(blocks)
-        self.sample0 = torch.zeros((), dtype=torch.int64, device=self.device)   # device-side sample index (graph replay)
+        self.sample0 = torch.zeros(S, dtype=torch.int64, device=self.device)   # device-side sample index of every set (graph replay)
         self._net = net
         self._stamp = self._net_stamp()
         self.plans = {}   # input shape -> functional.PackPlan: the pack steps of all Bayesian 1x1 layers in one launch per draw
@@ -121,14 +126,28 @@ class MCArena:
         for L in self.layers:
             L._arena = self.views[id(L)] if on else None
 
-    def draw(self, sample_id: Optional[int] = None, plan=None):
-        """fill the arena for global sample `sample_id`; None = read the index from the device word `self.sample0`.
+    def set_samples(self, sample_ids):
+        """global sample indices of the S sets of the next device-indexed draw (a short list is padded with its last id);
+        stream-ordered fills, no host synchronisation"""
+        ids = [int(i) for i in sample_ids]
+        ids = ids + [ids[-1]] * (self.S - len(ids))
+        if self.S == 1:
+            self.sample0.fill_(ids[0])
+        else:
+            for j in range(self.S):
+                self.sample0[j].fill_(ids[j])
+
+    def draw(self, sample_id=None, plan=None):
+        """fill the arena: set s gets global sample `sample_id + s` (an int) / `sample_id[s]` (a sequence); None = read the indices
+        from the device words `self.sample0` (what a captured graph does). One launch per weight set.
         `plan`: a built PackPlan whose layers are packed from the fresh draw (one more launch)."""
         from .bayesian import functional as BF
-        if sample_id is None:
-            BF.sample_batched(self.entries, self.blocks, self.n_blocks, self.seed, 0, self.sample0)
-        else:
-            BF.sample_batched(self.entries, self.blocks, self.n_blocks, self.seed, int(sample_id), None)
+        for sset in range(self.S):
+            if sample_id is None:
+                BF.sample_batched(self.entries[sset], self.blocks, self.n_blocks, self.seed, 0, self.sample0[sset:])
+            else:
+                sid = sample_id[min(sset, len(sample_id) - 1)] if isinstance(sample_id, (list, tuple)) else int(sample_id) + sset
+                BF.sample_batched(self.entries[sset], self.blocks, self.n_blocks, self.seed, int(sid), None)
         if plan is not None:
             plan.run()
 
@@ -190,9 +209,12 @@ class MCSampler:
 
     net        : network whose Bayesian layers come from bem_b200.bayesian (e.g. network.build_bayesian_model())
     seed       : Philox seed shared by all ranks
-    batch      : samples evaluated per forward (S-batched grouped kernels); 1 reproduces the reference loop
+    batch      : Monte-Carlo samples evaluated per forward: every launch carries `batch` images and `batch` weight sets
+                 (S-batched kernels), which amortises the ramp of the ~150 kernels of a forward; the arena then draws `batch`
+                 sets per forward. Sample i's prediction does not depend on the batch it was computed in (bit for bit).
+                 1 reproduces the reference loop
     out_index  : which element of the network's output list is the prediction (eval.py:200 uses [-1])
-    arena      : draw all layers' weights with one launch per sample (philox source, batch 1); same numbers as without
+    arena      : draw all layers' weights with one launch per sample set (philox source); same numbers as without
     graph      : capture the forward of one sample as a CUDA graph per input shape and replay it (needs `arena`); the
                  reference's ~700 launches per sample are otherwise bound by the host
     lanes      : samples in flight at once (needs `graph`): each lane replays its own graph on its own stream, so the ramp
@@ -207,7 +229,7 @@ class MCSampler:
         self.eps_source = eps_source
         self.out_index = out_index
         self.post = post or (lambda y: torch.clamp(y, 0, 1))   # eval.py:201
-        self.use_arena = bool(arena) and eps_source == "philox" and self.batch == 1
+        self.use_arena = bool(arena) and eps_source == "philox"
         self.use_graph = bool(graph) and self.use_arena
         self._lanes = [_Lane() for _ in range(max(1, int(lanes)) if self.use_graph else 1)]
         bayesian.set_prediction_type(net, deterministic=False)
@@ -224,14 +246,22 @@ class MCSampler:
     def _get_arena(self, lane=None):
         lane = lane or self._lanes[0]
         if lane.arena is None or not lane.arena.valid():
-            lane.arena = MCArena(self.net, self.seed)
+            lane.arena = MCArena(self.net, self.seed, self.batch)
             lane.graphs = {}
         return lane.arena
 
     def _forward_one(self, x):
+        """one forward of `batch` Monte-Carlo samples of the image x (1, C, H, W) -> (batch, C_out, H, W): the image is repeated,
+        image s meets weight set s in every Bayesian layer (mc_samples = batch)"""
+        if self.batch > 1:
+            x = x.expand(self.batch, -1, -1, -1).contiguous()
         y = self.net(x)
         y = y[self.out_index] if isinstance(y, (list, tuple)) else y
         return self.post(y)
+
+    def _groups(self, ids):
+        """the ids of a request in runs of `batch` (one run per forward)"""
+        return [ids[i:i + self.batch] for i in range(0, len(ids), self.batch)]
 
     def _graph_for(self, x, lane=None):
         """(graph, static input, static output) of `lane` for inputs like x; captured with the lane's arena attached"""
@@ -258,8 +288,8 @@ class MCSampler:
 
     def _lane_graphs(self, x, n):
         """the first min(lanes, n) lanes with their graphs for inputs like x (captured on first use)"""
-        lanes = self._lanes[: max(1, min(len(self._lanes), n))]
-        bayesian.set_mc_config(self.net, mc_samples=1, eps_source="philox", seed=self.seed, sample0=0)
+        lanes = self._lanes[: max(1, min(len(self._lanes), (n + self.batch - 1) // self.batch))]
+        bayesian.set_mc_config(self.net, mc_samples=self.batch, eps_source="philox", seed=self.seed, sample0=0)
         recs = []
         for lane in lanes:
             arena = self._get_arena(lane)
@@ -295,7 +325,8 @@ class MCSampler:
         side by side: per sample the image goes H2D into the lane's graph input and the prediction D2H from its output.
         Returns after everything has landed."""
         ids = list(sample_ids)
-        if not (self.use_graph and x_host.shape[0] == 1 and len(self._lanes) > 1 and len(ids) > 1):
+        groups = self._groups(ids)
+        if not (self.use_graph and x_host.shape[0] == 1 and (len(self._lanes) > 1 or self.batch > 1) and len(ids) > 1):
             for i, sid in enumerate(ids):
                 self._sample_to_host(x_host, out_host[i:i + 1], sid)
             return out_host
@@ -305,13 +336,15 @@ class MCSampler:
             lanes, recs = self._lane_graphs(torch.empty(x_host.shape, dtype=x_host.dtype, device=dev), len(ids))
             for lane in lanes:
                 lane.stream.wait_stream(cur)
-            for i, sid in enumerate(ids):
-                lane, (g, static_x, static_y) = lanes[i % len(lanes)], recs[i % len(lanes)]
+            row = 0
+            for gi, grp in enumerate(groups):
+                lane, (g, static_x, static_y) = lanes[gi % len(lanes)], recs[gi % len(lanes)]
                 with torch.cuda.stream(lane.stream):
                     static_x.copy_(x_host, non_blocking=True)
-                    lane.arena.sample0.fill_(int(sid))
+                    lane.arena.set_samples(grp)
                     g.replay()
-                    out_host[i].copy_(static_y[0], non_blocking=True)
+                    out_host[row:row + len(grp)].copy_(static_y[:len(grp)], non_blocking=True)
+                row += len(grp)
             for lane in lanes:
                 lane.stream.synchronize()
         return out_host
@@ -327,7 +360,7 @@ class MCSampler:
             key = (tuple(x_host.shape), x_host.dtype, dev)
             rec = self._graphs.get(key)
             if rec is None:
-                bayesian.set_mc_config(self.net, mc_samples=1, eps_source="philox", seed=self.seed, sample0=0)
+                bayesian.set_mc_config(self.net, mc_samples=self.batch, eps_source="philox", seed=self.seed, sample0=0)
                 arena.attach(True)
                 try:
                     rec = self._graph_for(x_host.to(dev))
@@ -335,8 +368,9 @@ class MCSampler:
                     arena.attach(False)
             g, static_x, static_y = rec
             static_x.copy_(x_host, non_blocking=True)
-            arena.sample0.fill_(int(sample_id))
+            arena.set_samples([int(sample_id)])
             g.replay()
+            static_y = static_y[:1]
             out_host.copy_(static_y[0] if out_host.dim() == static_y.dim() - 1 else static_y, non_blocking=True)
         else:
             dev = next(self.net.parameters()).device
@@ -350,40 +384,42 @@ class MCSampler:
         outs = []
         ids = list(sample_ids)
         if self.use_arena and ids and x.is_cuda and x.shape[0] == 1:
-            if self.use_graph and len(self._lanes) > 1 and len(ids) > 1:
+            groups = self._groups(ids)
+            if self.use_graph and len(self._lanes) > 1 and len(groups) > 1:
                 cur = torch.cuda.current_stream(x.device)
                 lanes, recs = self._lane_graphs(x, len(ids))
                 for lane, (g, static_x, static_y) in zip(lanes, recs):
                     lane.stream.wait_stream(cur)
                     with torch.cuda.stream(lane.stream):
                         static_x.copy_(x)
-                outs = [None] * len(ids)
-                for i, sid in enumerate(ids):
-                    lane, (g, static_x, static_y) = lanes[i % len(lanes)], recs[i % len(lanes)]
+                outs = [None] * len(groups)
+                for gi, grp in enumerate(groups):
+                    lane, (g, static_x, static_y) = lanes[gi % len(lanes)], recs[gi % len(lanes)]
                     with torch.cuda.stream(lane.stream):
-                        lane.arena.sample0.fill_(int(sid))
+                        lane.arena.set_samples(grp)
                         g.replay()
-                        outs[i] = static_y.clone()
+                        outs[gi] = static_y[:len(grp)].clone()
                 for lane in lanes:
                     cur.wait_stream(lane.stream)
                 for o in outs:
                     o.record_stream(cur)
                 return torch.cat(outs, dim=0)
             arena = self._get_arena()
-            bayesian.set_mc_config(self.net, mc_samples=1, eps_source="philox", seed=self.seed, sample0=0)
+            bayesian.set_mc_config(self.net, mc_samples=self.batch, eps_source="philox", seed=self.seed, sample0=0)
             arena.attach(True)
             try:
                 if self.use_graph:
                     g, static_x, static_y = self._graph_for(x)
                     static_x.copy_(x)
-                    for sid in ids:
-                        arena.sample0.fill_(int(sid))
+                    for grp in groups:
+                        arena.set_samples(grp)
                         g.replay()
-                        outs.append(static_y.clone())
+                        outs.append(static_y[:len(grp)].clone())
                 else:
                     key = (tuple(x.shape), x.dtype, x.device)
-                    for sid in ids:
-                        outs.append(arena.forward_planned(key, int(sid), lambda: self._forward_one(x)))
+                    for grp in groups:
+                        full = [int(i) for i in grp] + [int(grp[-1])] * (self.batch - len(grp))
+                        outs.append(arena.forward_planned(key, full, lambda: self._forward_one(x))[:len(grp)])
             finally:
                 arena.attach(False)
             return torch.cat(outs, dim=0)

@@ -333,11 +333,33 @@ def test_batched_sampling_matches_per_layer_sampling():
                     continue
                 sid = 2 * int(L.layer_id) + (which == "bias")
                 w, _ = BF.sample_weights(getattr(L, "mu_" + which), getattr(L, "rho_" + which), None, 1, 99, sid, sample)
-                assert torch.equal(w[0], L._arena_views[which]), (L.layer_id, which, sample)
+                assert torch.equal(w, L._arena_views[which]), (L.layer_id, which, sample)
     arena.sample0.fill_(5)
     arena.draw(None)                                   # sample index from the device word (CUDA-graph replay path)
     ref, _ = BF.sample_weights(arena.layers[1].mu_weight, arena.layers[1].rho_weight, None, 1, 99, 2 * int(arena.layers[1].layer_id), 5)
-    assert torch.equal(ref[0], arena.layers[1]._arena_views["weight"])
+    assert torch.equal(ref, arena.layers[1]._arena_views["weight"])
+    # S weight sets per draw (the S-batched Monte-Carlo forward): set s = the per-layer draw of its own global sample index
+    arena4 = mc.MCArena(net, seed=99, n_sets=4)
+    ids = [7, 3, 2 ** 33 + 5, 3]
+    for mode in ("host", "device"):
+        if mode == "host":
+            arena4.draw(ids)
+        else:
+            arena4.set_samples(ids)
+            arena4.draw(None)
+        for L in arena4.layers:
+            for which in ("weight", "bias"):
+                if which == "bias" and not L.bias:
+                    continue
+                v = arena4.views[id(L)][which]
+                assert v.shape[0] == 4 and v.is_contiguous()
+                sid = 2 * int(L.layer_id) + (which == "bias")
+                for j, sample in enumerate(ids):
+                    w, _ = BF.sample_weights(getattr(L, "mu_" + which), getattr(L, "rho_" + which), None, 1, 99, sid, sample)
+                    assert torch.equal(w[0], v[j]), (mode, L.layer_id, which, j)
+    arena4.draw(10)                                    # an int: consecutive samples 10, 11, 12, 13
+    w, _ = BF.sample_weights(arena4.layers[0].mu_weight, arena4.layers[0].rho_weight, None, 1, 99, 2 * int(arena4.layers[0].layer_id), 12)
+    assert torch.equal(w[0], arena4.views[id(arena4.layers[0])]["weight"][2])
 
 
 def test_constant_weight_pack_cache_tracks_in_place_updates():

@@ -105,6 +105,32 @@ def test_mc_sampler_is_batch_and_shard_invariant():
     assert nmax_err(res["mean"].cpu().numpy(), a.mean(0).clamp(0, 1).cpu().numpy()) < 1e-6
 
 
+def test_s_batched_graph_sampler_is_bit_identical_to_one_sample_per_forward():
+    """MCSampler(batch = S): every launch of the captured forward carries S images and S weight sets (the north_star's
+    MC-sample-batched convs). The prediction of sample i must not depend on the batch it rode in — bit for bit, with ragged
+    last groups, sharded id lists, one lane or two."""
+    from bem_b200 import mc, network
+    torch.manual_seed(0)
+    net = network.build_bayesian_model().cuda().eval()
+    x = torch.rand(1, 3, 64, 96, device="cuda")
+    ids = [0, 1, 2, 3, 4, 5, 6]
+    with torch.backends.cudnn.flags(allow_tf32=False):
+        ref = mc.MCSampler(net, seed=11, batch=1, arena=True, graph=True).sample(x, ids)
+        for S, lanes in ((2, 1), (4, 1), (3, 2)):
+            got = mc.MCSampler(net, seed=11, batch=S, arena=True, graph=True, lanes=lanes).sample(x, ids)
+            assert got.shape == ref.shape
+            assert torch.equal(got, ref), (S, lanes, float((got - ref).abs().max()))
+        shard = mc.shard_samples(16, 3, 8)              # ids 3, 11
+        a = mc.MCSampler(net, seed=11, batch=4, arena=True, graph=True).sample(x, shard)
+        b = mc.MCSampler(net, seed=11, batch=1, arena=True, graph=False).sample(x, shard)
+        assert torch.equal(a, b)
+        eager4 = mc.MCSampler(net, seed=11, batch=4, arena=True, graph=False).sample(x, ids)
+        assert torch.equal(eager4, ref)
+        host = torch.empty(7, 3, 64, 96).pin_memory()
+        mc.MCSampler(net, seed=11, batch=4, arena=True, graph=True).samples_to_host(x.cpu().pin_memory(), host, ids)
+        assert torch.equal(host.cuda(), ref)
+
+
 def test_select_best_golden(golden_select):
     """bit-exact index: first max / first min with Python's NaN behaviour (Enhancement/eval.py:270-274)"""
     from bem_b200 import mc
