@@ -263,6 +263,17 @@ class MCSampler:
         """the ids of a request in runs of `batch` (one run per forward)"""
         return [ids[i:i + self.batch] for i in range(0, len(ids), self.batch)]
 
+    def _tail_sampler(self, n):
+        """a sampler of the same network / seed whose forwards carry exactly n samples: the ragged last group of a request
+        (13 samples per rank on 8 GPUs = 3 x 4 + 1) runs at its own size instead of padding a full batch"""
+        tails = self.__dict__.setdefault("_tails", {})
+        t = tails.get(n)
+        if t is None:
+            t = MCSampler(self.net, self.seed, batch=n, eps_source=self.eps_source, out_index=self.out_index, post=self.post,
+                          arena=self.use_arena, graph=self.use_graph, lanes=1)
+            tails[n] = t
+        return t
+
     def _graph_for(self, x, lane=None):
         """(graph, static input, static output) of `lane` for inputs like x; captured with the lane's arena attached"""
         lane = lane or self._lanes[0]
@@ -325,8 +336,19 @@ class MCSampler:
         side by side: per sample the image goes H2D into the lane's graph input and the prediction D2H from its output.
         Returns after everything has landed."""
         ids = list(sample_ids)
+        if self.batch > 1 and len(ids) % self.batch and self.use_arena:     # ragged last group: its own batch size
+            cut = len(ids) - len(ids) % self.batch
+            if cut:
+                self._samples_to_host(x_host, out_host[:cut], ids[:cut])
+            self._tail_sampler(len(ids) - cut)._samples_to_host(x_host, out_host[cut:], ids[cut:])
+            return out_host
         groups = self._groups(ids)
         if not (self.use_graph and x_host.shape[0] == 1 and (len(self._lanes) > 1 or self.batch > 1) and len(ids) > 1):
+            if self.batch > 1:      # one full group without the graph path
+                dev = next(self.net.parameters()).device
+                out_host.copy_(self._sample(x_host.to(dev, non_blocking=True), ids), non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()
+                return out_host
             for i, sid in enumerate(ids):
                 self._sample_to_host(x_host, out_host[i:i + 1], sid)
             return out_host
@@ -384,6 +406,10 @@ class MCSampler:
         outs = []
         ids = list(sample_ids)
         if self.use_arena and ids and x.is_cuda and x.shape[0] == 1:
+            if self.batch > 1 and len(ids) % self.batch:                    # ragged last group: its own batch size
+                cut = len(ids) - len(ids) % self.batch
+                tail = self._tail_sampler(len(ids) - cut)._sample(x, ids[cut:])
+                return torch.cat([self._sample(x, ids[:cut]), tail], dim=0) if cut else tail
             groups = self._groups(ids)
             if self.use_graph and len(self._lanes) > 1 and len(groups) > 1:
                 cur = torch.cuda.current_stream(x.device)

@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying the CUDA graph")
-    ap.add_argument("--lanes", type=int, default=2, help="MC samples in flight per GPU (sampler lanes, each its own graph and stream)")
+    ap.add_argument("--lanes", type=int, default=2, help="forwards in flight per GPU (sampler lanes, each its own graph and stream)")
+    ap.add_argument("--batch", type=int, default=1, help="Monte-Carlo samples per forward (S-batched kernels: every launch carries S images and S weight sets)")
     ap.add_argument("--job", type=int, default=100, help="samples of the MC job timed after the steps (0 = skip)")
     ap.add_argument("--config", default="mc", choices=["mc", "c1", "hd", "train"],
                     help="mc = BASELINE configs[1]/[2] (headline); c1 / hd / train = configs[0] / [3] / [4]")
@@ -311,8 +312,8 @@ def main_ours(args):
     torch.manual_seed(0)                              # same random-init weights on every rank
     net = network.build_bayesian_model().to(dev).eval()
     # product path: one-launch weight arena + the forward of one sample captured as a CUDA graph and replayed
-    sampler = mc.MCSampler(net, seed=287128, batch=1, eps_source="philox", arena=True, graph=not args.no_graph, lanes=args.lanes)
-    eager = mc.MCSampler(net, seed=287128, batch=1, eps_source="philox", arena=True, graph=False)   # per-kernel profile pass
+    sampler = mc.MCSampler(net, seed=287128, batch=args.batch, eps_source="philox", arena=True, graph=not args.no_graph, lanes=args.lanes)
+    eager = mc.MCSampler(net, seed=287128, batch=args.batch, eps_source="philox", arena=True, graph=False)   # per-kernel profile pass
     img_host = torch.rand(1, 3, H_IMG, W_IMG).pin_memory()
     img = img_host.to(dev)
     out_host = torch.empty(max(args.steps, 2), 3, H_IMG, W_IMG).pin_memory()
@@ -330,7 +331,7 @@ def main_ours(args):
     def steps_e2e(first, n):   # the public host-buffer call: per step H2D of the image, one MC sample, D2H of the prediction
         sampler.samples_to_host(img_host, out_host[:n], [rank + (first + i) * world for i in range(n)])
 
-    steps(0, max(args.warmup, 2 * args.lanes))
+    steps(0, max(args.warmup, 2 * args.lanes * args.batch))
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -355,17 +356,18 @@ def main_ours(args):
 
     # per-kernel pass, outside the timed region: the same samples run eagerly, every C-ABI call bracketed by CUDA events
     # on the launching stream (the graph replays exactly these launches); also counts the launches of one step
-    eager.sample(img, [rank])
+    eager.sample(img, [rank + i * world for i in range(args.batch)])
     _lib.profile.reset(armed=True)
-    prof_steps = min(args.steps, 5)
-    for i in range(prof_steps):
-        eager.sample(img, [rank + (args.warmup + i) * world])
+    prof_fwd = max(1, min(args.steps, 5) // args.batch)          # forwards of the profile pass, `batch` samples (= steps) each
+    prof_steps = prof_fwd * args.batch
+    for i in range(prof_fwd):
+        eager.sample(img, [rank + (args.warmup + i * args.batch + j) * world for j in range(args.batch)])
     launches = _lib.profile.launches * args.steps // prof_steps
     prof = _lib.profile.summary()
     _lib.profile.reset(armed=False)
 
     # end to end through the public API with host buffers
-    steps_e2e(0, max(2, min(args.steps, 2 * args.lanes)))
+    steps_e2e(0, max(2, min(args.steps, 2 * args.lanes * args.batch)))
     barrier()
     e2e_ms = []
     for _ in range(len(region_ms)):

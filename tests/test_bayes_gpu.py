@@ -352,7 +352,7 @@ def test_batched_sampling_matches_per_layer_sampling():
                 if which == "bias" and not L.bias:
                     continue
                 v = arena4.views[id(L)][which]
-                assert v.shape[0] == 4 and v.is_contiguous()
+                assert v.shape[0] == 4 and (v.is_contiguous() or v[0].numel() % 4 != 0)   # contiguous for 16-byte multiples (every BEM tensor)
                 sid = 2 * int(L.layer_id) + (which == "bias")
                 for j, sample in enumerate(ids):
                     w, _ = BF.sample_weights(getattr(L, "mu_" + which), getattr(L, "rho_" + which), None, 1, 99, sid, sample)
