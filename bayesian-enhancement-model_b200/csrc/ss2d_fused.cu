@@ -75,10 +75,14 @@ __global__ void __launch_bounds__(THREADS, APPLY ? 2 : 3) ss2d_tile_kernel(const
     pdl_trigger();
     pdl_wait();
     constexpr int CX = R + 2;                       // [dt rows | B | C] of one direction (dstate 1)
+    // projected channels staged per direction PAIR (two loads per tile) while that keeps two CTAs on an SM (dt_rank 3: 110 KB),
+    // else per direction (four loads, half the buffer): dt_rank 5 would otherwise run one CTA = 8 warps per SM
+    constexpr bool PAIR = R <= 3;
+    constexpr int XD_DIRS = PAIR ? 2 : 1;
     extern __shared__ __align__(16) float sm[];
     float* xs = sm;                                 // [DB][TS][PITCH]   u
     float* acc = xs + DB * TS * PITCH;              // [DB][TS][PITCH]   y0 + y2 (APPLY only)
-    float* xd = APPLY ? acc + DB * TS * PITCH : acc;   // [2][CX][TS][PITCH] projected channels of the two directions of a pair
+    float* xd = APPLY ? acc + DB * TS * PITCH : acc;   // [XD_DIRS][CX][TS][PITCH] projected channels of the staged direction(s)
     const TileGeom g = tile_geom(p);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int d = g.d0 + warp;
@@ -117,17 +121,17 @@ __global__ void __launch_bounds__(THREADS, APPLY ? 2 : 3) ss2d_tile_kernel(const
         for (int i = lane; i < TS * PITCH; i += 32) xs[warp * TS * PITCH + i] = 0.f;
     }
     // projected channels of directions pp, pp + 2: 2 * CX planes of TS rows, four rows per warp and plane
-    auto load_xd = [&](int pp) {
-        const float* plane = p.xdbl + ((int64_t)g.b * 4 + pp) * CX * HW + (int64_t)g.h0 * p.W + g.w0 + lane_c;
+    auto load_xd = [&](int k0, int ndirs) {                    // directions k0, k0 + 2, ... (ndirs of them) into xd
+        const float* plane = p.xdbl + ((int64_t)g.b * 4 + k0) * CX * HW + (int64_t)g.h0 * p.W + g.w0 + lane_c;
 #pragma unroll 1
-        for (int qc = 0; qc < 2 * CX; ++qc) {
+        for (int qc = 0; qc < ndirs * CX; ++qc) {
             cp_rows(xd + qc * TS * PITCH, plane, warp, DB, TS / DB);
-            plane += (qc == CX - 1) ? (int64_t)(CX + 1) * HW : HW;      // direction pp + 2 starts 2 * CX planes after direction pp
+            plane += (qc == CX - 1) ? (int64_t)(CX + 1) * HW : HW;      // direction k0 + 2 starts 2 * CX planes after direction k0
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     };
-    load_xd(0);
+    load_xd(0, XD_DIRS);
     __syncthreads();
 
     const int64_t NSr = (int64_t)p.H * p.NTW, NSc = (int64_t)p.W * p.NTH;     // segments per (b, d) sequence: rows / columns
@@ -172,7 +176,7 @@ __global__ void __launch_bounds__(THREADS, APPLY ? 2 : 3) ss2d_tile_kernel(const
         const int first = ASC ? 0 : (n_step - 1);                       // first visited pixel along the walk
         const int lane_off = ROWS ? lane * PITCH : lane;
         const float* us = xs + warp * PL + lane_off + first * ustep;
-        const float* xq = xd + q * CX * PL + lane_off + first * ustep;
+        const float* xq = xd + (PAIR ? q : 0) * CX * PL + lane_off + first * ustep;
         float* ac = acc + warp * PL + lane_off + first * ustep;
         // column walks: this lane's pixel column in the output image
         float* gy = p.y + ((int64_t)g.b * p.D + (dval ? d : 0)) * HW + (int64_t)(g.h0 + first) * p.W + g.w0 + lane;
@@ -296,12 +300,22 @@ __global__ void __launch_bounds__(THREADS, APPLY ? 2 : 3) ss2d_tile_kernel(const
 
     // ---- directions 0 / 2: along image rows ----
     walk(std::true_type{}, std::integral_constant<int, 0>{});
+    if constexpr (!PAIR) {
+        __syncthreads();
+        load_xd(2, 1);
+        __syncthreads();
+    }
     walk(std::true_type{}, std::integral_constant<int, 1>{});
-    __syncthreads();            // everyone is done with the pair-0 channels (acc is written and read by the same warp)
-    load_xd(1);
+    __syncthreads();            // everyone is done with the staged channels (acc is written and read by the same warp)
+    load_xd(1, XD_DIRS);
     __syncthreads();
     // ---- directions 1 / 3: along image columns ----
     walk(std::false_type{}, std::integral_constant<int, 0>{});
+    if constexpr (!PAIR) {
+        __syncthreads();
+        load_xd(3, 1);
+        __syncthreads();
+    }
     walk(std::false_type{}, std::integral_constant<int, 1>{});
 }
 
@@ -386,7 +400,8 @@ __global__ void __launch_bounds__(256) ss2d_carry_kernel(const Ss2dFusedArgs p) 
 template <int R, bool SP>
 static int launch_fused(const Ss2dFusedArgs& a, cudaStream_t stream) {
     constexpr int CX = R + 2;
-    const size_t sm1 = (size_t)(DB * TS * PITCH + 2 * CX * TS * PITCH) * 4;
+    constexpr int XD_DIRS = R <= 3 ? 2 : 1;
+    const size_t sm1 = (size_t)(DB * TS * PITCH + XD_DIRS * CX * TS * PITCH) * 4;
     const size_t sm3 = sm1 + (size_t)DB * TS * PITCH * 4;
     static bool attr_done[64] = {false};
     int dev = 0;

@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying the CUDA graph")
     ap.add_argument("--lanes", type=int, default=2, help="forwards in flight per GPU (sampler lanes, each its own graph and stream)")
-    ap.add_argument("--batch", type=int, default=1, help="Monte-Carlo samples per forward (S-batched kernels: every launch carries S images and S weight sets)")
+    ap.add_argument("--batch", type=int, default=4, help="Monte-Carlo samples per forward (S-batched kernels: every launch carries S images and S weight sets)")
     ap.add_argument("--job", type=int, default=100, help="samples of the MC job timed after the steps (0 = skip)")
     ap.add_argument("--config", default="mc", choices=["mc", "c1", "hd", "train"],
                     help="mc = BASELINE configs[1]/[2] (headline); c1 / hd / train = configs[0] / [3] / [4]")
@@ -435,7 +435,7 @@ def main_ours(args):
             "config": {"workload": "stage-1 Bayesian UNet (n_feat 40, blocks [2,2,2], d_state 1), 1 MC sample per rank per step, 600x400",
                        "l2": "per-step working set (38-307 MB activations per layer) exceeds the 126 MB L2",
                        "eps": "philox (seed, layer, sample)", "samples_sharding": "sample i -> rank i % n_gpus",
-                       "execution": "eager launches" if args.no_graph else f"CUDA graph replay of one sample's forward, {args.lanes} samples in flight per GPU (sampler lanes)"},
+                       "execution": "eager launches" if args.no_graph else f"CUDA graph replay of one S-batched forward ({args.batch} Monte-Carlo samples per forward: every launch carries {args.batch} images and {args.batch} weight sets), {args.lanes} forwards in flight per GPU (sampler lanes)"},
             "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": img_host.numel() * 4,
                     "d2h_bytes_per_step": out_host[0].numel() * 4},
             "regions": {"timed": len(region_ms), "ms": region_ms, "reported": "median"},
