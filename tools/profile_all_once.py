@@ -1,5 +1,5 @@
 """One pass over the hot-path kernels at their level-0 (600x400) shapes, each launched twice (the second launch is the one
-to read in an ncu capture): `ncu --set full -k regex:'scan_|pointwise_tc3|depthwise3|csm_|conv3x3' python tools/profile_all_once.py`."""
+to read in an ncu capture): `ncu --set full -k regex:'scan_|ss2d_|pointwise_tc3|depthwise3|csm_|conv3x3' python tools/profile_all_once.py`."""
 import os
 import sys
 
@@ -8,7 +8,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bem_b200  # noqa: E402
-from bem_b200 import csm  # noqa: E402
+from bem_b200 import csm, ss2d  # noqa: E402
 from bem_b200.bayesian import functional as BF  # noqa: E402
 
 dev = torch.device("cuda")
@@ -30,6 +30,12 @@ x160 = torch.randn(1, 160, H, W, device=dev)
 x320 = torch.randn(1, 320, H, W, device=dev)
 ln40 = (torch.ones(40, device=dev), torch.zeros(40, device=dev), 1e-5)
 w = lambda co, ci: torch.randn(1, co, ci, device=dev) / ci ** 0.5
+# traversal-aware SS2D core (ss2d_fused.cu), level 0: D = 40, dt_rank 3
+z40 = torch.randn(1, 4 * 5, L, device=dev) * 0.5
+dtw = torch.randn(160, 3, device=dev) * 0.5
+A4 = -torch.rand(160, 1, device=dev) - 0.5
+D4 = torch.randn(160, device=dev)
+b4 = torch.randn(160, device=dev) * 0.5
 for rep in range(2):
     out, xc = ext.fwd(u, delta, A, Bm, Cm, D, bias, True, 1, True)
     ext.bwd(u, delta, A, Bm, Cm, D, bias, dout, xc, True, 1)
@@ -40,6 +46,7 @@ for rep in range(2):
     BF.depthwise_conv3x3(x40, torch.randn(1, 40, 3, 3, device=dev), torch.randn(1, 40, device=dev), 1, act="silu")
     BF.conv3x3_direct(torch.randn(1, 3, H, W, device=dev), torch.randn(40, 3, 3, 3, device=dev), torch.randn(40, device=dev))   # first_conv
     BF.conv3x3_direct(x40, torch.randn(3, 40, 3, 3, device=dev), torch.randn(3, device=dev))                                     # proj
+    ss2d.ss2d_fwd(x40, z40, dtw, A4, D4, b4)
     xs = csm.cross_scan_fn(x40, True, True, 0)
     csm.cross_merge_fn(xs.view(1, 4, 40, H, W), True, True, 0)
 torch.cuda.synchronize()
