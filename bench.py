@@ -266,6 +266,20 @@ def scan_rooflines(dev, peak, reps=24):
     res["pointwise"] = {"bound": "hbm", "achieved": nb / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": nb / (ms * 1e-3) / 1e9 / peak, "traffic": None, "bytes_per_launch": float(nb), "ms_per_launch": ms,
                         "launches_timed": reps, "tensor_tflops": 3 * 2.0 * L * cin * cout / (ms * 1e-3) / 1e12}
+    # traversal-aware SS2D core at level 0 (D = 40, dt_rank 3): cross-scan gather + four-direction scan (dt_proj fused) + cross-merge
+    # scatter in three launches. Algorithmic bytes: SURVEY 8(d) "fused SS2D" form, B*D*L*s + B*KD*L*s + 2*B*K*N*L*s + B*D*L*s_o = 238 MB
+    # (which still counts a per-channel delta tensor; what the kernels need is x + the x_proj output + y = 96 MB).
+    from bem_b200 import ss2d
+    Dm, R = 40, 3
+    xs2 = torch.randn(1, Dm, H_IMG, W_IMG, generator=g).to(dev)
+    zs2 = (0.5 * torch.randn(1, 4 * (R + 2), L, generator=g)).to(dev)
+    dtw = (0.5 * torch.randn(4 * Dm, R, generator=g)).to(dev)
+    ms = timed(lambda: ss2d.ss2d_fwd(xs2, zs2, dtw, A, D, bias))
+    nb = 4 * L * (Dm + 4 * Dm + 2 * 4 + Dm)
+    res["ss2d"] = {"bound": "hbm", "achieved": nb / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": nb / (ms * 1e-3) / 1e9 / peak,
+                   "traffic": None, "bytes_per_launch": float(nb), "ms_per_launch": ms, "launches_timed": reps,
+                   "needed_bytes": float(4 * L * (2 * Dm + 4 * (R + 2))),
+                   "note": "three kernels (tile maps, carry scan, tile outputs); instruction-latency bound, not HBM bound (profiles/r02_kernels.md)"}
     s_in, s_o = 4, 4
     fwd_bytes = Bn * KD * L * (2 * s_in + s_o) + 2 * Bn * G * N * L * s_in
     bwd_bytes = Bn * KD * L * (4 * s_in + s_o) + 4 * Bn * G * N * L * s_in
@@ -411,18 +425,19 @@ def main_ours(args):
     peak, peak_src = measured_peaks()
     # dominant kernel of the hot path: the level-0 scan forward (largest traffic per launch of the section-8 rows)
     sr = scan_rooflines(dev, peak)
-    roof = dict(sr["fwd"], kernel="scan_fwd_deferred_kernel<0> (B1, KD160, N1, L240000, fp32)", peak_source=peak_src,
+    roof = dict(sr["fwd"], kernel="scan_fwd_deferred_kernel<0, softplus> (B1, KD160, N1, L240000, fp32)", peak_source=peak_src,
                 timing="8 back-to-back C-ABI calls per CUDA-graph replay, CUDA events around the replay / 8; working set 468 MB >> 126 MB L2")
     eager_fwd = prof.get("scan_fwd")
     if eager_fwd:   # the same launches as they ran inside the eager per-kernel pass (adds host launch gaps)
         key, rec = max(eager_fwd["by_key"].items(), key=lambda kv: kv[1]["bytes"] / max(kv[1]["calls"], 1))
         roof["eager_ms_per_launch"] = rec["ms"] / rec["calls"]
-    roof_bwd = dict(sr["bwd"], kernel="scan_bwd_kernel<float,float,12,8,N1> (same shape)", peak_source=peak_src)
+    roof_bwd = dict(sr["bwd"], kernel="scan_bwd_kernel<float,float,12,8,N1,softplus> (same shape)", peak_source=peak_src)
     try:   # DRAM traffic per launch from the committed ncu capture of the same kernels and shapes
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_traffic.json")) as f:
             tr = json.load(f)
         roof["traffic"], roof_bwd["traffic"] = tr.get("scan_fwd_L0"), tr.get("scan_bwd_L0")
-        roof["traffic_source"] = roof_bwd["traffic_source"] = "profiles/r01_traffic.json (ncu --set full)"
+        sr["ss2d"]["traffic"] = tr.get("ss2d_core_L0")
+        roof["traffic_source"] = roof_bwd["traffic_source"] = "profiles/r02_traffic.json (ncu --set full)"
     except (OSError, ValueError):
         tr = {}
     roof_pw = dict(sr["pointwise"], traffic=tr.get("pointwise_40_320_ln_L0"), kernel="bayes_weight_pack_kernel + bayes_pointwise_tc3_kernel<LN> (40 -> 320 ch, 240000 px, fp32 via 3xTF32)",
@@ -439,7 +454,9 @@ def main_ours(args):
             "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": img_host.numel() * 4,
                     "d2h_bytes_per_step": out_host[0].numel() * 4},
             "regions": {"timed": len(region_ms), "ms": region_ms, "reported": "median"},
-            "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_scan_bwd": roof_bwd, "roofline_pointwise": roof_pw, "kernels": shares, "job": job}
+            "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_scan_bwd": roof_bwd, "roofline_pointwise": roof_pw,
+            "roofline_ss2d": dict(sr["ss2d"], kernel="ss2d_tile_kernel<3> map + ss2d_carry_kernel + ss2d_tile_kernel<3> apply (B1, D40, 400x600, dt_rank 3, fp32)", peak_source=peak_src),
+            "kernels": shares, "job": job}
     if not args.no_reference_gpu:
         try:   # the reference's own GPU path on this box, after everything of ours has been measured
             import bench_configs as bc

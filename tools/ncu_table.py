@@ -12,7 +12,7 @@ COLS = [("gpu__time_duration.sum", "time us", 1e-3), ("dram__bytes_read.sum", "D
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %", 1),
         ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma pipe %", 1),
         ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu pipe %", 1),
-        ("sm__pipe_tensor_subunits_active.avg.pct_of_peak_sustained_active", "tensor pipe %", 1),
+        ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe %", 1),
         ("launch__registers_per_thread", "regs", 1), ("smsp__inst_executed.sum", "warp instr M", 1e-6)]
 
 
