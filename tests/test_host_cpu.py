@@ -356,3 +356,19 @@ def test_prior_state_side_dict_closes_the_resume_gap(bem):
     assert B.load_prior_state_dict(nb, side) == ["0"]
     assert torch.equal(b.prior_mu_weight, a.prior_mu_weight) and torch.equal(b.prior_rho_bias, a.prior_rho_bias) and b.step == 41
     assert torch.allclose(b.prior_sigma_bias, torch.log1p(torch.exp(a.prior_rho_bias)))
+
+
+def test_integration_stub_declares_the_whole_scan_struct(bem):
+    """the ctypes stub of INTEGRATION.md must end where include/bem_b200.h's struct ends (a short struct makes the
+    library read dt_rank / dt_weight from whatever follows it)"""
+    import ctypes
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"class BemScanFwdParams\(ctypes\.Structure\):.*?\n(?=assert lib|lib\.)", text, flags=re.S)
+    assert m, "INTEGRATION.md no longer contains the BemScanFwdParams stub"
+    ns = {"ctypes": ctypes}
+    exec(m.group(0), ns)
+    doc = ns["BemScanFwdParams"]
+    ours = bem._lib.BemScanFwdParams
+    assert [f[0] for f in doc._fields_] == [f[0] for f in ours._fields_]
+    assert ctypes.sizeof(doc) == ctypes.sizeof(ours)
+    assert f"bem_abi_version() == {bem._lib.ABI_VERSION}" in text
