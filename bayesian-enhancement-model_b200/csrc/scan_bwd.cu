@@ -263,6 +263,37 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                         lds_items<T, VT>(su + e0 + v * VT, uv);
                         lds_items<T, VT>(sd + e0 + v * VT, dl);
                         lds_items<T, VT>(sB + e0 + v * VT, Bv);
+                        if constexpr (kAcc && VT % 2 == 0) {
+                            // fp32: softplus, decay and b for two positions at a time on the packed fp32 pipe (scan_common.cuh;
+                            // bit-identical to the scalar forms); the recurrence stays scalar
+#pragma unroll
+                            for (int k = 0; k < VT; k += 2) {
+                                f32x2 x2 = add2(pk2(dl[k], dl[k + 1]), splat2(bias));
+                                if (softplus_on) {
+                                    float x0, x1;
+                                    upk2(x2, x0, x1);
+                                    x2 = softplus2(x0, x1);
+                                }
+                                float ee[2], bb[2], xx[2];
+                                upk2(decay_m1_2(mul2(x2, splat2(Av))), ee[0], ee[1]);
+                                upk2(mul2(mul2(x2, pk2(uv[k], uv[k + 1])), pk2(Bv[k], Bv[k + 1])), bb[0], bb[1]);
+                                upk2(x2, xx[0], xx[1]);
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {
+                                    const int i = v * VT + k + j;
+                                    if (PART && e0 + i >= len) {
+                                        ee[j] = 0.f;
+                                        bb[j] = 0.f;
+                                        xx[j] = 0.f;
+                                    }
+                                    dl[k + j] = xx[j];
+                                    a[i] = ee[j];
+                                    decay_step(ee[j], bb[j], P, Vv);
+                                    h[i] = Vv;
+                                    rp[i] = P;
+                                }
+                            }
+                        } else {
 #pragma unroll
                         for (int k = 0; k < VT; ++k) {
                             const int i = v * VT + k;
@@ -280,6 +311,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                             decay_step(ei, bi, P, Vv);
                             h[i] = Vv;   // local inclusive state
                             rp[i] = P;   // local inclusive decay (temporarily)
+                        }
                         }
                         // keep the activated delta (fp32 accuracy matters only for fp32 inputs) for the output pass:
                         // same lane, same addresses, so no cross-lane hazard
@@ -357,6 +389,53 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
 #pragma unroll
                             for (int k = 0; k < VT; ++k) cB[k] = cC[k] = 0.f;
                         }
+                        if constexpr (kAcc && VT % 2 == 0) {
+                            // fp32: the ~25 independent fp32 operations of a position, two positions per instruction. Same
+                            // operations and association as the scalar branch below.
+#pragma unroll
+                            for (int k = 0; k < VT; k += 2) {
+                                const int i = v * VT + k;
+                                const bool v0 = !(PART && e0 + i >= len), v1 = !(PART && e0 + i + 1 >= len);
+                                const f32x2 x2 = pk2(dl[k], dl[k + 1]);                       // activated delta (written back above)
+                                const f32x2 u2 = pk2(v0 ? uv[k] : 0.f, v1 ? uv[k + 1] : 0.f);
+                                const f32x2 dy2 = pk2(v0 ? dy[k] : 0.f, v1 ? dy[k + 1] : 0.f);
+                                const f32x2 B2 = pk2(v0 ? Bv[k] : 0.f, v1 ? Bv[k + 1] : 0.f);
+                                const f32x2 h2 = pk2(h[i], h[i + 1]);
+                                const f32x2 gt2 = fma2(pk2(rp[i], rp[i + 1]), splat2(rin_t), pk2(gl[i], gl[i + 1]));
+                                const f32x2 bi2 = mul2(mul2(x2, u2), B2);
+                                f32x2 tt2 = mul2(gt2, add2(h2, mul2(bi2, splat2(-1.f))));          // g_t * a_t * h_{t-1} = g_t * (h_t - b_t)
+                                if (PART) {
+                                    float t0, t1;
+                                    upk2(tt2, t0, t1);
+                                    tt2 = pk2(v0 ? t0 : 0.f, v1 ? t1 : 0.f);
+                                }
+                                const f32x2 gx2 = mul2(gt2, x2);
+                                const f32x2 du2 = fma2(gx2, B2, mul2(splat2(Dv), dy2));
+                                f32x2 ddl2 = fma2(mul2(gt2, u2), B2, mul2(splat2(Av), tt2));
+                                float xt0, xt1;
+                                upk2(mul2(x2, tt2), xt0, xt1);
+                                dA_acc += xt0;                                                  // dA_acc = fma(x, tt, dA_acc): product rounded first here
+                                dA_acc += xt1;
+                                const f32x2 cB2 = fma2(gx2, u2, pk2(cB[k], cB[k + 1]));
+                                const f32x2 cC2 = fma2(dy2, h2, pk2(cC[k], cC[k + 1]));
+                                upk2(cB2, cB[k], cB[k + 1]);
+                                upk2(cC2, cC[k], cC[k + 1]);
+                                float yu0, yu1;
+                                upk2(mul2(dy2, u2), yu0, yu1);
+                                dD_acc += yu0;
+                                dD_acc += yu1;
+                                if (softplus_on) ddl2 = mul2(ddl2, mul2(decay_m1_2(mul2(x2, splat2(-1.f))), splat2(-1.f)));   // sigmoid = -expm1(-x)
+                                float d0, d1;
+                                upk2(ddl2, d0, d1);
+                                if (!v0) d0 = 0.f;
+                                if (!v1) d1 = 0.f;
+                                dbias_acc += d0;
+                                dbias_acc += d1;
+                                ddv[k] = d0;
+                                ddv[k + 1] = d1;
+                                upk2(du2, duv[k], duv[k + 1]);
+                            }
+                        } else {
 #pragma unroll
                         for (int k = 0; k < VT; ++k) {
                             const int i = v * VT + k;
@@ -386,6 +465,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (N1 && sizeof(T) == 4) ? 2 : 1)
                             if (!valid) ddl = 0.f;
                             dbias_acc += ddl;
                             ddv[k] = ddl;
+                        }
                         }
                         sts_items<float, VT>(accB + v * VT, cB);
                         sts_items<float, VT>(accC + v * VT, cC);
