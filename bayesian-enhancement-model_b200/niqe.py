@@ -87,6 +87,13 @@ class NiqeScorer:
         self._win = np.asarray(z["gaussian_window"], np.float64)
         gam = np.arange(0.2, 10.001, 0.001)                                     # niqe.py:24
         self._gam = gam
+        # everything the fits need of the gamma function, tabulated once on the host over the 9801 candidate shapes (alpha is
+        # always one of them): r(gamma) of niqe.py:26, sqrt(G(1/a) / G(3/a)) of :36-37 and G(2/a) / G(1/a) of :58
+        lg = np.vectorize(math.lgamma)
+        g1, g2, g3 = lg(1.0 / gam), lg(2.0 / gam), lg(3.0 / gam)
+        self._r_gam = np.exp(2 * g2 - g1 - g3)
+        self._beta_scale = np.exp(0.5 * (g1 - g3))
+        self._mean_scale = np.exp(g2 - g1)
         self._dev = {}
         self._resize = {}
 
@@ -94,10 +101,8 @@ class NiqeScorer:
         c = self._dev.get(device)
         if c is None:
             t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=device)
-            gam = t(self._gam)
-            rg = 1.0 / gam
-            r_gam = torch.exp(2 * torch.lgamma(rg * 2) - torch.lgamma(rg) - torch.lgamma(rg * 3))   # niqe.py:26
-            c = dict(mu=t(self._mu), cov=t(self._cov), win=t(self._win).contiguous(), gam=gam, r_gam=r_gam.contiguous())
+            c = dict(mu=t(self._mu), cov=t(self._cov), win=t(self._win).contiguous(), gam=t(self._gam), r_gam=t(self._r_gam).contiguous(),
+                     beta_scale=t(self._beta_scale), mean_scale=t(self._mean_scale))
             self._dev[device] = c
         return c
 
@@ -126,9 +131,8 @@ class NiqeScorer:
         pick_hi = (rg[hi] - rn) ** 2 < (rg[lo] - rn) ** 2
         idx = torch.where(pick_hi, hi, lo)
         idx = torch.where(torch.isnan(rn), torch.zeros_like(idx), idx)
-        alpha = c["gam"][idx]
-        s = torch.exp(0.5 * (torch.lgamma(1 / alpha) - torch.lgamma(3 / alpha)))
-        return alpha, left * s, right * s
+        s = c["beta_scale"][idx]
+        return c["gam"][idx], left * s, right * s, c["mean_scale"][idx]
 
     def _features(self, img, c, bs):
         """img: (S, H, W) float32, H / W multiples of bs -> (S, blocks, 18) float64   (niqe.py:104-116, 41-60): the per-pixel
@@ -146,8 +150,7 @@ class NiqeScorer:
             _lib.check(lib.bem_niqe_mscn(_lib.ptr(img), _lib.ptr(c["win"]), _lib.ptr(nrm), S, H, W, st), "niqe_mscn")
             _lib.check(lib.bem_niqe_block_stats(_lib.ptr(nrm), _lib.ptr(mom), S, H, W, bs, st), "niqe_block_stats")
         _lib.profile.launches += 2
-        a, bl, br = self._aggd_from_moments(mom, float(bs * bs), c)          # (S, nb, 5) each
-        g21 = torch.exp(torch.lgamma(2 / a) - torch.lgamma(1 / a))
+        a, bl, br, g21 = self._aggd_from_moments(mom, float(bs * bs), c)     # (S, nb, 5) each
         feats = [a[..., 0], (bl[..., 0] + br[..., 0]) / 2]
         for k in range(1, 5):
             feats += [a[..., k], (br[..., k] - bl[..., k]) * g21[..., k], bl[..., k], br[..., k]]
