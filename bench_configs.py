@@ -469,17 +469,48 @@ def build_train_stack(dev):
     return Stack().to(dev)
 
 
+def build_reference_train_model(dev):
+    """The REAL configs[4] network: the reference's DecompDualBranchDDWavelet (model code from oracle/_ref, built exactly as
+    Options/DecompDualBranch2DDWavelet_4.yml:54-68) AFTER bem_b200.patch.install() — the reference's model and trainer-side code
+    unmodified, its selective scan / traversal operators replaced by this package's kernels (what INTEGRATION.md section 1 gives a user)."""
+    import bem_b200
+    R = _ref()
+    bem_b200.patch.install()
+    return R.train_model(True, device=str(dev))
+
+
 def run_train_config(args, rank, world, dev):
     import torch
     import torch.distributed as dist
     from bem_b200 import _lib
     torch.manual_seed(0)
-    net = build_train_stack(dev).train()
-    model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index]) if world > 1 else net
-    opt = torch.optim.Adam(net.parameters(), lr=2e-4)      # Options/DecompDualBranch2DDWavelet_4.yml: Adam
     Bp = 8
     g = torch.Generator(device="cpu").manual_seed(100 + rank)
-    host = [torch.randn(Bp, c, h, h, generator=g).pin_memory() for c, h, _ in TRAIN_LEVELS]
+    real = _ref().available()
+    if real:
+        net = build_reference_train_model(dev).train()
+        host = [torch.rand(Bp, 6, 128, 128, generator=g).pin_memory(), torch.rand(Bp, 3, 128, 128, generator=g).pin_memory()]
+
+        class Wrap(torch.nn.Module):       # loss inside the DDP-wrapped module's graph, as basicsr's trainer computes it after net_g(lq)
+            def __init__(self, m):
+                super().__init__()
+                self.m = m
+
+            def forward(self, xs):
+                return torch.nn.functional.l1_loss(self.m(xs[0])[-1], xs[1])    # train.pixel_opt: L1Loss (yml:100-103)
+        core = Wrap(net)
+        opt = torch.optim.AdamW([p for p in net.parameters() if p.requires_grad], lr=2e-4, weight_decay=1e-4, betas=(0.9, 0.999))   # yml:88-92
+        workload = ("BASELINE configs[4]: fwd + L1 loss + bwd + AdamW step of the reference's DecompDualBranchDDWavelet "
+                    "(Options/DecompDualBranch2DDWavelet_4.yml; model code unmodified from oracle/_ref, bem_b200.patch.install() applied: scan fwd/bwd and "
+                    "cross scan / merge on libbem_b200), 8 x 6 x 128 x 128 per rank, DDP gradient all-reduce over the ranks")
+    else:
+        net = build_train_stack(dev).train()
+        host = [torch.randn(Bp, c, h, h, generator=g).pin_memory() for c, h, _ in TRAIN_LEVELS]
+        core = net
+        opt = torch.optim.Adam(net.parameters(), lr=2e-4)
+        workload = ("BASELINE configs[4] (scan-carrying part; the reference model is not staged): fwd+bwd+Adam step of the 18 VSSBlocks of "
+                    "DecompDualBranch2DDWavelet_4 (8 @ 40ch 64x64, 8 @ 80ch 32x32, 2 @ 160ch 16x16; d_state 1), 8 patches of 128x128 per rank, DDP")
+    model = torch.nn.parallel.DistributedDataParallel(core, device_ids=[dev.index]) if world > 1 else core
     xs = [t.to(dev) for t in host]
 
     def step(inputs):
@@ -533,8 +564,7 @@ def run_train_config(args, rank, world, dev):
     line = {"metric": "train_patches_per_sec_128x128", "value": patches / (ms * 1e-3), "unit": "patches/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[4] (scan-carrying part): fwd+bwd+Adam step of the 18 VSSBlocks of DecompDualBranch2DDWavelet_4 "
-                                   "(8 @ 40ch 64x64, 8 @ 80ch 32x32, 2 @ 160ch 16x16; d_state 1), 8 patches of 128x128 per rank, DDP gradient all-reduce over the ranks",
+            "config": {"workload": workload,
                        "l2": "activations of a step (8 x 40 x 4096 x 4 B x ~30 tensors per block) exceed the L2 only at level 0; no flush inside a step",
                        "parallelism": f"ddp{world}", "loss_last": lv},
             "e2e": {"value": world * Bp * 1e3 / ms_e2e, "unit": "patches/s", "h2d_bytes_per_step": sum(t.numel() * 4 for t in host),
@@ -546,6 +576,34 @@ def run_train_config(args, rank, world, dev):
         line["reference_gpu"] = {"scan_fwd_B8_KD160_L4096_ms": time_graph_rotating(lambda i: rc[i][0], len(sets), dev)[1],
                                  "scan_bwd_B8_KD160_L4096_ms": time_graph_rotating(lambda i: rc[i][1], len(sets), dev)[1],
                                  "what": "selective_scan_cuda_oflex (reference, unmodified, sm_100a), same shape and protocol"}
+        if real:
+            try:   # the same training step on the UNPATCHED reference model (its CUDA extension + Triton traversal), this GPU, no DDP
+                import bem_b200
+                bem_b200.patch.uninstall()
+                torch.manual_seed(0)
+                ref_net = R.train_model(True, device=str(dev)).train()
+                ref_opt = torch.optim.AdamW([p for p in ref_net.parameters() if p.requires_grad], lr=2e-4, weight_decay=1e-4)
+
+                def ref_step():
+                    ref_opt.zero_grad(set_to_none=True)
+                    torch.nn.functional.l1_loss(ref_net(xs[0])[-1], xs[1]).backward()
+                    ref_opt.step()
+                for _ in range(3):
+                    ref_step()
+                torch.cuda.synchronize(dev)
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                r0.record()
+                nref = max(3, min(args.steps, 10))
+                for _ in range(nref):
+                    ref_step()
+                r1.record()
+                torch.cuda.synchronize(dev)
+                rms = r0.elapsed_time(r1) / nref
+                line["reference_gpu"]["train_step_ms"] = rms
+                line["reference_gpu"]["train_patches_per_s_one_gpu"] = Bp * 1e3 / rms
+                line["reference_gpu"]["train_what"] = "the same model, unpatched: reference CUDA extension (sm_100a) + Triton cross scan / merge, one GPU"
+            except Exception as ex:
+                line["reference_gpu"]["train_step_ms"] = f"failed: {type(ex).__name__}: {ex}"
     if not args.no_cpu_baseline and world == 1:
         try:
             r = cpu_reference_scan(Bp, 160, 4, 1, 4096, "f32", True)

@@ -225,3 +225,23 @@ def niqe_module():
         pkg.__path__ = [os.path.join(ROOT, "basicsr", "metrics")]
         sys.modules["basicsr.metrics"] = pkg
     return importlib.import_module("basicsr.metrics.niqe")
+
+
+def train_model(with_ext=True, device="cuda"):
+    """the reference's configs[4] network exactly as Options/DecompDualBranch2DDWavelet_4.yml:54-68 builds it
+    (basicsr/archs/DecompDualBranchDDWavelet_arch.py:147; its frozen decomposition net loads basicsr/QD/checkpoints/model4_999.pth
+    through a path relative to the reference root, :67, so the working directory is switched for the construction)"""
+    import torch
+    mod = arch("DecompDualBranchDDWavelet_arch", with_ext)
+    cwd = os.getcwd()
+    real_load = torch.load
+    os.chdir(ROOT)
+    torch.load = lambda f, *a, **k: real_load(f, *a, **{**k, "map_location": device})
+    try:
+        net = mod.DecompDualBranchDDWavelet(in_channels=6, out_channels=3, n_feat=40, d_state=[1, 1, 1], ssm_ratio=1, mlp_ratio=4,
+                                            mlp_type="gdmlp", use_pixelshuffle=True, drop_path=0.0, sam=False, stage=1,
+                                            num_blocks=[2, 2, 2], decomp_model="model4")
+    finally:
+        torch.load = real_load
+        os.chdir(cwd)
+    return net.to(device)

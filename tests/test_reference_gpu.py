@@ -383,3 +383,46 @@ def test_linear_reparameterization_on_the_pointwise_kernel_vs_reference(S):
         ours.set_mc_config(o, mc_samples=1)
     assert bem_b200._lib.profile.launches >= 2            # sample kernel(s) + the pointwise kernel
     assert nmax_err(y.reshape(S, 6, 10, 24).cpu().numpy(), torch.stack(outs).cpu().numpy()) < 1e-5
+
+
+def test_patch_install_on_the_reference_training_model_forward_and_backward():
+    """BASELINE configs[4]: the reference's own DecompDualBranchDDWavelet (Options/DecompDualBranch2DDWavelet_4.yml: 18 VSSBlocks,
+    d_state 1, frozen quaternion / wavelet decomposition in front), training mode, forward + L1 loss + backward on 2 x 6 x 64 x 64:
+    unpatched (reference CUDA extension + Triton traversal) vs after bem_b200.patch.install() (this package's scan forward /
+    backward and traversal kernels under the reference's autograd graph), same weights. Outputs and every parameter gradient."""
+    import bem_b200
+    torch.manual_seed(31)
+    net = R.train_model(True).train()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    x = torch.rand(2, 6, 64, 64, device="cuda")
+    tgt = torch.rand(2, 3, 64, 64, device="cuda")
+
+    def step(model):
+        model.zero_grad(set_to_none=True)
+        with torch.backends.cudnn.flags(allow_tf32=False):
+            out = model(x)[-1]
+            loss = torch.nn.functional.l1_loss(out, tgt)
+            loss.backward()
+        return out.detach(), {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        out_ref, g_ref = step(net)
+        bem_b200.patch.install()
+        try:
+            net2 = R.train_model(True).train()          # built after the patch: forward_core binds the patched forward_corev2
+            net2.load_state_dict(sd, strict=True)
+            bem_b200._lib.profile.reset()
+            out, g = step(net2)
+            launches = bem_b200._lib.profile.launches
+        finally:
+            bem_b200.patch.uninstall()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    assert launches >= 18 * 4          # per VSSBlock: cross_scan, scan fwd, cross_merge forward + scan bwd (+ traversal adjoints) backward
+    assert out.shape == out_ref.shape == (2, 3, 64, 64)
+    assert nmax_err(out.cpu().numpy(), out_ref.cpu().numpy()) < 1e-4
+    assert set(g) == set(g_ref) and len(g) > 300
+    worst = max((nmax_err(g[n].cpu().numpy(), g_ref[n].cpu().numpy()), n) for n in g if float(g_ref[n].abs().max()) > 0)
+    assert worst[0] < 2e-3, worst       # the reference extension is built with --use_fast_math and sums dB / dC with fp32 atomics
