@@ -475,7 +475,9 @@ def build_reference_train_model(dev):
     unmodified, its selective scan / traversal operators replaced by this package's kernels (what INTEGRATION.md section 1 gives a user)."""
     import bem_b200
     R = _ref()
-    bem_b200.patch.install()
+    R.arch("DecompDualBranchDDWavelet_arch", True)       # import the reference's modules first: install() patches what is loaded
+    patched = bem_b200.patch.install()
+    assert any(n.endswith("vmamba") for n in patched), patched
     return R.train_model(True, device=str(dev))
 
 
