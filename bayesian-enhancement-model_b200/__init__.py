@@ -7,6 +7,7 @@
     MC inference        bem_b200.mc.{MCSampler, mc_infer, select_best}; bem_b200.NiqeScorer (device-resident no-reference score)
     stage-1 network     bem_b200.network.{Network, build_model, build_bayesian_model}
     reference patching  bem_b200.patch.install(...) / uninstall()
+    training            bem_b200.GraphedTrainStep (forward + loss + backward + optimizer step as one CUDA-graph replay)
     after `.data` writes  bem_b200.invalidate_caches()  (derived-weight caches and captured graphs key on tensor versions,
                         which in-place writes through `.data` — e.g. an EMA update — do not advance)
 
@@ -15,7 +16,8 @@ raises ImportError — there is no fallback path.
 """
 from . import _lib  # noqa: F401  (loads libbem_b200.so, raises if it is missing)
 from ._lib import invalidate_caches  # noqa: F401
-from . import bayesian, mc, network, niqe, patch  # noqa: F401
+from . import bayesian, graphed, mc, network, niqe, patch  # noqa: F401
+from .graphed import GraphedTrainStep  # noqa: F401
 from .niqe import NiqeScorer  # noqa: F401
 from .csm import CrossMergeF, CrossScanF, cross_merge_fn, cross_scan_fn  # noqa: F401
 from .selective_scan import (SelectiveScanCuda, build_selective_scan_fn, chunk_len, selective_scan_cuda_oflex,  # noqa: F401

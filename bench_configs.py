@@ -501,7 +501,8 @@ def run_train_config(args, rank, world, dev):
             def forward(self, xs):
                 return torch.nn.functional.l1_loss(self.m(xs[0])[-1], xs[1])    # train.pixel_opt: L1Loss (yml:100-103)
         core = Wrap(net)
-        opt = torch.optim.AdamW([p for p in net.parameters() if p.requires_grad], lr=2e-4, weight_decay=1e-4, betas=(0.9, 0.999))   # yml:88-92
+        opt = torch.optim.AdamW([p for p in net.parameters() if p.requires_grad], lr=2e-4, weight_decay=1e-4, betas=(0.9, 0.999),
+                                capturable=True)   # yml:88-92
         workload = ("BASELINE configs[4]: fwd + L1 loss + bwd + AdamW step of the reference's DecompDualBranchDDWavelet "
                     "(Options/DecompDualBranch2DDWavelet_4.yml; model code unmodified from oracle/_ref, bem_b200.patch.install() applied: scan fwd/bwd and "
                     "cross scan / merge on libbem_b200), 8 x 6 x 128 x 128 per rank, DDP gradient all-reduce over the ranks")
@@ -509,7 +510,7 @@ def run_train_config(args, rank, world, dev):
         net = build_train_stack(dev).train()
         host = [torch.randn(Bp, c, h, h, generator=g).pin_memory() for c, h, _ in TRAIN_LEVELS]
         core = net
-        opt = torch.optim.Adam(net.parameters(), lr=2e-4)
+        opt = torch.optim.Adam(net.parameters(), lr=2e-4, capturable=True)
         workload = ("BASELINE configs[4] (scan-carrying part; the reference model is not staged): fwd+bwd+Adam step of the 18 VSSBlocks of "
                     "DecompDualBranch2DDWavelet_4 (8 @ 40ch 64x64, 8 @ 80ch 32x32, 2 @ 160ch 16x16; d_state 1), 8 patches of 128x128 per rank, DDP")
     model = torch.nn.parallel.DistributedDataParallel(core, device_ids=[dev.index]) if world > 1 else core
@@ -537,12 +538,33 @@ def run_train_config(args, rank, world, dev):
         step(xs)
     e1.record()
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms_eager = e0.elapsed_time(e1)
     launches = _lib.profile.launches
+    # the product's execution strategy for a training step: the whole step (forward, loss, backward, gradient all-reduce under DDP,
+    # optimizer) captured as one CUDA graph and replayed (bem_b200.GraphedTrainStep); the eager figure is kept beside it
+    graphed = None
+    try:
+        import bem_b200
+        gs = bem_b200.GraphedTrainStep(model, lambda m, *ins: m(list(ins)), opt, xs, warmup=11 if world > 1 else 3)
+        for _ in range(3):
+            gs(*xs)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            gs(*xs)
+        g1.record()
+        barrier()
+        graphed = g0.elapsed_time(g1)
+    except Exception as ex:
+        graph_error = f"{type(ex).__name__}: {ex}"
+        torch.cuda.synchronize()
+    ms = graphed if graphed is not None else ms_eager
+    run = (lambda ins: gs(*ins)) if graphed is not None else step
     t0 = time.perf_counter()
     n_e2e = max(3, min(args.steps, 10))
     for _ in range(n_e2e):
-        loss = step([t.to(dev, non_blocking=True) for t in host])
+        loss = run([t.to(dev, non_blocking=True) for t in host])
         lv = float(loss.item())
     barrier()
     ms_e2e = 1e3 * (time.perf_counter() - t0) / n_e2e
@@ -568,7 +590,10 @@ def run_train_config(args, rank, world, dev):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload,
                        "l2": "activations of a step (8 x 40 x 4096 x 4 B x ~30 tensors per block) exceed the L2 only at level 0; no flush inside a step",
-                       "parallelism": f"ddp{world}", "loss_last": lv},
+                       "parallelism": f"ddp{world}", "loss_last": lv,
+                       "execution": ("whole step replayed as one CUDA graph (bem_b200.GraphedTrainStep)" if graphed is not None
+                                     else "eager launches (graph capture failed: " + graph_error + ")"),
+                       "eager_ms_per_step": ms_eager / args.steps},
             "e2e": {"value": world * Bp * 1e3 / ms_e2e, "unit": "patches/s", "h2d_bytes_per_step": sum(t.numel() * 4 for t in host),
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "roofline": roof}
