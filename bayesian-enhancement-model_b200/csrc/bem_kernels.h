@@ -135,6 +135,10 @@ int ss2d_fused_dispatch(Ss2dFusedArgs a, void* workspace, cudaStream_t stream);
 int scan_fwd_dispatch(const ScanFwdArgs& a, int dtype, int out_dtype, int sm_count, cudaStream_t stream);
 int scan_fwd_deferred_dispatch(const ScanFwdArgs& a, int sm_count, cudaStream_t stream);   // fp32, N = 1: deferred-finish schedule
 int scan_bwd_dispatch(ScanBwdArgs& a, int dtype, int dout_dtype, int sm_count, cudaStream_t stream);
+// dstate >= 2: one CTA per channel row, chunks walked in order (scan_rows.cu)
+bool scan_rows_preferred(int batch, int dim, int N, int sm_count);
+int scan_rows_fwd_dispatch(const ScanFwdArgs& a, int dtype, int out_dtype, int sm_count, cudaStream_t stream);
+int scan_rows_bwd_dispatch(const ScanBwdArgs& a, int dtype, int dout_dtype, int sm_count, cudaStream_t stream);
 
 int bayes_pointwise_tc_launch(const BemBayesPointwiseParams& p, cudaStream_t stream);
 int64_t bayes_pointwise_tc_workspace(int n_samples, int cin, int cout);

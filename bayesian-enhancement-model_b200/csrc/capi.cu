@@ -70,7 +70,6 @@ int bem_scan_fwd(const BemScanFwdParams* q, void* stream_) {
     if (!q->u || !q->delta || !q->A || !q->B || !q->C || !q->out) return BEM_ERR_BAD_ARG;
     const int64_t need = bem_scan_workspace_bytes(q->batch, q->dim, q->seqlen, q->dstate, q->dtype);
     if (!q->workspace || q->workspace_bytes < need || (reinterpret_cast<uintptr_t>(q->workspace) & 15)) return BEM_ERR_WORKSPACE;
-    if (q->dstate > kMaxDstate) return BEM_ERR_UNSUPPORTED;
 
     const int CL = bem_scan_chunk_len(q->dtype);
     ScanFwdArgs a{};
@@ -106,7 +105,6 @@ int bem_scan_bwd(const BemScanBwdParams* q, void* stream_) {
     if (nchunks > 1 && !q->x) return BEM_ERR_BAD_ARG;   // selective_scan_oflex.cpp:315
     const int64_t need = bem_scan_workspace_bytes(q->batch, q->dim, q->seqlen, q->dstate, q->dtype);
     if (!q->workspace || q->workspace_bytes < need || (reinterpret_cast<uintptr_t>(q->workspace) & 15)) return BEM_ERR_WORKSPACE;
-    if (q->dstate > kMaxDstate) return BEM_ERR_UNSUPPORTED;
 
     ScanBwdArgs a{};
     a.u = q->u; a.delta = q->delta; a.Bm = q->B; a.Cm = q->C; a.A = q->A; a.D = q->D; a.bias = q->delta_bias;

@@ -779,6 +779,8 @@ static int launch_bwd_n(ScanBwdArgs& a, int sm_count, cudaStream_t stream) {
 }
 
 int scan_bwd_dispatch(ScanBwdArgs& a, int dtype, int dout_dtype, int sm_count, cudaStream_t stream) {
+    if (scan_rows_preferred(a.batch, a.dim, a.N, sm_count)) return scan_rows_bwd_dispatch(a, dtype, dout_dtype, sm_count, stream);
+    if (a.N > kMaxDstate) return BEM_ERR_UNSUPPORTED;
     if (dtype == BEM_F32) return launch_bwd_n<float, float, kItemsF32>(a, sm_count, stream);
     if (dtype == BEM_F16) {
         if (dout_dtype == BEM_F32) return launch_bwd_n<__half, float, kItems16>(a, sm_count, stream);

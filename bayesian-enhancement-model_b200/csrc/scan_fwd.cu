@@ -548,6 +548,8 @@ static int launch_fwd(ScanFwdArgs a, int sm_count, cudaStream_t stream) {
 
 int scan_fwd_dispatch(const ScanFwdArgs& a, int dtype, int out_dtype, int sm_count, cudaStream_t stream) {
     const bool n1 = a.N == 1;
+    if (a.R == 0 && scan_rows_preferred(a.batch, a.dim, a.N, sm_count)) return scan_rows_fwd_dispatch(a, dtype, out_dtype, sm_count, stream);
+    if (a.N > kMaxDstate) return BEM_ERR_UNSUPPORTED;
     if (dtype == BEM_F32) {
         if (n1) {
             // A/B and debugging knobs (tools/) select the classic schedule of this file

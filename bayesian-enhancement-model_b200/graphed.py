@@ -14,6 +14,33 @@ synchronisation inside the step (`.item()`, data-dependent control flow). The ea
 from __future__ import annotations
 
 import torch
+from torch.overrides import TorchFunctionMode
+
+
+class _DeviceIndexMode(TorchFunctionMode):
+    """`t[:, [0, 2, 4]]` builds its index tensor on the host and copies it to the device on every call, which a stream capture
+    refuses (the reference's decomposition front end does this: DecompDualBranchDDWavelet_arch.py:129-130). Under this mode a
+    Python-list index is replaced by a device tensor made once, during the eager warm-up, and reused by the capture."""
+
+    def __init__(self):
+        super().__init__()
+        self.cache = {}
+
+    def _dev(self, idx, device):
+        key = (tuple(idx), device)
+        if key not in self.cache:
+            self.cache[key] = torch.tensor(idx, dtype=torch.long, device=device)
+        return self.cache[key]
+
+    def __torch_function__(self, func, types, args=(), kwargs=None):
+        if func is torch.Tensor.__getitem__ and len(args) == 2 and isinstance(args[0], torch.Tensor) and args[0].is_cuda:
+            t, idx = args
+            flat = lambda i: isinstance(i, list) and len(i) > 0 and all(isinstance(v, int) for v in i)
+            if flat(idx):
+                args = (t, self._dev(idx, t.device))
+            elif isinstance(idx, tuple) and any(flat(i) for i in idx):
+                args = (t, tuple(self._dev(i, t.device) if flat(i) else i for i in idx))
+        return func(*args, **(kwargs or {}))
 
 
 class GraphedTrainStep:
@@ -24,13 +51,14 @@ class GraphedTrainStep:
         dev = self.static_in[0].device
         self.stream = torch.cuda.Stream(device=dev)
         self.stream.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(self.stream):          # warm-up on the capturing stream: allocator, workspaces, optimizer state
+        self._mode = _DeviceIndexMode()
+        with torch.cuda.stream(self.stream), self._mode:          # warm-up on the capturing stream: allocator, workspaces, optimizer state
             for _ in range(max(1, warmup)):
                 self._body()
         torch.cuda.current_stream(dev).wait_stream(self.stream)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, stream=self.stream):
+        with torch.cuda.graph(self.graph, stream=self.stream), self._mode:
             self.static_loss = self._body()
 
     def _body(self):

@@ -16,7 +16,6 @@ from . import _lib
 from ._lib import lib
 
 MAX_DSTATE = 256      # selective_scan_oflex.cpp:190
-BUILT_DSTATE = 16     # states staged per launch (csrc/bem_kernels.h kMaxDstate)
 
 
 def chunk_len(dtype: torch.dtype) -> int:
@@ -54,7 +53,6 @@ def _common_checks(u, delta, A, B, C, D_, delta_bias_):
             _check(t.dtype == torch.float32, f"{name} must be float32")
             _check(tuple(t.shape) == (dim,), f"{name} must have shape (dim,)")
             _check(t.stride(-1) == 1 or t.size(-1) == 1, f"{name} must be contiguous")
-    _check(dstate <= BUILT_DSTATE, f"bem_b200: dstate {dstate} > {BUILT_DSTATE} is not built (DESIGN.md, out of scope)")
     return batch, dim, seqlen, dstate, n_groups
 
 

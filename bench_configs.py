@@ -469,15 +469,16 @@ def build_train_stack(dev):
     return Stack().to(dev)
 
 
-def build_reference_train_model(dev):
+def build_reference_train_model(dev, patched=True):
     """The REAL configs[4] network: the reference's DecompDualBranchDDWavelet (model code from oracle/_ref, built exactly as
     Options/DecompDualBranch2DDWavelet_4.yml:54-68) AFTER bem_b200.patch.install() — the reference's model and trainer-side code
     unmodified, its selective scan / traversal operators replaced by this package's kernels (what INTEGRATION.md section 1 gives a user)."""
     import bem_b200
     R = _ref()
     R.arch("DecompDualBranchDDWavelet_arch", True)       # import the reference's modules first: install() patches what is loaded
-    patched = bem_b200.patch.install()
-    assert any(n.endswith("vmamba") for n in patched), patched
+    if patched:
+        done = bem_b200.patch.install()
+        assert any(n.endswith("vmamba") for n in done), done
     return R.train_model(True, device=str(dev))
 
 
@@ -558,6 +559,9 @@ def run_train_config(args, rank, world, dev):
         graphed = g0.elapsed_time(g1)
     except Exception as ex:
         graph_error = f"{type(ex).__name__}: {ex}"
+        if os.environ.get("BEM_BENCH_TRACE"):
+            import traceback
+            traceback.print_exc()
         torch.cuda.synchronize()
     ms = graphed if graphed is not None else ms_eager
     run = (lambda ins: gs(*ins)) if graphed is not None else step

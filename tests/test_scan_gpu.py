@@ -397,3 +397,54 @@ def test_full_size_hd_bf16_forward(cfg):
     assert err < 1e-4, err      # the inputs are bf16, the arithmetic is fp32: far inside the bf16 bar
     out_b = bem.selective_scan_fn(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["delta_bias"], True, False)
     assert out_b.dtype == torch.bfloat16 and nmax_err(out_b.float().cpu().numpy(), o["out"]) < LOW_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# row-sequential kernels for dstate >= 2 (scan_rows.cu). The dispatcher picks them when B * KD fills the machine; the env
+# knob forces them here so that the small shapes exercise every code path (partial chunks, misaligned rows, states per warp).
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L", [1, 37, 384, 385, 1000, 2049, 4096])
+@pytest.mark.parametrize("N,G", [(2, 1), (3, 1), (8, 2), (16, 4), (24, 2)])
+def test_row_kernels_fp32(monkeypatch, L, N, G):
+    monkeypatch.setenv("BEM_SCAN_ROWS", "1")
+    inp = make_inputs(2, 8, N, G, L, torch.float32, seed=L + N)
+    run_case(inp, True, FP32_TOL)
+
+
+@pytest.mark.parametrize("has_D,has_bias,softplus", [(False, False, False), (True, False, True), (False, True, True), (True, True, False)])
+def test_row_kernels_option_grid(monkeypatch, has_D, has_bias, softplus):
+    monkeypatch.setenv("BEM_SCAN_ROWS", "1")
+    inp = make_inputs(2, 12, 16, 2, 777, torch.float32, has_D=has_D, has_bias=has_bias, seed=9)
+    run_case(inp, softplus, FP32_TOL)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("L", [64, 513, 2048])
+@pytest.mark.parametrize("N", [2, 16])
+def test_row_kernels_low_precision(monkeypatch, dtype, L, N):
+    monkeypatch.setenv("BEM_SCAN_ROWS", "1")
+    inp = make_inputs(2, 8, N, 2, L, dtype, seed=3)
+    run_case(inp, True, LOW_TOL)
+
+
+def test_row_kernels_agree_with_the_look_back_kernels(monkeypatch):
+    """same inputs through both organisations (the dispatcher switches between them on the row count): outputs, carries and
+    gradients agree to rounding"""
+    bem = _bem()
+    inp = make_inputs(2, 16, 16, 4, 3000, torch.float32, seed=21)
+    res = {}
+    for rows in ("0", "1"):
+        monkeypatch.setenv("BEM_SCAN_ROWS", rows)
+        out, x = bem.selective_scan_cuda_oflex.fwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["delta_bias"], True, 1, True)
+        grads = bem.selective_scan_cuda_oflex.bwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["delta_bias"],
+                                                  inp["dout"], x, True, 1)
+        res[rows] = [out, x] + list(grads)
+    for a, b in zip(res["0"], res["1"]):
+        assert nmax_err(b.float().cpu().numpy(), a.double().cpu().numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("N", [32, 64, 256])
+def test_large_dstate_runs_on_the_row_kernels(N):
+    """dstate up to the reference's MAX_DSTATE 256 (selective_scan_oflex.cpp:190)"""
+    inp = make_inputs(1, 6, N, 1, 700, torch.float32, seed=N)
+    run_case(inp, True, FP32_TOL)
