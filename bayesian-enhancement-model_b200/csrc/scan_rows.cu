@@ -68,6 +68,23 @@ __device__ __forceinline__ void stage_full(T* dst, const T* src, int lane) {
 #pragma unroll
     for (int q = 0; q < NV; ++q) cp_async16(dst + (lane + 32 * q) * PER, src + (lane + 32 * q) * PER);
 }
+// Loads whose position in the instruction stream matters (issued a chunk ahead of their use): as volatile asm the compiler
+// cannot sink them down to the use to save registers.
+__device__ __forceinline__ float ldg_early(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_early(const __half* p) {
+    unsigned short v;
+    asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return __half2float(__ushort_as_half(v));
+}
+__device__ __forceinline__ float ldg_early(const __nv_bfloat16* p) {
+    unsigned short v;
+    asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return __bfloat162float(__ushort_as_bfloat16(v));
+}
 __device__ __forceinline__ bool aligned16(const void* p, int64_t stride_bytes) {
     return ((reinterpret_cast<uintptr_t>(p) | (uintptr_t)stride_bytes) & 15) == 0;
 }
@@ -124,8 +141,8 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 3) scan_rows_fwd_kernel(const
                 const int pos = tid + q * NT;
                 const int l = c * CL + pos;
                 const bool valid = pos < CL && l < p.L;
-                ru[q] = valid ? ElemTraits<T>::to_f(gu[l]) : 0.f;
-                rd[q] = valid ? ElemTraits<T>::to_f(gd[l]) : 0.f;
+                ru[q] = valid ? ldg_early(gu + l) : 0.f;
+                rd[q] = valid ? ldg_early(gd + l) : 0.f;
             }
         };
         auto prepass = [&](int c) {
@@ -300,7 +317,7 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 2) scan_rows_bwd_kernel(const
     const int N = p.N;
     const int Npad = (N + 3) & ~3;
     float* sR = sA + Npad;      // [N] adjoint entering the chunk from the right
-    float* sdA = sR + Npad;     // [N] dA of this row
+    float* sdA = sR + Npad;     // [N][32] dA of this row, one partial sum per lane of the owning warp (reduced once per row)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int SPW = (N + NW - 1) / NW;
@@ -316,8 +333,8 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 2) scan_rows_bwd_kernel(const
         for (int n = tid; n < N; n += NT) {
             sA[n] = p.A[(int64_t)d * p.A_ds + (int64_t)n * p.A_ns];
             sR[n] = 0.f;
-            sdA[n] = 0.f;
         }
+        for (int i = tid; i < N * 32; i += NT) sdA[i] = 0.f;
         const float Dv = p.D ? p.D[d] : 0.f, bias = p.bias ? p.bias[d] : 0.f;
         const T* gu = reinterpret_cast<const T*>(p.u) + b * p.u_bs + d * p.u_ds;
         const T* gd = reinterpret_cast<const T*>(p.delta) + b * p.dl_bs + d * p.dl_ds;
@@ -340,9 +357,9 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 2) scan_rows_bwd_kernel(const
                 const int pos = tid + q * NT;
                 const int l = c * CL + pos;
                 const bool valid = pos < CL && l < p.L;
-                ru[q] = valid ? ElemTraits<T>::to_f(gu[l]) : 0.f;
-                rd[q] = valid ? ElemTraits<T>::to_f(gd[l]) : 0.f;
-                ry[q] = valid ? ElemTraits<DT>::to_f(gdy[l]) : 0.f;
+                ru[q] = valid ? ldg_early(gu + l) : 0.f;
+                rd[q] = valid ? ldg_early(gd + l) : 0.f;
+                ry[q] = valid ? ldg_early(gdy + l) : 0.f;
             }
         };
         auto prepass = [&](int c) {
@@ -405,9 +422,10 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 2) scan_rows_bwd_kernel(const
         int it = 0;
         for (int c = nt - 1; c >= 0; --c) {
             const int l0 = c * CL, len = min(CL, p.L - l0);
-            float duA[ITEMS], ddA[ITEMS];
-#pragma unroll
-            for (int i = 0; i < ITEMS; ++i) duA[i] = ddA[i] = 0.f;
+            // du / ddelta summed over this warp's states accumulate in the warp's own rows of redU / redD (registers are what
+            // limits this kernel to two CTAs per SM)
+            float* accU = redU + warp * CL + e0;
+            float* accD = redD + warp * CL + e0;
             for (int j = 0; j < SPW; ++j, ++it) {
                 const int n = warp + NW * j;
                 cp_async_wait<1>();
@@ -417,56 +435,62 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 2) scan_rows_bwd_kernel(const
                     const T* sC = sB + CL;
                     const float An = sA[n];
                     const float h_in = sHin[warp * 2 + (it & 1)];
-                    float a[ITEMS], h[ITEMS], gl[ITEMS], rp[ITEMS];
+                    float a[ITEMS], h[ITEMS];
                     // forward states of the chunk from the carry of the forward pass
                     float P = 1.f, V = 0.f;
+                    {
+                        float rp[ITEMS];
 #pragma unroll
-                    for (int v = 0; v < ITEMS / VT; ++v) {
-                        float dl[VT], uv[VT], Bv[VT];
-                        lds_items<float, VT>(sdl + e0 + v * VT, dl);
-                        lds_items<float, VT>(su + e0 + v * VT, uv);
-                        lds_items<T, VT>(sB + e0 + v * VT, Bv);
-                        if constexpr (kAcc) {
+                        for (int v = 0; v < ITEMS / VT; ++v) {
+                            float dl[VT], uv[VT], Bv[VT];
+                            lds_items<float, VT>(sdl + e0 + v * VT, dl);
+                            lds_items<float, VT>(su + e0 + v * VT, uv);
+                            lds_items<T, VT>(sB + e0 + v * VT, Bv);
+                            if constexpr (kAcc) {
 #pragma unroll
-                            for (int k = 0; k < VT; k += 2) {
-                                const f32x2 x2 = pk2(dl[k], dl[k + 1]);
-                                float ee[2], bb[2];
-                                upk2(decay_m1_2(mul2(x2, splat2(An))), ee[0], ee[1]);
-                                upk2(mul2(mul2(x2, pk2(uv[k], uv[k + 1])), pk2(Bv[k], Bv[k + 1])), bb[0], bb[1]);
+                                for (int k = 0; k < VT; k += 2) {
+                                    const f32x2 x2 = pk2(dl[k], dl[k + 1]);
+                                    float ee[2], bb[2];
+                                    upk2(decay_m1_2(mul2(x2, splat2(An))), ee[0], ee[1]);
+                                    upk2(mul2(mul2(x2, pk2(uv[k], uv[k + 1])), pk2(Bv[k], Bv[k + 1])), bb[0], bb[1]);
 #pragma unroll
-                                for (int q = 0; q < 2; ++q) {
-                                    const int i = v * VT + k + q;
-                                    a[i] = ee[q];
-                                    decay_step(ee[q], bb[q], P, V);
+                                    for (int q = 0; q < 2; ++q) {
+                                        const int i = v * VT + k + q;
+                                        a[i] = ee[q];
+                                        decay_step(ee[q], bb[q], P, V);
+                                        h[i] = V;
+                                        rp[i] = P;
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < VT; ++k) {
+                                    const int i = v * VT + k;
+                                    const float ei = decay_m1<false>(dl[k] * An);
+                                    const float bi = dl[k] * uv[k] * Bv[k];
+                                    a[i] = ei;
+                                    decay_step(ei, bi, P, V);
                                     h[i] = V;
                                     rp[i] = P;
                                 }
                             }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < VT; ++k) {
-                                const int i = v * VT + k;
-                                const float ei = decay_m1<false>(dl[k] * An);
-                                const float bi = dl[k] * uv[k] * Bv[k];
-                                a[i] = ei;
-                                decay_step(ei, bi, P, V);
-                                h[i] = V;
-                                rp[i] = P;
-                            }
                         }
-                    }
-                    const float Pth = P;
-                    warp_scan_fwd(P, V, lane);
-                    float Pe = __shfl_up_sync(FULL, P, 1), Ve = __shfl_up_sync(FULL, V, 1);
-                    if (lane == 0) {
-                        Pe = 1.f;
-                        Ve = 0.f;
-                    }
-                    const float seed = fmaf(Pe, h_in, Ve);
+                        const float Pth0 = P;
+                        warp_scan_fwd(P, V, lane);
+                        float Pe = __shfl_up_sync(FULL, P, 1), Ve = __shfl_up_sync(FULL, V, 1);
+                        if (lane == 0) {
+                            Pe = 1.f;
+                            Ve = 0.f;
+                        }
+                        const float seed = fmaf(Pe, h_in, Ve);
 #pragma unroll
-                    for (int i = 0; i < ITEMS; ++i) h[i] = fmaf(rp[i], seed, h[i]);
-                    // reverse local scan of the adjoint g_t = C_t dout_t + a_{t+1} g_{t+1}
-                    float r = 0.f, RP = 1.f;
+                        for (int i = 0; i < ITEMS; ++i) h[i] = fmaf(rp[i], seed, h[i]);
+                        P = Pth0;   // product of this lane's decays
+                    }
+                    // adjoint g_t = C_t dout_t + a_{t+1} g_{t+1}. First the lane aggregate with zero incoming adjoint (the decay
+                    // product of the lane is P from above), then the warp scan, then the true adjoints together with the outputs:
+                    // nothing per position is kept between the two passes.
+                    float r = 0.f;
 #pragma unroll
                     for (int v = ITEMS / VT - 1; v >= 0; --v) {
                         float Cv[VT], dy[VT];
@@ -474,14 +498,11 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 2) scan_rows_bwd_kernel(const
                         lds_items<float, VT>(sdy + e0 + v * VT, dy);
 #pragma unroll
                         for (int k = VT - 1; k >= 0; --k) {
-                            const int i = v * VT + k;
-                            gl[i] = fmaf(Cv[k], dy[k], r);
-                            rp[i] = RP;
-                            r = fmaf(a[i], gl[i], gl[i]);
-                            RP = fmaf(a[i], RP, RP);
+                            const float gz = fmaf(Cv[k], dy[k], r);
+                            r = fmaf(a[v * VT + k], gz, gz);
                         }
                     }
-                    float Pr = Pth, Rr = r;
+                    float Pr = P, Rr = r;
                     warp_scan_rev(Pr, Rr, lane);
                     float Ps = __shfl_down_sync(FULL, Pr, 1), Rs = __shfl_down_sync(FULL, Rr, 1);
                     if (lane == 31) {
@@ -489,33 +510,44 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 2) scan_rows_bwd_kernel(const
                         Rs = 0.f;
                     }
                     const float r_in = sR[n];
-                    const float rin_t = fmaf(Ps, r_in, Rs);   // adjoint entering this lane's last position
                     const float Pa = __shfl_sync(FULL, Pr, 0), Ra = __shfl_sync(FULL, Rr, 0);
                     __syncwarp();
                     if (lane == 0) sR[n] = fmaf(Pa, r_in, Ra);
+                    r = fmaf(Ps, r_in, Rs);   // a_{t+1} g_{t+1} entering this lane's last position
                     float dA_acc = 0.f;
                     float* dBn = gdB + (int64_t)n * p.L + l0 + e0;
                     float* dCn = gdC + (int64_t)n * p.L + l0 + e0;
 #pragma unroll
-                    for (int v = 0; v < ITEMS / VT; ++v) {
-                        float dl[VT], uv[VT], Bv[VT], dy[VT], cB[VT], cC[VT];
+                    for (int v = ITEMS / VT - 1; v >= 0; --v) {
+                        float dl[VT], uv[VT], Bv[VT], dy[VT], Cv[VT], cB[VT], cC[VT], aU[VT], aD[VT];
                         lds_items<float, VT>(sdl + e0 + v * VT, dl);
                         lds_items<float, VT>(su + e0 + v * VT, uv);
                         lds_items<T, VT>(sB + e0 + v * VT, Bv);
+                        lds_items<T, VT>(sC + e0 + v * VT, Cv);
                         lds_items<float, VT>(sdy + e0 + v * VT, dy);
+                        if (j > 0) {
+                            lds_items<float, VT>(accU + v * VT, aU);
+                            lds_items<float, VT>(accD + v * VT, aD);
+                        } else {
 #pragma unroll
-                        for (int k = 0; k < VT; ++k) {
+                            for (int k = 0; k < VT; ++k) aU[k] = aD[k] = 0.f;
+                        }
+#pragma unroll
+                        for (int k = VT - 1; k >= 0; --k) {
                             const int i = v * VT + k;
-                            const float gt = fmaf(rp[i], rin_t, gl[i]);
+                            const float gt = fmaf(Cv[k], dy[k], r);
+                            r = fmaf(a[i], gt, gt);
                             const float bi = dl[k] * uv[k] * Bv[k];
                             const float tt = gt * (h[i] - bi);        // g_t a_t h_{t-1}
                             const float gx_ = gt * dl[k];
-                            duA[i] = fmaf(gx_, Bv[k], duA[i]);
-                            ddA[i] += fmaf(gt * uv[k], Bv[k], An * tt);
+                            aU[k] = fmaf(gx_, Bv[k], aU[k]);
+                            aD[k] += fmaf(gt * uv[k], Bv[k], An * tt);
                             dA_acc = fmaf(dl[k], tt, dA_acc);
                             cB[k] = gx_ * uv[k];
                             cC[k] = dy[k] * h[i];
                         }
+                        sts_items<float, VT>(accU + v * VT, aU);
+                        sts_items<float, VT>(accD + v * VT, aD);
                         if (vec_red && len == CL) {
 #pragma unroll
                             for (int k = 0; k < VT; k += 4) {
@@ -532,16 +564,10 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 2) scan_rows_bwd_kernel(const
                             }
                         }
                     }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) dA_acc += __shfl_xor_sync(FULL, dA_acc, o);
-                    if (lane == 0) sdA[n] += dA_acc;
+                    sdA[n * 32 + lane] += dA_acc;
                 }
                 __syncwarp();
                 issue();
-            }
-            if (warp < NWV) {
-                sts_items<float, ITEMS>(redU + warp * CL + e0, duA);
-                sts_items<float, ITEMS>(redD + warp * CL + e0, ddA);
             }
             __syncthreads();
 #pragma unroll
@@ -576,7 +602,12 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 2) scan_rows_bwd_kernel(const
             __syncthreads();
         }
         cp_async_wait<0>();
-        for (int n = tid; n < N; n += NT) atomicAdd(p.dA + (int64_t)d * N + n, sdA[n]);
+        for (int n = warp; n < N; n += NW) {   // warp w owns states w, w + NW, ...: its own partial sums, no barrier needed
+            float v = sdA[n * 32 + lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+            if (lane == 0) atomicAdd(p.dA + (int64_t)d * N + n, v);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             dD_acc += __shfl_xor_sync(FULL, dD_acc, o);
@@ -633,7 +664,7 @@ static int launch_rows_bwd(const ScanBwdArgs& a, int sm_count, cudaStream_t stre
     constexpr int CL = 32 * ITEMS, NW = kRowsWarps;
     auto kernel = scan_rows_bwd_kernel<T, DT, ITEMS>;
     const int Npad = (a.N + 3) & ~3;
-    const int smem_bytes = (3 + 2 * NW) * CL * 4 + NW * 4 * CL * (int)sizeof(T) + NW * 2 * 4 + 3 * Npad * 4 + 16;
+    const int smem_bytes = (3 + 2 * NW) * CL * 4 + NW * 4 * CL * (int)sizeof(T) + NW * 2 * 4 + 2 * Npad * 4 + a.N * 32 * 4 + 16;
     static int cache[64] = {0};
     if (int rc = set_smem(kernel, smem_bytes, cache)) return rc;
     const int64_t rows = (int64_t)a.batch * a.dim;
