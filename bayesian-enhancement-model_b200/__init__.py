@@ -16,7 +16,8 @@ raises ImportError — there is no fallback path.
 """
 from . import _lib  # noqa: F401  (loads libbem_b200.so, raises if it is missing)
 from ._lib import invalidate_caches  # noqa: F401
-from . import bayesian, graphed, mc, network, niqe, patch  # noqa: F401
+from . import bayesian, graphed, layernorm, mc, network, niqe, patch  # noqa: F401
+from .layernorm import layer_norm_2d  # noqa: F401
 from .graphed import GraphedTrainStep  # noqa: F401
 from .niqe import NiqeScorer  # noqa: F401
 from .csm import CrossMergeF, CrossScanF, cross_merge_fn, cross_scan_fn  # noqa: F401

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libbem_b200.so")
 
 BEM_F32, BEM_F16, BEM_BF16 = 0, 1, 2
 BEM_OK, BEM_ERR_BAD_ARG, BEM_ERR_WORKSPACE, BEM_ERR_UNSUPPORTED = 0, 10001, 10002, 10003
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 i32, i64, u64, vp = C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
 
@@ -95,6 +95,8 @@ SYMBOLS = {
     "bem_select_best": (C.c_int, [vp, i32, i32, vp, vp, vp]),
     "bem_niqe_mscn": (C.c_int, [vp, vp, vp, i32, i32, i32, vp]),
     "bem_niqe_block_stats": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
+    "bem_layernorm2d_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, C.c_int64, C.c_float, vp]),
+    "bem_layernorm2d_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, C.c_int64, vp]),
 }
 
 if not os.path.exists(LIB_PATH):

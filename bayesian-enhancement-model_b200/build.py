@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libbem_b200.so")
-SOURCES = ["capi.cu", "scan_fwd.cu", "scan_fwd_deferred.cu", "scan_bwd.cu", "scan_rows.cu", "ss2d_fused.cu", "csm.cu", "bayes.cu", "bayes_tc.cu", "select.cu", "niqe.cu"]
+SOURCES = ["capi.cu", "scan_fwd.cu", "scan_fwd_deferred.cu", "scan_bwd.cu", "scan_rows.cu", "ss2d_fused.cu", "csm.cu", "bayes.cu", "bayes_tc.cu", "select.cu", "niqe.cu", "ln2d.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"]
 

@@ -10,6 +10,8 @@ What gets replaced:
   * `csm_triton.cross_scan_fn` / `cross_merge_fn` and the names imported into vmamba.py (:22-25)
   * `SS2D.forward_corev2` (vmamba.py:547-698) by `ss2d.forward_corev2_patched` (one x_proj launch on the un-scanned x + the
     fused bem_ss2d_fwd call at inference; the reference op sequence on this package's kernels when a gradient is needed)
+  * `LayerNorm2d.forward` (vmamba.py:58-63) by the channel-first LayerNorm kernels, forward and backward (layernorm.py;
+    `install(layernorm=False)` leaves it alone)
   * the top-level `bayesian` package that basicsr/bayesian/tools.py:1 and the model wrappers import
 """
 from __future__ import annotations
@@ -43,8 +45,9 @@ def uninstall():
             setattr(obj, name, old)
 
 
-def install(vmamba=None, csms6s=None, csm_triton=None, replace_bayesian=True):
+def install(vmamba=None, csms6s=None, csm_triton=None, replace_bayesian=True, layernorm=True):
     from . import bayesian as _bayes
+    from .layernorm import layernorm2d_forward_patched
     from .csm import cross_merge_fn, cross_scan_fn
     from .selective_scan import SelectiveScanCuda, selective_scan_cuda_oflex, selective_scan_fn
     from .ss2d import forward_corev2_patched
@@ -73,6 +76,9 @@ def install(vmamba=None, csms6s=None, csm_triton=None, replace_bayesian=True):
                 cls = getattr(mod, cls_name, None)
                 if cls is not None and "forward_corev2" in vars(cls):
                     _set(cls, "forward_corev2", forward_corev2_patched)
+            ln = getattr(mod, "LayerNorm2d", None)
+            if layernorm and ln is not None and "forward" in vars(ln):
+                _set(ln, "forward", layernorm2d_forward_patched)
             patched.append(name)
 
     def set_module(name, value):

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define BEM_ABI_VERSION 13
+#define BEM_ABI_VERSION 14
 
 /* element types of u/delta/B/C/x-activations */
 enum { BEM_F32 = 0, BEM_F16 = 1, BEM_BF16 = 2 };
@@ -353,6 +353,19 @@ int bem_select_best(const float* scores, int32_t n, int32_t take_min, int32_t* o
  * ---------------------------------------------------------------------------------------------- */
 int bem_niqe_mscn(const float* img, const double* window7x7, double* out, int32_t n_images, int32_t H, int32_t W, void* stream);
 int bem_niqe_block_stats(const double* normalized, double* out, int32_t n_images, int32_t H, int32_t W, int32_t block, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm over the channels of a channel-first tensor, forward and backward (training path).
+ * Replaces LayerNorm2d.forward (basicsr/vmamba/models/vmamba.py:58-63: permute, F.layer_norm, permute) and its autograd.
+ *     x, y, dy, dx : (batch, channels, hw) fp32 contiguous;  weight, bias : (channels) fp32 or NULL (no affine)
+ *     mean, rstd   : (batch, hw) fp32, written by the forward for the backward; both NULL for an inference-only forward
+ *     dweight, dbias : (channels) fp32, ACCUMULATED with atomics (zero-fill before the call); NULL to skip; dx NULL to skip
+ * Statistics are the biased variance and rstd = rsqrt(var + eps) of torch.nn.functional.layer_norm.
+ * ---------------------------------------------------------------------------------------------- */
+int bem_layernorm2d_fwd(const float* x, const float* weight, const float* bias, float* y, float* mean, float* rstd,
+                        int32_t batch, int32_t channels, int64_t hw, float eps, void* stream);
+int bem_layernorm2d_bwd(const float* dy, const float* x, const float* weight, const float* mean, const float* rstd, float* dx,
+                        float* dweight, float* dbias, int32_t batch, int32_t channels, int64_t hw, void* stream);
 
 #ifdef __cplusplus
 }

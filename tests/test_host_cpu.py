@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(bem):
     exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
     assert declared <= exported, declared - exported
     assert declared == set(bem._lib.SYMBOLS.keys())
-    assert bem._lib.lib.bem_abi_version() == bem._lib.ABI_VERSION == 13
+    assert bem._lib.lib.bem_abi_version() == bem._lib.ABI_VERSION == 14
     assert b"workspace" in bem._lib.lib.bem_error_string(10002)
 
 
