@@ -47,7 +47,7 @@ class _LayerNorm2dFn(torch.autograd.Function):
                                            _lib.ptr(dwb[0]) if need_w else None, _lib.ptr(dwb[1]) if need_b else None,
                                            B, Cn, hw, _lib.stream_ptr(x.device))
         _lib.check(code, "layernorm2d_bwd")
-        _lib.profile.launches += int(need_x) + int(need_w or need_b)
+        _lib.profile.launches += 1 if Cn <= 160 else int(need_x) + int(need_w or need_b)   # one tiled kernel up to 160 channels
         return dx, (dwb[0] if need_w else None), (dwb[1] if need_b else None), None
 
 

@@ -13,7 +13,7 @@ def _ref(x, w, b, eps):
     return y.permute(0, 3, 1, 2)
 
 
-@pytest.mark.parametrize("shape", [(8, 40, 64, 64), (2, 80, 32, 32), (1, 160, 16, 16), (3, 7, 5, 9), (1, 3, 4, 4), (2, 40, 100, 150)])
+@pytest.mark.parametrize("shape", [(8, 40, 64, 64), (2, 80, 32, 32), (1, 160, 16, 16), (3, 7, 5, 9), (1, 3, 4, 4), (2, 40, 100, 150), (2, 200, 9, 11), (1, 161, 33, 3)])
 @pytest.mark.parametrize("affine", ["wb", "w", "none"])
 def test_layernorm2d_matches_torch_forward_and_backward(shape, affine):
     import bem_b200
