@@ -10,6 +10,10 @@ their stream from torch, so the whole step can be captured; the replay runs at t
 
 Constraints (torch's for any whole-network capture): static shapes; an optimizer constructed with `capturable=True`; no host
 synchronisation inside the step (`.item()`, data-dependent control flow). The eager step stays available as `step.eager(*inputs)`.
+Under DistributedDataParallel (torch's rules for capturing the NCCL all-reduce with the step): set
+TORCH_NCCL_ASYNC_ERROR_HANDLING=0 before init_process_group, construct the DDP wrapper inside `with torch.cuda.stream(side)` and
+pass the same `stream=side` here (the reducer records the stream it was built on; the legacy default stream cannot take part in
+a capture), and give it `warmup >= 11` iterations.
 """
 from __future__ import annotations
 
@@ -44,12 +48,12 @@ class _DeviceIndexMode(TorchFunctionMode):
 
 
 class GraphedTrainStep:
-    def __init__(self, model, loss_fn, optimizer, example_inputs, warmup: int = 3, max_grad_norm=None):
+    def __init__(self, model, loss_fn, optimizer, example_inputs, warmup: int = 3, max_grad_norm=None, stream=None):
         self.model, self.loss_fn, self.opt = model, loss_fn, optimizer
         self.max_grad_norm = max_grad_norm
         self.static_in = [t.clone() for t in example_inputs]
         dev = self.static_in[0].device
-        self.stream = torch.cuda.Stream(device=dev)
+        self.stream = stream if stream is not None else torch.cuda.Stream(device=dev)
         self.stream.wait_stream(torch.cuda.current_stream(dev))
         self._mode = _DeviceIndexMode()
         with torch.cuda.stream(self.stream), self._mode:          # warm-up on the capturing stream: allocator, workspaces, optimizer state

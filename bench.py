@@ -306,6 +306,7 @@ def main_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")    # a captured all-reduce (train config) cannot be watched from the host
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cudnn.allow_tf32 = False          # fp32 everywhere: the metric is quoted in the reference's precision
     torch.backends.cuda.matmul.allow_tf32 = False

@@ -514,7 +514,14 @@ def run_train_config(args, rank, world, dev):
         opt = torch.optim.Adam(net.parameters(), lr=2e-4, capturable=True)
         workload = ("BASELINE configs[4] (scan-carrying part; the reference model is not staged): fwd+bwd+Adam step of the 18 VSSBlocks of "
                     "DecompDualBranch2DDWavelet_4 (8 @ 40ch 64x64, 8 @ 80ch 32x32, 2 @ 160ch 16x16; d_state 1), 8 patches of 128x128 per rank, DDP")
-    model = torch.nn.parallel.DistributedDataParallel(core, device_ids=[dev.index]) if world > 1 else core
+    side = torch.cuda.Stream(device=dev)      # DDP is built on the stream the step is later captured on (bem_b200/graphed.py)
+    if world > 1:
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            model = torch.nn.parallel.DistributedDataParallel(core, device_ids=[dev.index])
+        torch.cuda.current_stream(dev).wait_stream(side)
+    else:
+        model = core
     xs = [t.to(dev) for t in host]
 
     def step(inputs):
@@ -546,7 +553,7 @@ def run_train_config(args, rank, world, dev):
     graphed = None
     try:
         import bem_b200
-        gs = bem_b200.GraphedTrainStep(model, lambda m, *ins: m(list(ins)), opt, xs, warmup=11 if world > 1 else 3)
+        gs = bem_b200.GraphedTrainStep(model, lambda m, *ins: m(list(ins)), opt, xs, warmup=11 if world > 1 else 3, stream=side)
         for _ in range(3):
             gs(*xs)
         barrier()
@@ -589,6 +596,14 @@ def run_train_config(args, rank, world, dev):
             "kernel": "scan bwd (B8 KD160 N1 L4096 fp32), level-0 scan of the train step", "peak_source": peak_src,
             "bytes_per_launch": float(bb), "ms_per_launch": bwd_ms, "fwd": {"ms": fwd_ms, "GBps": fb / fwd_ms / 1e6, "frac": fb / fwd_ms / 1e6 / peak}}
     patches = world * Bp * args.steps
+    # every rank trains on its own patches: after the timed steps the replicas hold the same parameters only if the gradient
+    # all-reduce really ran inside the (captured) step
+    in_sync = None
+    if world > 1:
+        chk = torch.stack([p.detach().double().sum() for p in core.parameters() if p.requires_grad]).sum().reshape(1)
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        in_sync = bool(all(torch.equal(allc[0], c) for c in allc))
     line = {"metric": "train_patches_per_sec_128x128", "value": patches / (ms * 1e-3), "unit": "patches/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -597,7 +612,7 @@ def run_train_config(args, rank, world, dev):
                        "parallelism": f"ddp{world}", "loss_last": lv,
                        "execution": ("whole step replayed as one CUDA graph (bem_b200.GraphedTrainStep)" if graphed is not None
                                      else "eager launches (graph capture failed: " + graph_error + ")"),
-                       "eager_ms_per_step": ms_eager / args.steps},
+                       "eager_ms_per_step": ms_eager / args.steps, "ddp_replicas_in_sync_after_run": in_sync},
             "e2e": {"value": world * Bp * 1e3 / ms_e2e, "unit": "patches/s", "h2d_bytes_per_step": sum(t.numel() * 4 for t in host),
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "roofline": roof}
