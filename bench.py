@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--config", default="mc", choices=["mc", "c1", "hd", "train"],
                     help="mc = BASELINE configs[1]/[2] (headline); c1 / hd / train = configs[0] / [3] / [4]")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference-on-GPU columns")
+    ap.add_argument("--graph-ddp", action="store_true",
+                    help="--config train on N > 1 GPUs: capture the DDP step (all-reduce included) as a CUDA graph; measured on 2 GPUs only, "
+                         "without it the multi-GPU train step is launched eagerly")
     ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds of host work of the --impl reference arm")
     return ap.parse_args()
 
@@ -306,7 +309,8 @@ def main_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")    # a captured all-reduce (train config) cannot be watched from the host
+        if args.config == "train" and args.graph_ddp:
+            os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")    # a captured all-reduce cannot be watched from the host
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cudnn.allow_tf32 = False          # fp32 everywhere: the metric is quoted in the reference's precision
     torch.backends.cuda.matmul.allow_tf32 = False

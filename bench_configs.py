@@ -551,9 +551,27 @@ def run_train_config(args, rank, world, dev):
     # the product's execution strategy for a training step: the whole step (forward, loss, backward, gradient all-reduce under DDP,
     # optimizer) captured as one CUDA graph and replayed (bem_b200.GraphedTrainStep); the eager figure is kept beside it
     graphed = None
-    try:
-        import bem_b200
-        gs = bem_b200.GraphedTrainStep(model, lambda m, *ins: m(list(ins)), opt, xs, warmup=11 if world > 1 else 3, stream=side)
+    graph_error = "capture under DDP is opt-in, --graph-ddp"
+    gs = None
+    if world == 1 or getattr(args, "graph_ddp", False):
+        try:
+            import bem_b200
+            gs = bem_b200.GraphedTrainStep(model, lambda m, *ins: m(list(ins)), opt, xs, warmup=11 if world > 1 else 3, stream=side)
+        except Exception as ex:
+            gs = None
+            graph_error = f"{type(ex).__name__}: {ex}"
+            if os.environ.get("BEM_BENCH_TRACE"):
+                import traceback
+                traceback.print_exc()
+            torch.cuda.synchronize()
+        if world > 1:      # every rank replays the graph or none does: a rank that fell back would issue different collectives
+            ok = torch.tensor([1 if gs is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                if gs is not None:
+                    graph_error = "capture failed on another rank"
+                gs = None
+    if gs is not None:
         for _ in range(3):
             gs(*xs)
         barrier()
@@ -564,12 +582,6 @@ def run_train_config(args, rank, world, dev):
         g1.record()
         barrier()
         graphed = g0.elapsed_time(g1)
-    except Exception as ex:
-        graph_error = f"{type(ex).__name__}: {ex}"
-        if os.environ.get("BEM_BENCH_TRACE"):
-            import traceback
-            traceback.print_exc()
-        torch.cuda.synchronize()
     ms = graphed if graphed is not None else ms_eager
     run = (lambda ins: gs(*ins)) if graphed is not None else step
     t0 = time.perf_counter()
@@ -583,6 +595,14 @@ def run_train_config(args, rank, world, dev):
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
+    # every rank trains on its own patches: after the timed steps the replicas hold the same parameters only if the gradient
+    # all-reduce really ran inside the (captured) step
+    in_sync = None
+    if world > 1:
+        chk = torch.stack([p.detach().double().sum() for p in core.parameters() if p.requires_grad]).sum().reshape(1)
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        in_sync = bool(all(torch.equal(allc[0], c) for c in allc))
     if rank != 0:
         return None
     peak, peak_src = _peaks()
@@ -596,14 +616,6 @@ def run_train_config(args, rank, world, dev):
             "kernel": "scan bwd (B8 KD160 N1 L4096 fp32), level-0 scan of the train step", "peak_source": peak_src,
             "bytes_per_launch": float(bb), "ms_per_launch": bwd_ms, "fwd": {"ms": fwd_ms, "GBps": fb / fwd_ms / 1e6, "frac": fb / fwd_ms / 1e6 / peak}}
     patches = world * Bp * args.steps
-    # every rank trains on its own patches: after the timed steps the replicas hold the same parameters only if the gradient
-    # all-reduce really ran inside the (captured) step
-    in_sync = None
-    if world > 1:
-        chk = torch.stack([p.detach().double().sum() for p in core.parameters() if p.requires_grad]).sum().reshape(1)
-        allc = [torch.zeros_like(chk) for _ in range(world)]
-        dist.all_gather(allc, chk)
-        in_sync = bool(all(torch.equal(allc[0], c) for c in allc))
     line = {"metric": "train_patches_per_sec_128x128", "value": patches / (ms * 1e-3), "unit": "patches/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -611,7 +623,7 @@ def run_train_config(args, rank, world, dev):
                        "l2": "activations of a step (8 x 40 x 4096 x 4 B x ~30 tensors per block) exceed the L2 only at level 0; no flush inside a step",
                        "parallelism": f"ddp{world}", "loss_last": lv,
                        "execution": ("whole step replayed as one CUDA graph (bem_b200.GraphedTrainStep)" if graphed is not None
-                                     else "eager launches (graph capture failed: " + graph_error + ")"),
+                                     else "eager launches (no graph: " + graph_error + ")"),
                        "eager_ms_per_step": ms_eager / args.steps, "ddp_replicas_in_sync_after_run": in_sync},
             "e2e": {"value": world * Bp * 1e3 / ms_e2e, "unit": "patches/s", "h2d_bytes_per_step": sum(t.numel() * 4 for t in host),
                     "d2h_bytes_per_step": 4},
