@@ -110,6 +110,19 @@ def test_pack_plan_matches_calls_by_position_and_signature(bem):
         assert plan._lookup(("a",)) == "ws_a"
 
 
+def test_training_helpers_refuse_the_cpu(bem):
+    """layer_norm_2d has no CPU path (RuntimeError like the other operators); the list-index mode of GraphedTrainStep leaves CPU
+    indexing alone"""
+    with pytest.raises(RuntimeError):
+        bem.layer_norm_2d(torch.randn(1, 4, 3, 3), torch.ones(4), torch.zeros(4))
+    assert not bem.layernorm.supported(torch.randn(1, 4, 3, 3))
+    from bem_b200.graphed import _DeviceIndexMode
+    t = torch.arange(24.0).view(2, 4, 3)
+    with _DeviceIndexMode() as mode:
+        got = t[:, [0, 2]]
+    assert torch.equal(got, t[:, [0, 2]]) and not mode.cache
+
+
 def test_no_cpu_fallback(bem):
     u = torch.randn(1, 4, 16)
     with pytest.raises(RuntimeError):
@@ -213,7 +226,7 @@ def test_patch_install_and_uninstall_on_the_staged_reference(bem):
     cs = sys.modules["basicsr.vmamba.models.csms6s"]
     ct = sys.modules["basicsr.vmamba.models.csm_triton"]
     before = (vm.selective_scan_fn, vm.cross_scan_fn, vm.cross_merge_fn, vm.SS2D.forward_corev2, cs.selective_scan_fn,
-              cs.SelectiveScanCuda, ct.cross_scan_fn, sys.modules["bayesian"])
+              cs.SelectiveScanCuda, ct.cross_scan_fn, sys.modules["bayesian"], vm.LayerNorm2d.forward)
     names = bem.patch.install()
     try:
         assert {"basicsr.vmamba.models.vmamba", "basicsr.vmamba.models.csms6s", "basicsr.vmamba.models.csm_triton", "bayesian"} <= set(names)
@@ -221,6 +234,12 @@ def test_patch_install_and_uninstall_on_the_staged_reference(bem):
         assert vm.cross_scan_fn is bem.cross_scan_fn and ct.cross_merge_fn is bem.cross_merge_fn
         assert cs.SelectiveScanCuda is bem.SelectiveScanCuda and cs.WITH_SELECTIVESCAN_OFLEX is True
         assert vm.SS2D.forward_corev2 is bem.ss2d.forward_corev2_patched
+        assert vm.LayerNorm2d.forward is bem.layernorm.layernorm2d_forward_patched
+        # tensors the kernels do not take (here: CPU) go through the reference's own permute / F.layer_norm / permute
+        ln = vm.LayerNorm2d(6)
+        xin = torch.randn(2, 6, 5, 4)
+        want = torch.nn.functional.layer_norm(xin.permute(0, 2, 3, 1), (6,), ln.weight, ln.bias, ln.eps).permute(0, 3, 1, 2)
+        assert torch.equal(ln(xin), want)
         assert sys.modules["bayesian"] is bem.bayesian
         # the reference's own model code, built AFTER the patch, is converted by this package's layers
         unet = R.unet_arch(False)
@@ -234,7 +253,7 @@ def test_patch_install_and_uninstall_on_the_staged_reference(bem):
     finally:
         bem.patch.uninstall()
     after = (vm.selective_scan_fn, vm.cross_scan_fn, vm.cross_merge_fn, vm.SS2D.forward_corev2, cs.selective_scan_fn,
-             cs.SelectiveScanCuda, ct.cross_scan_fn, sys.modules["bayesian"])
+             cs.SelectiveScanCuda, ct.cross_scan_fn, sys.modules["bayesian"], vm.LayerNorm2d.forward)
     assert all(a is b for a, b in zip(before, after)) and sys.modules["bayesian"] is refb
 
 
