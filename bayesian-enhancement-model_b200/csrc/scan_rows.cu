@@ -654,7 +654,8 @@ static int launch_rows_fwd(const ScanFwdArgs& a, int sm_count, cudaStream_t stre
     static int cache[64] = {0};
     if (int rc = set_smem(kernel, smem_bytes, cache)) return rc;
     const int64_t rows = (int64_t)a.batch * a.dim;
-    const int grid = (int)(rows < (int64_t)sm_count * 24 ? rows : (int64_t)sm_count * 24);
+    (void)sm_count;
+    const int grid = (int)(rows < 0x7fffffffLL ? rows : 0x7fffffffLL);   // one CTA per row; the row loop only matters beyond 2^31 rows
     launch_pdl(kernel, dim3(grid), dim3(NW * 32), smem_bytes, stream, a);
     return (int)cudaGetLastError();
 }
@@ -668,7 +669,8 @@ static int launch_rows_bwd(const ScanBwdArgs& a, int sm_count, cudaStream_t stre
     static int cache[64] = {0};
     if (int rc = set_smem(kernel, smem_bytes, cache)) return rc;
     const int64_t rows = (int64_t)a.batch * a.dim;
-    const int grid = (int)(rows < (int64_t)sm_count * 16 ? rows : (int64_t)sm_count * 16);
+    (void)sm_count;
+    const int grid = (int)(rows < 0x7fffffffLL ? rows : 0x7fffffffLL);   // one CTA per row
     launch_pdl(kernel, dim3(grid), dim3(NW * 32), smem_bytes, stream, a);
     return (int)cudaGetLastError();
 }
