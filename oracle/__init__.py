@@ -319,3 +319,30 @@ def select_best_oracle(scores, take_min=False):
         if s is v or s == v:
             return i
     return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# LayerNorm2d (basicsr/vmamba/models/vmamba.py:58-63: permute to channels-last, F.layer_norm over C, permute back) and its
+# gradients, fp64 numpy. Checker for csrc/ln2d.cu (tests only).
+# ---------------------------------------------------------------------------------------------------------------------
+def layernorm2d_oracle(x, weight=None, bias=None, eps=1e-5, dy=None):
+    """x: (B, C, *spatial). Returns {"y"} and, when dy is given, {"dx", "dweight", "dbias"} — the biased variance and
+    rstd = 1/sqrt(var + eps) of torch.nn.functional.layer_norm."""
+    x = np.asarray(x, dtype=np.float64)
+    C = x.shape[1]
+    shp = (1, C) + (1,) * (x.ndim - 2)
+    w = np.ones(C) if weight is None else np.asarray(weight, dtype=np.float64)
+    b = np.zeros(C) if bias is None else np.asarray(bias, dtype=np.float64)
+    mean = x.mean(axis=1, keepdims=True)
+    var = ((x - mean) ** 2).mean(axis=1, keepdims=True)
+    rstd = 1.0 / np.sqrt(var + eps)
+    xh = (x - mean) * rstd
+    out = {"y": xh * w.reshape(shp) + b.reshape(shp)}
+    if dy is not None:
+        g = np.asarray(dy, dtype=np.float64)
+        gw = g * w.reshape(shp)
+        out["dx"] = rstd * (gw - gw.mean(axis=1, keepdims=True) - xh * (gw * xh).mean(axis=1, keepdims=True))
+        red = (0,) + tuple(range(2, x.ndim))
+        out["dweight"] = (g * xh).sum(axis=red)
+        out["dbias"] = g.sum(axis=red)
+    return out

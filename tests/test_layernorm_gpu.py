@@ -3,6 +3,7 @@
 import pytest
 import torch
 
+import oracle
 from conftest import nmax_err
 
 pytestmark = pytest.mark.gpu
@@ -33,6 +34,11 @@ def test_layernorm2d_matches_torch_forward_and_backward(shape, affine):
     for got, want, name in zip(leaves, leaves64, ("dx", "dweight", "dbias")):
         if got is not None:
             assert nmax_err(got.grad.cpu().numpy(), want.grad.cpu().numpy()) < 1e-5, name
+    # ... and against the numpy restatement of the op (oracle.layernorm2d_oracle, itself pinned to torch on the CPU)
+    o = oracle.layernorm2d_oracle(x.cpu().numpy(), None if w is None else w.cpu().numpy(), None if b is None else b.cpu().numpy(), 1e-5,
+                                  dy.cpu().numpy())
+    assert nmax_err(y.detach().cpu().numpy(), o["y"]) < 1e-5
+    assert nmax_err(leaves[0].grad.cpu().numpy(), o["dx"]) < 1e-5
 
 
 def test_layernorm2d_inference_forward_saves_nothing_and_rejects_what_it_cannot_run():

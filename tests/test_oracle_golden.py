@@ -211,3 +211,24 @@ def test_traversal_aware_ss2d_equals_the_cross_scan_form(D, H, W, N, R):
                                       Dv.reshape(-1).astype(np.float32), None, dtb.reshape(-1).astype(np.float32), True)
     y = oracle.cross_merge_oracle(np.asarray(ys).reshape(1, K, D, L), H, W)
     assert nmax_err(np.asarray(y).reshape(D, H, W), a) < 2e-5
+
+
+def test_layernorm2d_oracle_is_the_reference_op_and_its_autograd():
+    """oracle.layernorm2d_oracle against the op LayerNorm2d wraps (vmamba.py:58-63), forward and autograd, on the CPU in fp64"""
+    import torch
+    g = torch.Generator().manual_seed(5)
+    for shape, affine in (((2, 7, 5, 3), True), ((1, 40, 4, 6), True), ((3, 5, 2, 2), False)):
+        x = torch.randn(*shape, generator=g, dtype=torch.float64, requires_grad=True)
+        C = shape[1]
+        w = (torch.rand(C, generator=g, dtype=torch.float64) + 0.5).requires_grad_() if affine else None
+        b = torch.randn(C, generator=g, dtype=torch.float64).requires_grad_() if affine else None
+        dy = torch.randn(*shape, generator=g, dtype=torch.float64)
+        y = torch.nn.functional.layer_norm(x.permute(0, 2, 3, 1), (C,), w, b, 1e-5).permute(0, 3, 1, 2)
+        y.backward(dy)
+        o = oracle.layernorm2d_oracle(x.detach().numpy(), None if w is None else w.detach().numpy(), None if b is None else b.detach().numpy(),
+                                      1e-5, dy.numpy())
+        assert np.allclose(o["y"], y.detach().numpy(), rtol=0, atol=1e-12)
+        assert np.allclose(o["dx"], x.grad.numpy(), rtol=0, atol=1e-11)
+        if affine:
+            assert np.allclose(o["dweight"], w.grad.numpy(), rtol=0, atol=1e-11)
+            assert np.allclose(o["dbias"], b.grad.numpy(), rtol=0, atol=1e-11)
