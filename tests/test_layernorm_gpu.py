@@ -104,6 +104,7 @@ def test_graphed_train_step_replays_the_eager_step():
         l_ref = loss_fn(ref, xi, ti)
         l_ref.backward()
         opt_ref.step()
-        assert abs(l_graph - float(l_ref)) < 1e-5 * max(1.0, abs(float(l_ref))), i
+        assert abs(l_graph - float(l_ref)) < 1e-4 * max(1.0, abs(float(l_ref))), i
     for (n, p), q in zip(net.named_parameters(), ref.parameters()):
-        assert nmax_err(p.detach().cpu().numpy(), q.detach().cpu().numpy()) < 1e-4, n
+        # Adam divides by sqrt(v): rounding-level differences of a near-zero gradient move such a parameter by up to lr per step
+        assert nmax_err(p.detach().cpu().numpy(), q.detach().cpu().numpy()) < 1e-3, n
