@@ -429,7 +429,7 @@ def test_row_kernels_low_precision(monkeypatch, dtype, L, N):
 
 def test_row_kernels_agree_with_the_look_back_kernels(monkeypatch):
     """same inputs through both organisations (the dispatcher switches between them on the row count): outputs, carries and
-    gradients agree to rounding"""
+    gradients agree within the fp32 tier"""
     bem = _bem()
     inp = make_inputs(2, 16, 16, 4, 3000, torch.float32, seed=21)
     res = {}
@@ -440,7 +440,7 @@ def test_row_kernels_agree_with_the_look_back_kernels(monkeypatch):
                                                   inp["dout"], x, True, 1)
         res[rows] = [out, x] + list(grads)
     for a, b in zip(res["0"], res["1"]):
-        assert nmax_err(b.float().cpu().numpy(), a.double().cpu().numpy()) < 2e-6
+        assert nmax_err(b.float().cpu().numpy(), a.double().cpu().numpy()) < FP32_TOL   # two fp32 association orders + atomics
 
 
 @pytest.mark.parametrize("N", [32, 64, 256])
