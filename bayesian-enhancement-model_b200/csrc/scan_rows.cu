@@ -115,7 +115,6 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 3) scan_rows_fwd_kernel(const
     const int SPW = (N + NW - 1) / NW;     // states per warp
     const int NWV = N < NW ? N : NW;       // warps that own at least one state
     const int nt = p.nxchunks;
-    const int nitems = nt * SPW;
     const int e0 = lane * ITEMS;
     const int64_t nrows = (int64_t)p.batch * p.dim;
 
@@ -323,7 +322,6 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 2) scan_rows_bwd_kernel(const
     const int SPW = (N + NW - 1) / NW;
     const int NWV = N < NW ? N : NW;
     const int nt = p.nchunks;
-    const int nitems = nt * SPW;
     const int e0 = lane * ITEMS;
     const int64_t nrows = (int64_t)p.batch * p.dim;
 
